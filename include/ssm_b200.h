@@ -1,0 +1,143 @@
+/* ssm_b200.h — C ABI of libssmb200.so: the B200-native (sm_100a) batched structured-QR hot path of
+ * SemiseparableMatrices.jl.  Plain pointers and sizes only; no torch / CUDA types in any signature.
+ *
+ * Each entry point names the reference interface it replaces (file:line in /root/reference/src).  The
+ * reference has no batch API — a batch is a Vector of its matrices — so every call takes `nb` systems of
+ * identical shape; nb = 1 is the single-matrix call the Julia method overrides make.
+ *
+ * Memory convention at the boundary ("reference layout", 8-byte aligned, per system, then batch-strided):
+ *   AlmostBanded   bands : (l+u+1) x n column-major band storage, A[k,j] at row u+1+k-j of column j
+ *                          (BandedMatrices `.data`; AlmostBandedMatrix.jl:7-11)
+ *                  U     : n x r column-major, V : r x n column-major  (`A.fill.args`, SemiseparableMatrices.jl:20-26)
+ *   BPS            B     : (l+m+1) x n band storage; U,V : n x r; W,S : n x p  (BandedPlusSemiseparableMatrix.jl:1-8)
+ *   vectors        b     : n doubles
+ *   system s of a batch starts at ptr + s*stride (stride in doubles; 0 selects the dense packing).
+ * Pointers may be HOST or DEVICE addresses; the library detects which (cudaPointerGetAttributes).  Host
+ * pointers are staged through pinned memory; the library never retains a caller pointer after return.
+ *
+ * Inside the library the operands live in a batch-interleaved, tile-blocked layout in HBM.
+ *
+ * Return value: 0 ok; < 0 argument / shape error (SSM_E_*; the Julia glue maps them to DimensionMismatch /
+ * ArgumentError as the reference throws at AlmostBandedMatrix.jl:14-16,310 and semiseparableqr.jl:46,105-107);
+ * > 0 CUDA runtime failure (cudaError_t).  ssm_last_error() returns the message of the calling thread's
+ * last failure.  No singularity checks are made — like the reference, Inf/NaN propagate.
+ *
+ * Threading: handles are not shared-state; calls on different ssm_ctx from different host threads are
+ * safe.  Every call enqueues on its ctx's stream and returns after the work is ENQUEUED unless it copies
+ * to a host pointer (then it synchronises); use ssm_ctx_sync() to wait.
+ */
+#ifndef SSM_B200_H
+#define SSM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSM_OK            0
+#define SSM_E_ARG        -1   /* null pointer / negative size                                           */
+#define SSM_E_SHAPE      -2   /* DimensionMismatch: operands of incompatible sizes                      */
+#define SSM_E_UNSUPPORTED -3  /* (l,u,r) outside the compiled limits (SSM_MAX_*)                        */
+#define SSM_E_STATE      -4   /* e.g. re-factorising an already factored object (semiseparableqr.jl:105) */
+#define SSM_E_NOMEM      -5
+
+#define SSM_MAX_BW   8        /* l, u (and BPS l, m) supported up to this by the generic kernels        */
+#define SSM_MAX_RANK 4        /* r, p                                                                   */
+
+#define SSM_DIST_DD 0         /* synthetic inputs, SURVEY 8(d): diagonally dominant band + small fill   */
+#define SSM_DIST_BC 1         /* boundary-row (spectral) form: U=[I_r;0]                                */
+
+typedef struct ssm_ctx   ssm_ctx;    /* device + stream + staging workspace                             */
+typedef struct ssm_ab    ssm_ab;     /* batch of AlmostBandedMatrix operands, device resident           */
+typedef struct ssm_abqr  ssm_abqr;   /* batch of QR{Float64,AlmostBandedMatrix} factorisations          */
+typedef struct ssm_bps   ssm_bps;    /* batch of BandedPlusSemiseparableMatrix operands                 */
+typedef struct ssm_bpsqr ssm_bpsqr;  /* batch of QR(BandedPlusSemiseparableMatrix, tau)                 */
+typedef struct ssm_vec   ssm_vec;    /* batch of length-n vectors (right-hand sides / solutions)        */
+
+/* ---- library / context ------------------------------------------------------------------------- */
+int         ssm_version(void);
+const char *ssm_last_error(void);
+int  ssm_ctx_create(int device, ssm_ctx **ctx);                 /* own non-blocking stream               */
+int  ssm_ctx_create_on_stream(int device, void *cuda_stream, ssm_ctx **ctx); /* caller's cudaStream_t   */
+int  ssm_ctx_destroy(ssm_ctx *ctx);
+int  ssm_ctx_sync(ssm_ctx *ctx);
+/* tuning knobs (kernel variant selection for A/B measurements): key in {"ab_variant","pipeline_stages"} */
+int  ssm_ctx_set_option(ssm_ctx *ctx, const char *key, int value);
+int  ssm_ctx_get_option(ssm_ctx *ctx, const char *key, int *value);
+/* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */
+int64_t ssm_ctx_launch_count(ssm_ctx *ctx);
+
+/* ---- vectors ------------------------------------------------------------------------------------ */
+int  ssm_vec_create(ssm_ctx *ctx, int n, int64_t nb, ssm_vec **v);
+int  ssm_vec_destroy(ssm_vec *v);
+int  ssm_vec_set(ssm_vec *v, const double *b, int64_t stride);  /* reference layout -> device layout     */
+int  ssm_vec_get(const ssm_vec *v, double *b, int64_t stride);  /* device layout -> reference layout     */
+int  ssm_vec_copy(ssm_vec *dst, const ssm_vec *src);
+int  ssm_vec_generate(ssm_vec *v, uint64_t seed, int array_id); /* b = 2u-1 of the shared generator      */
+
+/* ---- AlmostBandedMatrix (src/AlmostBandedMatrix.jl) ------------------------------------------------ */
+/* AlmostBandedMatrix(bands, fill) constructor + size check (:7-18): allocates the device batch          */
+int  ssm_ab_create(ssm_ctx *ctx, int n, int l, int u, int r, int64_t nb, ssm_ab **A);
+int  ssm_ab_destroy(ssm_ab *A);
+int  ssm_ab_set(ssm_ab *A, const double *bands, int64_t bands_stride, const double *U, int64_t U_stride,
+                const double *V, int64_t V_stride);
+int  ssm_ab_get(const ssm_ab *A, double *bands, int64_t bands_stride, double *U, int64_t U_stride,
+                double *V, int64_t V_stride);
+int  ssm_ab_generate(ssm_ab *A, uint64_t seed, int dist);       /* device-side synthetic operands        */
+
+/* qr(A) / factorize(A): _qr -> almostbanded_qr -> widen (:30-38) + _almostbanded_qr! (:125-179).
+ * A is not mutated (test_almostbanded.jl:146).  *F must be NULL (a new factor object is returned) or an
+ * existing factor object of the same shape, which is overwritten (steady-state refactorisation).        */
+int  ssm_ab_qr(const ssm_ab *A, ssm_abqr **F);
+int  ssm_abqr_destroy(ssm_abqr *F);
+/* F.factors (widened band storage (2l+u+1) x n), F.factors.fill U (n x r), F.tau (n) (:174-185)           */
+int  ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t f_stride, double *U, int64_t U_stride,
+                  double *tau, int64_t tau_stride);
+/* ldiv!(F, b) (:187-192): b <- R \ (Q'b), in place                                                        */
+int  ssm_abqr_ldiv(const ssm_abqr *F, ssm_vec *b);
+/* F \ b = ldiv!(F, copy(b)): x <- R \ (Q'b), b untouched (x may alias b)                                   */
+int  ssm_abqr_solve(const ssm_abqr *F, const ssm_vec *b, ssm_vec *x);
+/* lmul!(F.Q', b) / lmul!(F.Q, b), Q = QRPackedQ(bandpart(F.factors), F.tau) (:181,201-207)                */
+int  ssm_abqr_lmul_qt(const ssm_abqr *F, ssm_vec *b);
+int  ssm_abqr_lmul_q(const ssm_abqr *F, ssm_vec *b);
+/* ldiv!(UpperTriangular(F.R), b): _almostbanded_upper_ldiv! (:215-248)                                    */
+int  ssm_abqr_upper_ldiv(const ssm_abqr *F, ssm_vec *b);
+/* A \ b (:125 _factorize = qr, then ldiv!): fused factor + solve, x <- A \ b (x may alias b); the factors
+ * are not kept (R still round-trips HBM in a scratch buffer owned by A).                                 */
+int  ssm_ab_solve(const ssm_ab *A, const ssm_vec *b, ssm_vec *x);
+/* Triangular solves on an unfactored AlmostBandedMatrix (:242-270): upper!=0 -> (Unit)UpperTriangular(A)\b */
+int  ssm_ab_tri_ldiv(const ssm_ab *A, ssm_vec *b, int upper, int unit);
+/* relres[s] = ||b - A x||_2 / ||b||_2 via getindex semantics (:84-90), one value per system               */
+int  ssm_ab_residual(const ssm_ab *A, const ssm_vec *x, const ssm_vec *b, double *relres);
+/* One-shot HOST-buffer path (end-to-end): H2D + pack + qr + ldiv! + D2H, chunk-pipelined over streams.    */
+int  ssm_ab_solve_host(ssm_ctx *ctx, int n, int l, int u, int r, int64_t nb, const double *bands,
+                       const double *U, const double *V, const double *b, double *x);
+
+/* ---- BandedPlusSemiseparableMatrix (src/BandedPlusSemiseparableMatrix.jl, src/semiseparableqr.jl) -- */
+/* BandedPlusSemiseparableMatrix(B,(U,V),(W,S)) + size check (BandedPlusSemiseparableMatrix.jl:10-16)      */
+int  ssm_bps_create(ssm_ctx *ctx, int n, int l, int m, int r, int p, int64_t nb, ssm_bps **A);
+int  ssm_bps_destroy(ssm_bps *A);
+int  ssm_bps_set(ssm_bps *A, const double *B, int64_t B_stride, const double *U, const double *V,
+                 int64_t UV_stride, const double *W, const double *S, int64_t WS_stride);
+int  ssm_bps_generate(ssm_bps *A, uint64_t seed);
+/* qr(A) (semiseparableqr.jl:104-152): returns QR(BandedPlusSemiseparableMatrix(F.factors), tau)           */
+int  ssm_bps_qr(const ssm_bps *A, ssm_bpsqr **F);
+int  ssm_bpsqr_destroy(ssm_bpsqr *F);
+/* F.factors = BPS(B (l, l+m), (U, Vnew), (W [alpha beta], S [S AtU])) and tau                              */
+int  ssm_bpsqr_get(const ssm_bpsqr *F, double *B, int64_t B_stride, double *U, double *V, int64_t UV_stride,
+                   double *W, double *S, int64_t WS_stride, double *tau, int64_t tau_stride);
+/* lmul!(F.Q', b) (semiseparableqr.jl:863-905)                                                              */
+int  ssm_bpsqr_lmul_qt(const ssm_bpsqr *F, ssm_vec *b);
+/* ldiv!(UpperTriangular(F.factors), b) (BandedPlusSemiseparableMatrix.jl:53-70)                            */
+int  ssm_bpsqr_upper_ldiv(const ssm_bpsqr *F, ssm_vec *b);
+/* F \ b = ldiv!(F.R, lmul!(F.Q', b)) (the two halves test_qr.jl:47-53 exercises)                           */
+int  ssm_bpsqr_ldiv(const ssm_bpsqr *F, ssm_vec *b);
+/* A * x (BandedPlusSemiseparableMatrix.jl:21-41) and the residual built on it                              */
+int  ssm_bps_mul(const ssm_bps *A, const ssm_vec *x, ssm_vec *y);
+int  ssm_bps_residual(const ssm_bps *A, const ssm_vec *x, const ssm_vec *b, double *relres);
+/* ldiv!(UpperTriangular(A), b) on an unfactored BPS (test_bandedplussemiseparable.jl:17)                   */
+int  ssm_bps_upper_ldiv(const ssm_bps *A, ssm_vec *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSM_B200_H */

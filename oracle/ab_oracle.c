@@ -209,17 +209,15 @@ static void ab_upper_ldiv(const ab_t *R, double *b, int unit) {
         if (jr2_beg < n) {                                          /* :229 (sic: '<') */
             for (int j = jr2_beg; j <= jr2_end && j <= n; ++j)      /* buffer += V[:,jr2]*b[jr2] :230 */
                 for (int q = 1; q <= r; ++q) buffer[q - 1] += Vget(R, q, j) * b[j - 1];
-            for (int i = kr_beg; i <= k; ++i) {                     /* b[kr] -= U[kr,:]*buffer   :231 */
-                double s = 0.0;
-                for (int q = 1; q <= r; ++q) s += Uget(R, i, q) * buffer[q - 1];
-                b[i - 1] -= s;
+            for (int q = 1; q <= r; ++q) {                          /* b[kr] -= U[kr,:]*buffer   :231 */
+                double ax = -1.0 * buffer[q - 1];                   /* (ArrayLayouts column-major matvec: */
+                for (int i = kr_beg; i <= k; ++i) b[i - 1] += ax * Uget(R, i, q); /* y += (alpha x_j) A[:,j]) */
             }
         }
         if (jr1_beg < n) {                                          /* b[kr] -= R[kr,jr1]*b[jr1] :233-235 */
-            for (int i = kr_beg; i <= k; ++i) {
-                double s = 0.0;
-                for (int j = jr1_beg; j <= jr1_end && j <= n; ++j) s += ab_getindex(R, i, j) * b[j - 1];
-                b[i - 1] -= s;
+            for (int j = jr1_beg; j <= jr1_end && j <= n; ++j) {
+                double ax = -1.0 * b[j - 1];
+                for (int i = kr_beg; i <= k; ++i) b[i - 1] += ax * ab_getindex(R, i, j);
             }
         }
         for (int i = k; i >= kr_beg; --i) {                         /* Tri(B[kr,kr]) \ b[kr]     :236 */

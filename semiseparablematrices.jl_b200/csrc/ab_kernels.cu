@@ -1,0 +1,297 @@
+// ab_kernels.cu — sm_100a kernels of the AlmostBanded hot path (K1 ab_qr, K2 ab_qt, K3 ab_backsolve) and their
+// dispatch.  One lane per system, one warp (= one CTA) per tile of 32 systems; the n axis is swept sequentially
+// with the Householder window held in registers (ab_core.cuh) and the record streams pulled either by direct
+// loads or by the bulk-async (TMA) shared-memory ring (stream_loader.cuh).
+//
+// Replaces: _almostbanded_qr! (AlmostBandedMatrix.jl:135-172) incl. the widening copy (:30-38),
+//           lmul!(Q',b) (:181,189), _almostbanded_upper_ldiv! (:215-240).
+#include "ab_core.cuh"
+#include "ab_generic.cuh"
+#include "ssm_internal.cuh"
+#include "stream_loader.cuh"
+
+namespace ssm {
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: QR sweep.  RHS: also carry b through the reflectors (fused Q'b, used by A\b).  STOREQ: keep reflectors.
+// ---------------------------------------------------------------------------------------------------------
+template <int L, int U, int R, bool RHS, bool STOREQ, template <int, int, int, int> class Loader>
+__global__ void __launch_bounds__(32) ab_qr_kernel(const AbArgs a, const int nstage) {
+    using D = AbDims<L, U, R>;
+    constexpr int P = D::P, UB = D::UB, NFA = D::NFA, NFR = D::NFR, NFQ = D::NFQ;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int64_t tile = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int n = a.n;
+    const double *au = a.AU + tile * a.np * NFA * 32 + lane;
+    const double *vv = a.V + tile * a.np * (R > 0 ? R : 1) * 32 + lane;
+    double *rhs = RHS ? a.rhs + tile * a.np * 32 + lane : nullptr;
+    const double *rin = RHS ? a.rhs_in + tile * a.np * 32 + lane : nullptr;
+    double *ru = a.RU + tile * a.np * NFR * 32 + lane;
+    double *qt = STOREQ ? a.QT + tile * a.np * NFQ * 32 + lane : nullptr;
+
+    AbState<L, U, R> st;
+    ab_prologue<L, U, R, RHS>(
+        st, [&](int rho, int f) { return __ldg(au + (rho * NFA + f) * 32); },
+        [&](int c, int q) { return __ldg(vv + (c * R + q) * 32); }, [&](int rho) { return rin[rho * 32]; });
+
+    const int64_t nsteps = ((n + P - 1) / P) * P;
+    Loader<NFA, R, RHS ? 1 : 0, +1> ld;
+    ld.init(au + (int64_t)L * NFA * 32, vv + (int64_t)(UB + 1) * R * 32, RHS ? rin + L * 32 : nullptr, smem, nstage, nsteps);
+
+    for (int kb = 0; kb < n; kb += P) {
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) {
+            const int k = kb + ph;
+            double rec[NFA], vc[R > 0 ? R : 1], bb[1];
+            ld.acquire(k, rec, vc, bb);
+            double out_r[NFR], out_q[NFQ], out_c;
+            ab_step<L, U, R, RHS>(st, ph, rec, vc, bb[0], k < n - 1, out_r, out_q, out_c);
+            if (k < n) {
+#pragma unroll
+                for (int f = 0; f < NFR; ++f) ru[((int64_t)k * NFR + f) * 32] = out_r[f];
+                if (STOREQ) {
+#pragma unroll
+                    for (int f = 0; f < NFQ; ++f) qt[((int64_t)k * NFQ + f) * 32] = out_q[f];
+                }
+                if (RHS) rhs[(int64_t)k * 32] = out_c;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: b <- Q'b from stored reflectors.
+// ---------------------------------------------------------------------------------------------------------
+template <int L, template <int, int, int, int> class Loader>
+__global__ void __launch_bounds__(32) ab_qt_kernel(const AbSolveArgs a, const int nstage) {
+    constexpr int P = L + 1, NFQ = L + 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int64_t tile = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int n = a.n;
+    const double *qt = a.QT + tile * a.np * NFQ * 32 + lane;
+    double *rhs = a.rhs + tile * a.np * 32 + lane;
+    const double *rin = a.rhs_in + tile * a.np * 32 + lane;
+    QtState<L> st;
+    qt_prologue<L>(st, [&](int rho) { return rin[rho * 32]; });
+    const int64_t nsteps = ((n + P - 1) / P) * P;
+    Loader<NFQ, 1, 0, +1> ld;
+    ld.init(qt, rin + L * 32, nullptr, smem, nstage, nsteps);
+    for (int kb = 0; kb < n; kb += P) {
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) {
+            const int k = kb + ph;
+            double q[NFQ], bb[1], dummy[1];
+            ld.acquire(k, q, bb, dummy);
+            const double c = qt_step<L>(st, ph, q, bb[0]);
+            if (k < n) rhs[(int64_t)k * 32] = c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: x <- R \ c, rows n-1 .. 0.
+// ---------------------------------------------------------------------------------------------------------
+template <int L, int U, int R, template <int, int, int, int> class Loader>
+__global__ void __launch_bounds__(32) ab_backsolve_kernel(const AbSolveArgs a, const int nstage) {
+    using D = AbDims<L, U, R>;
+    constexpr int UB = D::UB, PX = UB + 1, NFR = D::NFR;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int64_t tile = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int n = a.n;
+    const double *ru = a.RU + tile * a.np * NFR * 32 + lane;
+    const double *vv = a.V + tile * a.np * (R > 0 ? R : 1) * 32 + lane;
+    double *rhs = a.rhs + tile * a.np * 32 + lane;
+    const double *rin = a.rhs_in + tile * a.np * 32 + lane;
+    BsState<UB, R> st;
+    bs_init<UB, R>(st);
+    const int nblk = (n + PX - 1) / PX;
+    const int itop = nblk * PX - 1;                 // first (padded) row visited; rows >= n are skipped
+    const int64_t nsteps = (int64_t)nblk * PX;
+    Loader<NFR, R, 1, -1> ld;
+    ld.init(ru + (int64_t)itop * NFR * 32, vv + (int64_t)(itop + UB + 1) * R * 32, rin + (int64_t)itop * 32, smem, nstage, nsteps);
+    const bool unit = a.unit != 0;
+    int64_t g = 0;
+    for (int ib = (nblk - 1) * PX; ib >= 0; ib -= PX) {
+#pragma unroll
+        for (int ph = PX - 1; ph >= 0; --ph) {
+            const int i = ib + ph;
+            double r[NFR], vc[R > 0 ? R : 1], cc[1];
+            ld.acquire(g++, r, vc, cc);
+            if (i < n) {
+                const double x = bs_step<UB, R>(st, ph, r, vc, cc[0], unit);
+                rhs[(int64_t)i * 32] = x;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generic (runtime l,u,r) kernels — any shape within SSM_MAX_*; also Q*b and the operand-level triangular solves
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) ab_qr_generic_kernel(const AbArgs a, int l, int u, int r, int with_rhs, int store_q) {
+    generic_ab_qr(a, l, u, r, with_rhs != 0, store_q != 0, (int64_t)blockIdx.x, (int)threadIdx.x);
+}
+__global__ void __launch_bounds__(32) ab_qt_generic_kernel(const AbSolveArgs a, int l, int transpose) {
+    generic_ab_qt(a, l, transpose != 0, (int64_t)blockIdx.x, (int)threadIdx.x);
+}
+__global__ void __launch_bounds__(32) ab_backsolve_generic_kernel(const AbSolveArgs a, int l, int u, int r) {
+    generic_ab_backsolve(a, l, u, r, (int64_t)blockIdx.x, (int)threadIdx.x);
+}
+__global__ void __launch_bounds__(32) ab_tri_generic_kernel(const double *AU, const double *V, double *rhs, int n, int64_t np,
+                                                            int l, int u, int r, int upper, int unit) {
+    generic_ab_tri(AU, V, rhs, n, np, l, u, r, upper != 0, unit != 0, (int64_t)blockIdx.x, (int)threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------------------
+static int pick_stages(const ssm_ctx *c, size_t stage_bytes) {
+    if (c->pipeline_stages > 0) return c->pipeline_stages;
+    // fill ~15 KB per warp so that 14 single-warp CTAs (all 2048 tiles of the headline config) stay co-resident
+    int s = (int)(15000 / (stage_bytes + 8));
+    if (s < 2) s = 2;
+    if (s > 8) s = 8;
+    return s;
+}
+
+template <class K>
+static int launch1(ssm_ctx *c, K kern, int64_t ntiles, size_t smem, const char *name) {
+    (void)name;
+    if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 0) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return 0;
+}
+
+template <int L, int U, int R>
+static int qr_inst(ssm_ctx *c, int64_t ntiles, const AbArgs &a, bool with_rhs, bool store_q, int variant) {
+    using D = AbDims<L, U, R>;
+    dim3 grid((unsigned)ntiles), block(32);
+#define SSM_QR_CASE(RHS_, SQ_)                                                                                   \
+    if (with_rhs == RHS_ && store_q == SQ_) {                                                                    \
+        if (variant == 2) {                                                                                      \
+            using LD = RingLoader<D::NFA, R, RHS_ ? 1 : 0, +1>;                                                  \
+            const int ns = pick_stages(c, LD::STAGE_BYTES);                                                      \
+            const size_t smem = LD::smem_bytes(ns);                                                              \
+            auto kern = ab_qr_kernel<L, U, R, RHS_, SQ_, RingLoader>;                                            \
+            SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qr_ring"));                                               \
+            kern<<<grid, block, smem, c->stream>>>(a, ns);                                                       \
+        } else {                                                                                                 \
+            ab_qr_kernel<L, U, R, RHS_, SQ_, DirectLoader><<<grid, block, 0, c->stream>>>(a, 0);                 \
+        }                                                                                                        \
+    }
+    SSM_QR_CASE(false, true)
+    SSM_QR_CASE(true, true)
+    SSM_QR_CASE(true, false)
+    SSM_QR_CASE(false, false)
+#undef SSM_QR_CASE
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int L>
+static int qt_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant) {
+    dim3 grid((unsigned)ntiles), block(32);
+    if (variant == 2) {
+        using LD = RingLoader<L + 1, 1, 0, +1>;
+        const int ns = pick_stages(c, LD::STAGE_BYTES);
+        const size_t smem = LD::smem_bytes(ns);
+        auto kern = ab_qt_kernel<L, RingLoader>;
+        SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qt_ring"));
+        kern<<<grid, block, smem, c->stream>>>(a, ns);
+    } else {
+        ab_qt_kernel<L, DirectLoader><<<grid, block, 0, c->stream>>>(a, 0);
+    }
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int L, int U, int R>
+static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant) {
+    using D = AbDims<L, U, R>;
+    dim3 grid((unsigned)ntiles), block(32);
+    if (variant == 2) {
+        using LD = RingLoader<D::NFR, R, 1, -1>;
+        const int ns = pick_stages(c, LD::STAGE_BYTES);
+        const size_t smem = LD::smem_bytes(ns);
+        auto kern = ab_backsolve_kernel<L, U, R, RingLoader>;
+        SSM_TRY(launch1(c, kern, ntiles, smem, "ab_bs_ring"));
+        kern<<<grid, block, smem, c->stream>>>(a, ns);
+    } else {
+        ab_backsolve_kernel<L, U, R, DirectLoader><<<grid, block, 0, c->stream>>>(a, 0);
+    }
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// shapes with a register-resident fast path (README (1,0,1); tests (1,1,1),(2,0,2),(1,0,2); C2 (2,2,2); C4 (4,4,2))
+#define SSM_AB_SHAPES(X) X(1, 0, 1) X(1, 1, 1) X(1, 0, 2) X(2, 0, 2) X(2, 2, 2) X(3, 3, 2) X(4, 4, 2)
+
+static int effective_variant(const ssm_ctx *c) { return c->ab_variant == 0 ? 2 : c->ab_variant; }
+
+int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, bool with_rhs, bool store_q) {
+    if (ntiles <= 0) return 0;
+    const int variant = effective_variant(c);
+    if (variant != 9) {
+#define X(L_, U_, R_) \
+    if (l == L_ && u == U_ && r == R_) return qr_inst<L_, U_, R_>(c, ntiles, a, with_rhs, store_q, variant);
+        SSM_AB_SHAPES(X)
+#undef X
+    }
+    if (l > SSM_MAX_BW || u > SSM_MAX_BW || r > SSM_MAX_RANK) { set_error("(l,u,r)=(%d,%d,%d) exceeds compiled limits", l, u, r); return SSM_E_UNSUPPORTED; }
+    ab_qr_generic_kernel<<<(unsigned)ntiles, 32, 0, c->stream>>>(a, l, u, r, with_rhs, store_q);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a, bool transpose) {
+    (void)u; (void)r;
+    if (ntiles <= 0) return 0;
+    const int variant = effective_variant(c);
+    if (variant != 9 && transpose) {
+        switch (l) {
+            case 1: return qt_inst<1>(c, ntiles, a, variant);
+            case 2: return qt_inst<2>(c, ntiles, a, variant);
+            case 3: return qt_inst<3>(c, ntiles, a, variant);
+            case 4: return qt_inst<4>(c, ntiles, a, variant);
+            default: break;
+        }
+    }
+    if (l > SSM_MAX_BW) { set_error("l=%d exceeds compiled limits", l); return SSM_E_UNSUPPORTED; }
+    ab_qt_generic_kernel<<<(unsigned)ntiles, 32, 0, c->stream>>>(a, l, transpose);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_ab_backsolve(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a) {
+    if (ntiles <= 0) return 0;
+    const int variant = effective_variant(c);
+    if (variant != 9) {
+#define X(L_, U_, R_) \
+    if (l == L_ && u == U_ && r == R_) return bs_inst<L_, U_, R_>(c, ntiles, a, variant);
+        SSM_AB_SHAPES(X)
+#undef X
+    }
+    if (l > SSM_MAX_BW || u > SSM_MAX_BW || r > SSM_MAX_RANK) { set_error("(l,u,r)=(%d,%d,%d) exceeds compiled limits", l, u, r); return SSM_E_UNSUPPORTED; }
+    ab_backsolve_generic_kernel<<<(unsigned)ntiles, 32, 0, c->stream>>>(a, l, u, r);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_ab_tri(ssm_ctx *c, const ssm_ab *A, double *rhs, bool upper, bool unit) {
+    if (A->ntiles <= 0) return 0;
+    ab_tri_generic_kernel<<<(unsigned)A->ntiles, 32, 0, c->stream>>>(A->AU->p, A->V->p, rhs, A->n, A->np, A->l, A->u, A->r, upper, unit);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ssm

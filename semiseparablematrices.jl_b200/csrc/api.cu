@@ -1,0 +1,429 @@
+// api.cu — the C ABI of libssmb200.so (include/ssm_b200.h): handle management, host/device pointer staging and
+// the AlmostBanded entry points.  BPS entry points live in bps_api.cu.
+#include <cstdarg>
+#include <algorithm>
+#include "ssm_internal.cuh"
+
+namespace ssm {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    cudaGetLastError();
+    return (int)e;
+}
+
+DevBuf::~DevBuf() {
+    if (p) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(device); cudaFree(p); cudaSetDevice(cur); }
+}
+int dev_alloc(int device, size_t count, bool zero, cudaStream_t st, DevBufPtr &out) {
+    auto b = std::make_shared<DevBuf>();
+    b->device = device; b->count = count;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&b->p, count * sizeof(double));
+    if (e != cudaSuccess) { b->p = nullptr; set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(double), cudaGetErrorString(e)); cudaGetLastError(); return SSM_E_NOMEM; }
+    if (zero) SSM_CUDA(cudaMemsetAsync(b->p, 0, count * sizeof(double), st));
+    out = b;
+    return 0;
+}
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int staging_dev(ssm_ctx *c, size_t count, double **out) {
+    if (c->stg.dev_count < count) {
+        if (c->stg.dev) { SSM_CUDA(cudaStreamSynchronize(c->stream)); SSM_CUDA(cudaFree(c->stg.dev)); c->stg.dev = nullptr; c->stg.dev_count = 0; }
+        cudaError_t e = cudaMalloc(&c->stg.dev, count * sizeof(double));
+        if (e != cudaSuccess) { set_error("staging cudaMalloc of %zu bytes failed", count * sizeof(double)); cudaGetLastError(); return SSM_E_NOMEM; }
+        c->stg.dev_count = count;
+    }
+    *out = c->stg.dev;
+    return 0;
+}
+
+// copy `count` systems of `elems` doubles each, source stride `stride`, into a dense device block
+static int h2d_block(ssm_ctx *c, double *dst, const double *src, int64_t stride, size_t elems, int64_t count) {
+    if (elems == 0 || count == 0) return 0;
+    if ((size_t)stride == elems) SSM_CUDA(cudaMemcpyAsync(dst, src, elems * count * sizeof(double), cudaMemcpyDefault, c->stream));
+    else SSM_CUDA(cudaMemcpy2DAsync(dst, elems * sizeof(double), src, stride * sizeof(double), elems * sizeof(double), count, cudaMemcpyDefault, c->stream));
+    return 0;
+}
+static int d2h_block(ssm_ctx *c, double *dst, int64_t stride, const double *src, size_t elems, int64_t count) {
+    if (elems == 0 || count == 0) return 0;
+    if ((size_t)stride == elems) SSM_CUDA(cudaMemcpyAsync(dst, src, elems * count * sizeof(double), cudaMemcpyDefault, c->stream));
+    else SSM_CUDA(cudaMemcpy2DAsync(dst, stride * sizeof(double), src, elems * sizeof(double), elems * sizeof(double), count, cudaMemcpyDefault, c->stream));
+    return 0;
+}
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+    ~DeviceGuard() { int cur; cudaGetDevice(&cur); if (cur != prev) cudaSetDevice(prev); }
+};
+
+static const int64_t STAGE_BYTES_MAX = 256ll << 20;
+static int64_t chunk_systems(size_t doubles_per_system, int64_t nb) {
+    int64_t ch = STAGE_BYTES_MAX / (int64_t)(doubles_per_system * sizeof(double) + 1);
+    ch = std::max<int64_t>(TILE, (ch / TILE) * TILE);
+    return std::min<int64_t>(ch, ((nb + TILE - 1) / TILE) * TILE);
+}
+
+}  // namespace ssm
+
+using namespace ssm;
+
+#define SSM_CHECK_ARG(cond, msg) do { if (!(cond)) { set_error("%s: %s", __func__, msg); return SSM_E_ARG; } } while (0)
+
+extern "C" {
+
+int ssm_version(void) { return 100; }
+const char *ssm_last_error(void) { return g_err.c_str(); }
+
+static int ctx_common(int device, ssm_ctx *c) {
+    int ndev = 0;
+    SSM_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d visible)", device, ndev); return SSM_E_ARG; }
+    c->device = device;
+    SSM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SSM_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) { set_error("libssmb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor); return SSM_E_UNSUPPORTED; }
+    return 0;
+}
+int ssm_ctx_create(int device, ssm_ctx **out) {
+    SSM_CHECK_ARG(out, "null output");
+    auto *c = new ssm_ctx();
+    int rc = ctx_common(device, c);
+    if (rc) { delete c; return rc; }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    c->own_stream = true;
+    *out = c;
+    return 0;
+}
+int ssm_ctx_create_on_stream(int device, void *cuda_stream, ssm_ctx **out) {
+    SSM_CHECK_ARG(out, "null output");
+    auto *c = new ssm_ctx();
+    int rc = ctx_common(device, c);
+    if (rc) { delete c; return rc; }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    *out = c;
+    return 0;
+}
+int ssm_ctx_destroy(ssm_ctx *c) {
+    if (!c) return 0;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    hostpipe_free(c);
+    if (c->stg.dev) cudaFree(c->stg.dev);
+    if (c->stg.pin) cudaFreeHost(c->stg.pin);
+    for (auto &s : c->aux) if (s) cudaStreamDestroy(s);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+int ssm_ctx_sync(ssm_ctx *c) {
+    SSM_CHECK_ARG(c, "null ctx");
+    DeviceGuard g(c->device);
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int ssm_ctx_set_option(ssm_ctx *c, const char *key, int value) {
+    SSM_CHECK_ARG(c && key, "null argument");
+    if (!strcmp(key, "ab_variant")) c->ab_variant = value;
+    else if (!strcmp(key, "pipeline_stages")) c->pipeline_stages = value;
+    else { set_error("unknown option '%s'", key); return SSM_E_ARG; }
+    return 0;
+}
+int ssm_ctx_get_option(ssm_ctx *c, const char *key, int *value) {
+    SSM_CHECK_ARG(c && key && value, "null argument");
+    if (!strcmp(key, "ab_variant")) *value = c->ab_variant;
+    else if (!strcmp(key, "pipeline_stages")) *value = c->pipeline_stages;
+    else if (!strcmp(key, "sm_count")) *value = c->sm_count;
+    else { set_error("unknown option '%s'", key); return SSM_E_ARG; }
+    return 0;
+}
+int64_t ssm_ctx_launch_count(ssm_ctx *c) { return c ? c->launches : 0; }
+
+// ---- vectors ----------------------------------------------------------------------------------------------
+int ssm_vec_create(ssm_ctx *c, int n, int64_t nb, ssm_vec **out) {
+    SSM_CHECK_ARG(c && out, "null argument");
+    SSM_CHECK_ARG(n >= 1 && nb >= 1, "n and nb must be positive");
+    DeviceGuard g(c->device);
+    auto *v = new ssm_vec();
+    v->ctx = c; v->n = n; v->nb = nb; v->ntiles = ntiles_of(nb); v->np = (int64_t)n + PAD;
+    int rc = dev_alloc(c->device, (size_t)(v->ntiles * v->np * 32), true, c->stream, v->d);
+    if (rc) { delete v; return rc; }
+    *out = v;
+    return 0;
+}
+int ssm_vec_destroy(ssm_vec *v) { if (v) { cudaStreamSynchronize(v->ctx->stream); delete v; } return 0; }
+
+int ssm_vec_set(ssm_vec *v, const double *b, int64_t stride) {
+    SSM_CHECK_ARG(v && b, "null argument");
+    ssm_ctx *c = v->ctx;
+    DeviceGuard g(c->device);
+    if (stride == 0) stride = v->n;
+    if (stride < v->n) { set_error("ssm_vec_set: stride %lld < n", (long long)stride); return SSM_E_SHAPE; }
+    if (is_device_ptr(b)) return launch_vec_pack(c, v, b, stride, 0, v->nb);
+    const int64_t ch = chunk_systems((size_t)v->n, v->nb);
+    for (int64_t s0 = 0; s0 < v->nb; s0 += ch) {
+        const int64_t cnt = std::min(ch, v->nb - s0);
+        double *stg;
+        SSM_TRY(staging_dev(c, (size_t)cnt * v->n, &stg));
+        SSM_TRY(h2d_block(c, stg, b + s0 * stride, stride, (size_t)v->n, cnt));
+        SSM_TRY(launch_vec_pack(c, v, stg, v->n, s0, cnt));
+    }
+    SSM_CUDA(cudaStreamSynchronize(c->stream));   // caller's host buffer may be reused on return
+    return 0;
+}
+int ssm_vec_get(const ssm_vec *v, double *b, int64_t stride) {
+    SSM_CHECK_ARG(v && b, "null argument");
+    ssm_ctx *c = v->ctx;
+    DeviceGuard g(c->device);
+    if (stride == 0) stride = v->n;
+    if (stride < v->n) { set_error("ssm_vec_get: stride %lld < n", (long long)stride); return SSM_E_SHAPE; }
+    if (is_device_ptr(b)) return launch_vec_unpack(c, v, b, stride, 0, v->nb);
+    const int64_t ch = chunk_systems((size_t)v->n, v->nb);
+    for (int64_t s0 = 0; s0 < v->nb; s0 += ch) {
+        const int64_t cnt = std::min(ch, v->nb - s0);
+        double *stg;
+        SSM_TRY(staging_dev(c, (size_t)cnt * v->n, &stg));
+        SSM_TRY(launch_vec_unpack(c, v, stg, v->n, s0, cnt));
+        SSM_TRY(d2h_block(c, b + s0 * stride, stride, stg, (size_t)v->n, cnt));
+    }
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int ssm_vec_copy(ssm_vec *dst, const ssm_vec *src) {
+    SSM_CHECK_ARG(dst && src, "null argument");
+    if (dst->n != src->n || dst->nb != src->nb) { set_error("ssm_vec_copy: shape mismatch"); return SSM_E_SHAPE; }
+    DeviceGuard g(dst->ctx->device);
+    SSM_CUDA(cudaMemcpyAsync(dst->d->p, src->d->p, src->d->count * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    return 0;
+}
+int ssm_vec_generate(ssm_vec *v, uint64_t seed, int array_id) {
+    SSM_CHECK_ARG(v, "null argument");
+    DeviceGuard g(v->ctx->device);
+    return launch_vec_generate(v->ctx, v, seed, array_id);
+}
+
+// ---- AlmostBanded -------------------------------------------------------------------------------------------
+int ssm_ab_create(ssm_ctx *c, int n, int l, int u, int r, int64_t nb, ssm_ab **out) {
+    SSM_CHECK_ARG(c && out, "null argument");
+    SSM_CHECK_ARG(n >= 1 && nb >= 1, "n and nb must be positive");
+    SSM_CHECK_ARG(l >= 0 && u >= 0 && r >= 0, "bandwidths and rank must be non-negative");
+    if (l > SSM_MAX_BW || u > SSM_MAX_BW || r > SSM_MAX_RANK) { set_error("(l,u,r)=(%d,%d,%d) exceeds compiled limits (%d,%d,%d)", l, u, r, SSM_MAX_BW, SSM_MAX_BW, SSM_MAX_RANK); return SSM_E_UNSUPPORTED; }
+    DeviceGuard g(c->device);
+    auto *A = new ssm_ab();
+    A->ctx = c; A->n = n; A->l = l; A->u = u; A->r = r; A->nb = nb; A->ntiles = ntiles_of(nb); A->np = (int64_t)n + PAD;
+    int rc = dev_alloc(c->device, (size_t)(A->ntiles * A->np * (l + u + 1 + r) * 32), true, c->stream, A->AU);
+    if (!rc) rc = dev_alloc(c->device, (size_t)(A->ntiles * A->np * (r > 0 ? r : 1) * 32), true, c->stream, A->V);
+    if (rc) { delete A; return rc; }
+    *out = A;
+    return 0;
+}
+int ssm_ab_destroy(ssm_ab *A) { if (A) { cudaStreamSynchronize(A->ctx->stream); delete A; } return 0; }
+
+int ssm_ab_set(ssm_ab *A, const double *bands, int64_t sb, const double *U, int64_t su, const double *V, int64_t sv) {
+    SSM_CHECK_ARG(A && bands && (A->r == 0 || (U && V)), "null argument");
+    ssm_ctx *c = A->ctx;
+    DeviceGuard g(c->device);
+    const size_t eb = (size_t)(A->l + A->u + 1) * A->n, eu = (size_t)A->n * A->r;
+    if (sb == 0) sb = (int64_t)eb;
+    if (su == 0) su = (int64_t)eu;
+    if (sv == 0) sv = (int64_t)eu;
+    if ((size_t)sb < eb || (size_t)su < eu || (size_t)sv < eu) { set_error("ssm_ab_set: Data and fill must be compatible size (stride smaller than one system)"); return SSM_E_SHAPE; }
+    const bool db = is_device_ptr(bands), du = A->r == 0 || is_device_ptr(U), dv = A->r == 0 || is_device_ptr(V);
+    if (db && du && dv) return launch_ab_pack(c, A, bands, sb, U, su, V, sv, 0, A->nb);
+    const int64_t ch = chunk_systems(eb + 2 * eu, A->nb);
+    for (int64_t s0 = 0; s0 < A->nb; s0 += ch) {
+        const int64_t cnt = std::min(ch, A->nb - s0);
+        double *stg;
+        SSM_TRY(staging_dev(c, (size_t)cnt * (eb + 2 * eu), &stg));
+        double *sB = stg, *sU = sB + (size_t)cnt * eb, *sV = sU + (size_t)cnt * eu;
+        SSM_TRY(h2d_block(c, sB, bands + s0 * sb, sb, eb, cnt));
+        if (A->r > 0) { SSM_TRY(h2d_block(c, sU, U + s0 * su, su, eu, cnt)); SSM_TRY(h2d_block(c, sV, V + s0 * sv, sv, eu, cnt)); }
+        SSM_TRY(launch_ab_pack(c, A, sB, (int64_t)eb, sU, (int64_t)eu, sV, (int64_t)eu, s0, cnt));
+    }
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// unpack helper shared by ssm_ab_get / ssm_abqr_get: run `launch` into device memory (direct or staged)
+int ssm_ab_get(const ssm_ab *A, double *bands, int64_t sb, double *U, int64_t su, double *V, int64_t sv) {
+    SSM_CHECK_ARG(A, "null argument");
+    ssm_ctx *c = A->ctx;
+    DeviceGuard g(c->device);
+    const size_t eb = (size_t)(A->l + A->u + 1) * A->n, eu = (size_t)A->n * A->r;
+    if (sb == 0) sb = (int64_t)eb;
+    if (su == 0) su = (int64_t)eu;
+    if (sv == 0) sv = (int64_t)eu;
+    const bool anyhost = (bands && !is_device_ptr(bands)) || (U && !is_device_ptr(U)) || (V && !is_device_ptr(V));
+    if (!anyhost) return launch_ab_unpack(c, A, bands, sb, U, su, V, sv);
+    // host destination: unpack the whole batch into device staging, then copy out (test / inspection path)
+    double *stg;
+    SSM_TRY(staging_dev(c, (size_t)A->nb * (eb + 2 * eu), &stg));
+    double *sB = stg, *sU = sB + (size_t)A->nb * eb, *sV = sU + (size_t)A->nb * eu;
+    SSM_TRY(launch_ab_unpack(c, A, bands ? sB : nullptr, (int64_t)eb, U ? sU : nullptr, (int64_t)eu, V ? sV : nullptr, (int64_t)eu));
+    if (bands) SSM_TRY(d2h_block(c, bands, sb, sB, eb, A->nb));
+    if (U) SSM_TRY(d2h_block(c, U, su, sU, eu, A->nb));
+    if (V) SSM_TRY(d2h_block(c, V, sv, sV, eu, A->nb));
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int ssm_ab_generate(ssm_ab *A, uint64_t seed, int dist) {
+    SSM_CHECK_ARG(A, "null argument");
+    SSM_CHECK_ARG(dist == SSM_DIST_DD || dist == SSM_DIST_BC, "unknown distribution");
+    DeviceGuard g(A->ctx->device);
+    return launch_ab_generate(A->ctx, A, seed, dist);
+}
+
+static int abqr_alloc(const ssm_ab *A, bool with_q, ssm_abqr **out) {
+    ssm_ctx *c = A->ctx;
+    auto *F = new ssm_abqr();
+    F->ctx = c; F->n = A->n; F->l = A->l; F->u = A->u; F->r = A->r; F->nb = A->nb; F->ntiles = A->ntiles; F->np = A->np;
+    int rc = dev_alloc(c->device, (size_t)(F->ntiles * F->np * (F->l + F->u + 1 + F->r) * 32), true, c->stream, F->RU);
+    if (!rc && with_q) rc = dev_alloc(c->device, (size_t)(F->ntiles * F->np * (F->l + 1) * 32), true, c->stream, F->QT);
+    if (rc) { delete F; return rc; }
+    F->V = A->V;
+    *out = F;
+    return 0;
+}
+
+int ssm_ab_qr(const ssm_ab *A, ssm_abqr **out) {
+    SSM_CHECK_ARG(A && out, "null argument");
+    ssm_ctx *c = A->ctx;
+    DeviceGuard g(c->device);
+    ssm_abqr *F = *out;
+    if (F) {   // refactor into an existing object of the same shape (steady-state benchmarking, no allocation)
+        if (F->n != A->n || F->l != A->l || F->u != A->u || F->r != A->r || F->nb != A->nb) { set_error("ssm_ab_qr: factor object has a different shape"); return SSM_E_SHAPE; }
+        F->V = A->V;
+    } else {
+        SSM_TRY(abqr_alloc(A, true, &F));
+    }
+    AbArgs a{A->AU->p, A->V->p, F->RU->p, F->QT->p, nullptr, nullptr, A->n, A->np};
+    int rc = launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, false, true);
+    if (rc) { if (!*out) delete F; return rc; }
+    *out = F;
+    return 0;
+}
+int ssm_abqr_destroy(ssm_abqr *F) { if (F) { cudaStreamSynchronize(F->ctx->stream); delete F; } return 0; }
+
+int ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t sf, double *U, int64_t su, double *tau, int64_t st) {
+    SSM_CHECK_ARG(F, "null argument");
+    ssm_ctx *c = F->ctx;
+    DeviceGuard g(c->device);
+    const size_t ef = (size_t)(2 * F->l + F->u + 1) * F->n, eu = (size_t)F->n * F->r, et = (size_t)F->n;
+    if (sf == 0) sf = (int64_t)ef;
+    if (su == 0) su = (int64_t)eu;
+    if (st == 0) st = (int64_t)et;
+    const bool anyhost = (factors && !is_device_ptr(factors)) || (U && !is_device_ptr(U)) || (tau && !is_device_ptr(tau));
+    if (!anyhost) return launch_abqr_unpack(c, F, factors, sf, U, su, tau, st);
+    double *stg;
+    SSM_TRY(staging_dev(c, (size_t)F->nb * (ef + eu + et), &stg));
+    double *sF = stg, *sU = sF + (size_t)F->nb * ef, *sT = sU + (size_t)F->nb * eu;
+    SSM_TRY(launch_abqr_unpack(c, F, factors ? sF : nullptr, (int64_t)ef, U ? sU : nullptr, (int64_t)eu, tau ? sT : nullptr, (int64_t)et));
+    if (factors) SSM_TRY(d2h_block(c, factors, sf, sF, ef, F->nb));
+    if (U) SSM_TRY(d2h_block(c, U, su, sU, eu, F->nb));
+    if (tau) SSM_TRY(d2h_block(c, tau, st, sT, et, F->nb));
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int check_vec(const char *fn, int n, int64_t nb, const ssm_ctx *c, const ssm_vec *b) {
+    if (!b) { set_error("%s: null vector", fn); return SSM_E_ARG; }
+    if (b->n != n || b->nb != nb) { set_error("%s: DimensionMismatch: vector batch is %lld x %d, matrix batch is %lld x %d", fn, (long long)b->nb, b->n, (long long)nb, n); return SSM_E_SHAPE; }
+    if (b->ctx->device != c->device) { set_error("%s: operands live on different devices", fn); return SSM_E_ARG; }
+    return 0;
+}
+
+int ssm_abqr_lmul_qt(const ssm_abqr *F, ssm_vec *b) {
+    SSM_CHECK_ARG(F, "null argument");
+    SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, b));
+    if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
+    DeviceGuard g(F->ctx->device);
+    AbSolveArgs a{F->RU->p, F->QT->p, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
+    return launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, a, true);
+}
+int ssm_abqr_lmul_q(const ssm_abqr *F, ssm_vec *b) {
+    SSM_CHECK_ARG(F, "null argument");
+    SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, b));
+    if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
+    DeviceGuard g(F->ctx->device);
+    AbSolveArgs a{F->RU->p, F->QT->p, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
+    return launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, a, false);
+}
+int ssm_abqr_upper_ldiv(const ssm_abqr *F, ssm_vec *b) {
+    SSM_CHECK_ARG(F, "null argument");
+    SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, b));
+    DeviceGuard g(F->ctx->device);
+    AbSolveArgs a{F->RU->p, F->QT ? F->QT->p : nullptr, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
+    return launch_ab_backsolve(F->ctx, F->l, F->u, F->r, F->ntiles, a);
+}
+int ssm_abqr_solve(const ssm_abqr *F, const ssm_vec *b, ssm_vec *x) {
+    SSM_CHECK_ARG(F, "null argument");
+    SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, b));
+    SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, x));
+    if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
+    DeviceGuard g(F->ctx->device);
+    AbSolveArgs q{F->RU->p, F->QT->p, F->V->p, b->d->p, x->d->p, F->n, F->np, 0};       // x <- Q'b
+    SSM_TRY(launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, q, true));
+    AbSolveArgs s{F->RU->p, F->QT->p, F->V->p, x->d->p, x->d->p, F->n, F->np, 0};       // x <- R \ x
+    return launch_ab_backsolve(F->ctx, F->l, F->u, F->r, F->ntiles, s);
+}
+int ssm_abqr_ldiv(const ssm_abqr *F, ssm_vec *b) { return ssm_abqr_solve(F, b, b); }
+
+int ssm_ab_solve(const ssm_ab *A, const ssm_vec *b, ssm_vec *x) {
+    SSM_CHECK_ARG(A, "null argument");
+    SSM_TRY(check_vec(__func__, A->n, A->nb, A->ctx, b));
+    SSM_TRY(check_vec(__func__, A->n, A->nb, A->ctx, x));
+    ssm_ctx *c = A->ctx;
+    DeviceGuard g(c->device);
+    // R round-trips through HBM (the back-substitution runs against the sweep); reflectors are not kept.
+    if (!A->scratch) SSM_TRY(dev_alloc(c->device, (size_t)(A->ntiles * A->np * (A->l + A->u + 1 + A->r) * 32), true, c->stream, A->scratch));
+    DevBufPtr RU = A->scratch;
+    AbArgs a{A->AU->p, A->V->p, RU->p, nullptr, b->d->p, x->d->p, A->n, A->np};
+    SSM_TRY(launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, true, false));
+    AbSolveArgs s{RU->p, nullptr, A->V->p, x->d->p, x->d->p, A->n, A->np, 0};
+    return launch_ab_backsolve(c, A->l, A->u, A->r, A->ntiles, s);
+}
+
+int ssm_ab_tri_ldiv(const ssm_ab *A, ssm_vec *b, int upper, int unit) {
+    SSM_CHECK_ARG(A, "null argument");
+    SSM_TRY(check_vec(__func__, A->n, A->nb, A->ctx, b));
+    DeviceGuard g(A->ctx->device);
+    return launch_ab_tri(A->ctx, A, b->d->p, upper != 0, unit != 0);
+}
+
+int ssm_ab_residual(const ssm_ab *A, const ssm_vec *x, const ssm_vec *b, double *relres) {
+    SSM_CHECK_ARG(A && relres, "null argument");
+    SSM_TRY(check_vec(__func__, A->n, A->nb, A->ctx, x));
+    SSM_TRY(check_vec(__func__, A->n, A->nb, A->ctx, b));
+    ssm_ctx *c = A->ctx;
+    DeviceGuard g(c->device);
+    if (is_device_ptr(relres)) return launch_ab_residual(c, A, x, b, relres);
+    double *stg;
+    SSM_TRY(staging_dev(c, (size_t)A->ntiles * 32, &stg));
+    SSM_TRY(launch_ab_residual(c, A, x, b, stg));
+    SSM_CUDA(cudaMemcpyAsync(relres, stg, (size_t)A->nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// ssm_internal.cuh — shared definitions of libssmb200.so (not installed; the public surface is include/ssm_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/ssm_b200.h"
+
+namespace ssm {
+
+// ---- device layout ------------------------------------------------------------------
+// Systems are grouped in tiles of 32 (one warp, one lane per system).  Every per-row quantity is a
+// "record": NF fields x 32 lanes of fp64, lane fastest, so one field of one record is one 256-byte
+// coalesced segment and one record is NF*256 contiguous bytes.  A tile's records are contiguous:
+//     addr(tile, rec, field, lane) = ((tile * NP + rec) * NF + field) * 32 + lane
+// NP = n + PAD records per tile; the PAD tail is zero so look-ahead loads and the rows "entering" after
+// the last row need no bounds checks.
+constexpr int TILE = 32;
+constexpr int PAD  = 48;
+
+inline int64_t ntiles_of(int64_t nb) { return (nb + TILE - 1) / TILE; }
+
+struct DevBuf {
+    double *p = nullptr;
+    size_t  count = 0;
+    int     device = 0;
+    ~DevBuf();
+};
+using DevBufPtr = std::shared_ptr<DevBuf>;
+int dev_alloc(int device, size_t count, bool zero, cudaStream_t st, DevBufPtr &out);
+
+void set_error(const char *fmt, ...);
+bool is_device_ptr(const void *p);
+int  cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SSM_CUDA(call)                                                      \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) return ::ssm::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define SSM_TRY(call)                        \
+    do {                                     \
+        int rc__ = (call);                   \
+        if (rc__ != 0) return rc__;          \
+    } while (0)
+
+struct Staging {        // lazily grown scratch: device staging in reference layout + pinned host bounce
+    double *dev = nullptr;  size_t dev_count = 0;
+    double *pin = nullptr;  size_t pin_count = 0;
+};
+
+}  // namespace ssm
+
+struct ssm_ctx;
+namespace ssm { int staging_dev(ssm_ctx *c, size_t count, double **out); void hostpipe_free(ssm_ctx *c); }
+
+struct ssm_ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    bool         own_stream = false;
+    int          ab_variant = 0;       // 0 auto, 1 direct-load kernels, 2 bulk-async (TMA) ring kernels, 9 generic
+    int          pipeline_stages = 0;  // 0 = kernel default
+    int          sm_count = 148;
+    int64_t      launches = 0;
+    ssm::Staging stg;
+    // extra streams / events for the chunk-pipelined host path
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    void        *hostpipe = nullptr;   // ssm::HostPipe of ssm_ab_solve_host (host_path.cu)
+};
+
+struct ssm_vec {
+    ssm_ctx *ctx; int n; int64_t nb, ntiles, np;
+    ssm::DevBufPtr d;           // [ntiles][np][32]
+};
+
+struct ssm_ab {
+    ssm_ctx *ctx; int n, l, u, r; int64_t nb, ntiles, np;
+    ssm::DevBufPtr AU;          // [ntiles][np][l+u+1+r][32]   row record: A[i, i-l .. i+u], U[i, :]
+    ssm::DevBufPtr V;           // [ntiles][np][r][32]         V[:, c]
+    mutable ssm::DevBufPtr scratch;  // R records of the fused A\\b path (kept between calls)
+};
+
+struct ssm_abqr {
+    ssm_ctx *ctx; int n, l, u, r; int64_t nb, ntiles, np;
+    ssm::DevBufPtr RU;          // [ntiles][np][l+u+1+r][32]   R[k, k .. k+ub], Ufinal[k, :]
+    ssm::DevBufPtr QT;          // [ntiles][np][l+1][32]       reflector tail of column k, tau_k
+    ssm::DevBufPtr V;           // shared with the operand batch (never written by the path)
+};
+
+namespace ssm {
+
+// kernel-argument bundles (plain pointers; passed by value)
+struct AbArgs {
+    const double *AU; const double *V;      // operands
+    double *RU; double *QT;                  // factors (QT may be null when reflectors are not kept)
+    const double *rhs_in;                    // b (may be null; may alias rhs)
+    double *rhs;                             // out: Q'b
+    int n; int64_t np;
+};
+struct AbSolveArgs {
+    const double *RU; const double *QT; const double *V;
+    const double *rhs_in;                    // input vector batch (may alias rhs)
+    double *rhs;                             // output / in-place vector batch
+    int n; int64_t np; int unit;
+};
+
+// launchers implemented in ab_kernels.cu; return 0 or SSM_E_UNSUPPORTED when (l,u,r) has no fast instance
+int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, bool with_rhs, bool store_q);
+int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a, bool transpose);
+int launch_ab_backsolve(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a);
+// operand-level triangular solves (unfactored AlmostBandedMatrix), generic kernels only
+int launch_ab_tri(ssm_ctx *c, const ssm_ab *A, double *rhs, bool upper, bool unit);
+
+// util_kernels.cu
+int launch_ab_pack(ssm_ctx *c, ssm_ab *A, const double *bands, int64_t sb, const double *U, int64_t su,
+                   const double *V, int64_t sv, int64_t s0, int64_t count);
+int launch_ab_unpack(ssm_ctx *c, const ssm_ab *A, double *bands, int64_t sb, double *U, int64_t su, double *V,
+                     int64_t sv);
+int launch_abqr_unpack(ssm_ctx *c, const ssm_abqr *F, double *factors, int64_t sf, double *U, int64_t su,
+                       double *tau, int64_t st);
+int launch_ab_generate(ssm_ctx *c, ssm_ab *A, uint64_t seed, int dist);
+int launch_vec_pack(ssm_ctx *c, ssm_vec *v, const double *b, int64_t stride, int64_t s0, int64_t count);
+int launch_vec_unpack(ssm_ctx *c, const ssm_vec *v, double *b, int64_t stride, int64_t s0, int64_t count);
+int launch_vec_generate(ssm_ctx *c, ssm_vec *v, uint64_t seed, int array_id);
+int launch_ab_residual(ssm_ctx *c, const ssm_ab *A, const ssm_vec *x, const ssm_vec *b, double *relres_dev);
+
+}  // namespace ssm

@@ -1,0 +1,143 @@
+// stream_loader.cuh — how a warp pulls its tile's record streams out of HBM.
+//
+// A sweep consumes, per step g, one record from each of up to three streams (e.g. the entering row record,
+// one V column, one right-hand-side value).  Each stream s is described by (base pointer of the tile for
+// this lane, fields per record NFs, record offset OFFs): step g reads record  OFFs + DIR*g.
+//
+//   DirectLoader : ld.global into registers one step ahead (no shared memory).
+//   RingLoader   : Blackwell/Hopper bulk-async copies (cp.async.bulk = TMA 1-D, SASS UBLKCP) issued by lane 0
+//                  into a per-warp shared-memory ring of NSTAGE steps, completion tracked by one mbarrier per
+//                  stage (complete_tx::bytes).  The warp reads its stage with conflict-free LDS.64 (lane-fastest
+//                  records), then lane 0 re-arms the stage NSTAGE steps ahead.  Loads therefore run NSTAGE-1
+//                  steps ahead of the arithmetic without costing registers.
+#pragma once
+#include <cstdint>
+
+namespace ssm {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a lost completion must never hang the GPU box — trap after ~2^31 cycles instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- DirectLoader -------------------------------------------------------------------------------------
+template <int NF0, int NF1, int NF2, int DIR>
+struct DirectLoader {
+    const double *p0, *p1, *p2;   // lane-adjusted pointers to record (OFFs) of each stream
+    int64_t nsteps;
+    double n0[NF0 > 0 ? NF0 : 1], n1[NF1 > 0 ? NF1 : 1], n2[NF2 > 0 ? NF2 : 1];
+
+    __device__ __forceinline__ void fetch() {
+#pragma unroll
+        for (int f = 0; f < NF0; ++f) n0[f] = p0[f * 32];
+#pragma unroll
+        for (int f = 0; f < NF1; ++f) n1[f] = p1[f * 32];
+#pragma unroll
+        for (int f = 0; f < NF2; ++f) n2[f] = p2[f * 32];
+        p0 += DIR * NF0 * 32; p1 += DIR * NF1 * 32; p2 += DIR * NF2 * 32;
+    }
+    __device__ __forceinline__ void init(const double *b0, const double *b1, const double *b2, void *, int, int64_t total_steps) {
+        p0 = b0; p1 = b1; p2 = b2; nsteps = total_steps;
+        if (total_steps > 0) fetch();
+    }
+    // hands out step g's records and starts loading step g+1 (never touches a record past the last step)
+    __device__ __forceinline__ void acquire(int64_t g, double *r0, double *r1, double *r2) {
+#pragma unroll
+        for (int f = 0; f < NF0; ++f) r0[f] = n0[f];
+#pragma unroll
+        for (int f = 0; f < NF1; ++f) r1[f] = n1[f];
+#pragma unroll
+        for (int f = 0; f < NF2; ++f) r2[f] = n2[f];
+        if (g + 1 < nsteps) fetch();
+    }
+};
+
+// ---- RingLoader ---------------------------------------------------------------------------------------
+template <int NF0, int NF1, int NF2, int DIR>
+struct RingLoader {
+    static constexpr int STAGE_DOUBLES = (NF0 + NF1 + NF2) * 32;
+    static constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
+    const double *g0, *g1, *g2;   // tile base (NOT lane adjusted) of record OFFs of each stream
+    double *ring;                 // this warp's ring
+    uint32_t bar0;                // smem address of mbarrier[0]
+    int nstage;
+    int64_t nsteps;               // total steps that will be consumed
+    int lane;
+
+    static __host__ __device__ size_t smem_bytes(int nstage) { return (size_t)nstage * STAGE_BYTES + (size_t)nstage * 8; }
+
+    __device__ __forceinline__ void issue(int64_t g) {
+        const int s = (int)(g % nstage);
+        const uint32_t bar = bar0 + 8u * s;
+        double *dst = ring + (size_t)s * STAGE_DOUBLES;
+        mbar_expect_tx(bar, STAGE_BYTES);
+        if (NF0 > 0) bulk_g2s(smem_u32(dst), g0 + (int64_t)DIR * g * NF0 * 32, NF0 * 256, bar);
+        if (NF1 > 0) bulk_g2s(smem_u32(dst + NF0 * 32), g1 + (int64_t)DIR * g * NF1 * 32, NF1 * 256, bar);
+        if (NF2 > 0) bulk_g2s(smem_u32(dst + (NF0 + NF1) * 32), g2 + (int64_t)DIR * g * NF2 * 32, NF2 * 256, bar);
+    }
+    // b0..b2: lane-adjusted pointers as for DirectLoader (lane offset removed here)
+    __device__ __forceinline__ void init(const double *b0, const double *b1, const double *b2, void *smem, int nst,
+                                         int64_t total_steps) {
+        lane = threadIdx.x & 31;
+        g0 = b0 - lane; g1 = b1 - lane; g2 = b2 - lane;
+        nstage = nst; nsteps = total_steps;
+        ring = reinterpret_cast<double *>(smem);
+        bar0 = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)nst * STAGE_BYTES);
+        if (lane == 0) {
+            for (int s = 0; s < nst; ++s) mbar_init(bar0 + 8u * s, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int64_t g = 0; g < nst && g < total_steps; ++g) issue(g);
+        }
+    }
+    __device__ __forceinline__ void acquire(int64_t g, double *r0, double *r1, double *r2) {
+        const int s = (int)(g % nstage);
+        const uint32_t parity = (uint32_t)((g / nstage) & 1);
+        mbar_wait(bar0 + 8u * s, parity);
+        const double *src = ring + (size_t)s * STAGE_DOUBLES + lane;
+#pragma unroll
+        for (int f = 0; f < NF0; ++f) r0[f] = src[f * 32];
+#pragma unroll
+        for (int f = 0; f < NF1; ++f) r1[f] = src[(NF0 + f) * 32];
+#pragma unroll
+        for (int f = 0; f < NF2; ++f) r2[f] = src[(NF0 + NF1 + f) * 32];
+        __syncwarp();   // every lane has its copy in registers before the stage is re-armed
+        if (lane == 0 && g + nstage < nsteps) issue(g + nstage);
+    }
+};
+
+}  // namespace ssm
