@@ -232,11 +232,13 @@ static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
 // shapes with a register-resident fast path (README (1,0,1); tests (1,1,1),(2,0,2),(1,0,2); C2 (2,2,2); C4 (4,4,2))
 #define SSM_AB_SHAPES(X) X(1, 0, 1) X(1, 1, 1) X(1, 0, 2) X(2, 0, 2) X(2, 2, 2) X(3, 3, 2) X(4, 4, 2)
 
-static int effective_variant(const ssm_ctx *c) { return c->ab_variant == 0 ? 2 : c->ab_variant; }
+// auto (0): measured on B200 at config 2 — the QR sweep is fastest with direct loads (it is register-rich and
+// store-heavy), the two light solve kernels with the bulk-async ring (profiles/README.md)
+static int effective_variant(const ssm_ctx *c, int kernel_default) { return c->ab_variant == 0 ? kernel_default : c->ab_variant; }
 
 int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, bool with_rhs, bool store_q) {
     if (ntiles <= 0) return 0;
-    const int variant = effective_variant(c);
+    const int variant = effective_variant(c, 1);
     if (variant != 9) {
 #define X(L_, U_, R_) \
     if (l == L_ && u == U_ && r == R_) return qr_inst<L_, U_, R_>(c, ntiles, a, with_rhs, store_q, variant);
@@ -253,7 +255,7 @@ int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &
 int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a, bool transpose) {
     (void)u; (void)r;
     if (ntiles <= 0) return 0;
-    const int variant = effective_variant(c);
+    const int variant = effective_variant(c, 2);
     if (variant != 9 && transpose) {
         switch (l) {
             case 1: return qt_inst<1>(c, ntiles, a, variant);
@@ -272,7 +274,7 @@ int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveA
 
 int launch_ab_backsolve(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a) {
     if (ntiles <= 0) return 0;
-    const int variant = effective_variant(c);
+    const int variant = effective_variant(c, 2);
     if (variant != 9) {
 #define X(L_, U_, R_) \
     if (l == L_ && u == U_ && r == R_) return bs_inst<L_, U_, R_>(c, ntiles, a, variant);

