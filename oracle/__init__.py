@@ -180,3 +180,80 @@ def dense_qr_unblocked(A):
     t = np.zeros(n); t[: len(tau)] = tau
     t[n - 1] = 0.0  # geqrf's last tau for a square real matrix is 0
     return qr_, t
+
+
+# --------------------------------------------------------------------------------------------------
+# BandedPlusSemiseparable — reference layout, stacked: B (nb, n, l+m+1); U,V (nb, r, n); W,S (nb, p, n); b (nb, n)
+# --------------------------------------------------------------------------------------------------
+def bps_generate(n, l, m, r, p, nb, seed, s0=0):
+    B = np.empty((nb, n, l + m + 1)); U = np.empty((nb, r, n)); V = np.empty((nb, r, n))
+    W = np.empty((nb, p, n)); S = np.empty((nb, p, n)); b = np.empty((nb, n))
+    lib().ssm_oracle_bps_generate(n, l, m, r, p, C.c_int64(s0), C.c_int64(nb), C.c_uint64(seed), _p(B), _p(U), _p(V), _p(W), _p(S), _p(b))
+    return B, U, V, W, S, b
+
+
+def bps_dense(B, U, V, W, S, l, m):
+    """Dense n x n matrix of ONE system: B + tril(UV',-1) + triu(WS',1) (BandedPlusSemiseparableMatrix.jl:2)."""
+    n = B.shape[0]; r = U.shape[0]; p = W.shape[0]
+    out = np.empty((n, n))
+    lib().ssm_oracle_bps_dense(n, l, m, r, p, _p(_f64(B)), _p(_f64(U)), _p(_f64(V)), _p(_f64(W)), _p(_f64(S)), _p(out))
+    return out.T.copy()
+
+
+def bps_qr(B, U, V, W, S, l, m):
+    """qr(A::BPS) of one system -> (Bf (n,2l+m+1), Vf (r,n), Wf (p+r,n), Sf (p+r,n), tau (n,))  [semiseparableqr.jl:128-131]"""
+    n = B.shape[0]; r = U.shape[0]; p = W.shape[0]
+    Bf = np.zeros((n, 2 * l + m + 1)); Vf = np.zeros((r, n)); Wf = np.zeros((p + r, n)); Sf = np.zeros((p + r, n)); tau = np.zeros(n)
+    rc = lib().ssm_oracle_bps_qr(n, l, m, r, p, _p(_f64(B)), _p(_f64(U)), _p(_f64(V)), _p(_f64(W)), _p(_f64(S)),
+                                 _p(Bf), _p(Vf), _p(Wf), _p(Sf), _p(tau))
+    assert rc == 0
+    return Bf, Vf, Wf, Sf, tau
+
+
+def bps_qr_batch(B, U, V, W, S, l, m):
+    nb, n, _ = B.shape; r = U.shape[1]; p = W.shape[1]
+    Bf = np.zeros((nb, n, 2 * l + m + 1)); Vf = np.zeros((nb, r, n)); Wf = np.zeros((nb, p + r, n)); Sf = np.zeros((nb, p + r, n)); tau = np.zeros((nb, n))
+    rc = lib().ssm_oracle_bps_qr_batch(n, l, m, r, p, C.c_int64(nb), _p(_f64(B)), _p(_f64(U)), _p(_f64(V)), _p(_f64(W)), _p(_f64(S)),
+                                       _p(Bf), _p(Vf), _p(Wf), _p(Sf), _p(tau))
+    assert rc == 0
+    return Bf, Vf, Wf, Sf, tau
+
+
+def bps_lmul_qt(Bf, U, Vf, tau, b, l, mw):
+    """lmul!(F.Q', b) [semiseparableqr.jl:863-905]; mw = upper bandwidth of the factor's B (= l + m)."""
+    n = Bf.shape[0]; r = U.shape[0]
+    x = np.array(b, dtype=np.float64, copy=True)
+    lib().ssm_oracle_bps_lmul_qt(n, l, mw, r, _p(_f64(Bf)), _p(_f64(U)), _p(_f64(Vf)), _p(_f64(tau)), _p(x))
+    return x
+
+
+def bps_upper_ldiv(Bf, Wf, Sf, b, l, mw):
+    """ldiv!(UpperTriangular(F), b) [BandedPlusSemiseparableMatrix.jl:53-70]."""
+    n = Bf.shape[0]; pw = Wf.shape[0]
+    x = np.array(b, dtype=np.float64, copy=True)
+    lib().ssm_oracle_bps_upper_ldiv(n, l, mw, pw, _p(_f64(Bf)), _p(_f64(Wf)), _p(_f64(Sf)), _p(x))
+    return x
+
+
+def bps_solve_batch(Bf, U, Vf, Wf, Sf, tau, b, l, mw):
+    nb, n, _ = Bf.shape; r = U.shape[1]; pw = Wf.shape[1]
+    x = np.array(b, dtype=np.float64, copy=True)
+    lib().ssm_oracle_bps_solve_batch(n, l, mw, r, pw, C.c_int64(nb), _p(_f64(Bf)), _p(_f64(U)), _p(_f64(Vf)), _p(_f64(Wf)), _p(_f64(Sf)), _p(_f64(tau)), _p(x))
+    return x
+
+
+def bps_mul(B, U, V, W, S, x, l, m):
+    n = B.shape[0]; r = U.shape[0]; p = W.shape[0]
+    y = np.empty(n)
+    lib().ssm_oracle_bps_mul(n, l, m, r, p, _p(_f64(B)), _p(_f64(U)), _p(_f64(V)), _p(_f64(W)), _p(_f64(S)), _p(_f64(x)), _p(y))
+    return y
+
+
+def bps_relres(B, U, V, W, S, x, b, l, m):
+    n = B.shape[0]; r = U.shape[0]; p = W.shape[0]
+    return float(lib().ssm_oracle_bps_relres(n, l, m, r, p, _p(_f64(B)), _p(_f64(U)), _p(_f64(V)), _p(_f64(W)), _p(_f64(S)), _p(_f64(x)), _p(_f64(b))))
+
+
+def bps_factors_dense(Bf, U, Vf, Wf, Sf, l, mw):
+    """Matrix(F.factors): R in the upper triangle, reflector tails below (what test_qr.jl:17,29 compares)."""
+    return bps_dense(Bf, U, Vf, Wf, Sf, l, mw)

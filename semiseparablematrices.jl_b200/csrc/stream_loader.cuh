@@ -98,8 +98,11 @@ struct RingLoader {
 
     static __host__ __device__ size_t smem_bytes(int nstage) { return (size_t)nstage * STAGE_BYTES + (size_t)nstage * 8; }
 
-    __device__ __forceinline__ void issue(int64_t g) {
-        const int s = (int)(g % nstage);
+    int cur = 0;                  // stage holding the next step to be consumed
+    uint32_t parity = 0;          // its mbarrier phase parity
+
+    // arm stage s with step g (s == g mod nstage by construction; no division on the hot path)
+    __device__ __forceinline__ void issue(int64_t g, int s) {
         const uint32_t bar = bar0 + 8u * s;
         double *dst = ring + (size_t)s * STAGE_DOUBLES;
         mbar_expect_tx(bar, STAGE_BYTES);
@@ -121,12 +124,12 @@ struct RingLoader {
         }
         __syncwarp();
         if (lane == 0) {
-            for (int64_t g = 0; g < nst && g < total_steps; ++g) issue(g);
+            for (int g = 0; g < nst && g < total_steps; ++g) issue(g, g);
         }
     }
+    // steps must be acquired in order g = 0, 1, 2, ...
     __device__ __forceinline__ void acquire(int64_t g, double *r0, double *r1, double *r2) {
-        const int s = (int)(g % nstage);
-        const uint32_t parity = (uint32_t)((g / nstage) & 1);
+        const int s = cur;
         mbar_wait(bar0 + 8u * s, parity);
         const double *src = ring + (size_t)s * STAGE_DOUBLES + lane;
 #pragma unroll
@@ -136,7 +139,8 @@ struct RingLoader {
 #pragma unroll
         for (int f = 0; f < NF2; ++f) r2[f] = src[(NF0 + NF1 + f) * 32];
         __syncwarp();   // every lane has its copy in registers before the stage is re-armed
-        if (lane == 0 && g + nstage < nsteps) issue(g + nstage);
+        if (lane == 0 && g + nstage < nsteps) issue(g + nstage, s);
+        if (++cur == nstage) { cur = 0; parity ^= 1u; }
     }
 };
 

@@ -130,7 +130,7 @@ def test_dense_lapack_parity_on_randn(ssm, ctx, variant):
 
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_readme_golden_vector(ssm, ctx, variant):
-    """README.md:50,73-94 (config 1 at n = 20) through the GPU path; 1/k! to 1e-15 and the printed values to 4 ulp."""
+    """README.md:50,73-94 (config 1 at n = 20) through the GPU path; 1/k! to 1e-15 and every printed value to 16 ulp."""
     with_variant(ctx, variant)
     g = json.loads((GOLDEN / "readme_expz.json").read_text())
     (l, u, r), bands, U, V, b = readme_expz(g["n"])
@@ -138,7 +138,7 @@ def test_readme_golden_vector(ssm, ctx, variant):
     x = A.solve(b)
     gx = np.array(g["x"])
     assert np.abs(x - gx).max() <= 1e-15
-    assert np.all(np.abs(x - gx) <= 4 * np.spacing(gx))
+    assert np.all(np.abs(x - gx) <= 16 * np.spacing(gx))   # componentwise, incl. the 1e-18 tail
     assert np.abs(x - np.array([1 / math.factorial(k) for k in range(g["n"])])).max() <= 1e-15
     x2 = ssm.qr(A).ldiv(b)
     assert np.array_equal(x, x2)       # A\b === F\b (test_almostbanded.jl:154): both run the same arithmetic
