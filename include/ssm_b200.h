@@ -131,6 +131,7 @@ int  ssm_bpsqr_lmul_qt(const ssm_bpsqr *F, ssm_vec *b);
 int  ssm_bpsqr_upper_ldiv(const ssm_bpsqr *F, ssm_vec *b);
 /* F \ b = ldiv!(F.R, lmul!(F.Q', b)) (the two halves test_qr.jl:47-53 exercises)                           */
 int  ssm_bpsqr_ldiv(const ssm_bpsqr *F, ssm_vec *b);
+int  ssm_bpsqr_solve(const ssm_bpsqr *F, const ssm_vec *b, ssm_vec *x);   /* x <- F \ b, b untouched (x may alias b) */
 /* A * x (BandedPlusSemiseparableMatrix.jl:21-41) and the residual built on it                              */
 int  ssm_bps_mul(const ssm_bps *A, const ssm_vec *x, ssm_vec *y);
 int  ssm_bps_residual(const ssm_bps *A, const ssm_vec *x, const ssm_vec *b, double *relres);

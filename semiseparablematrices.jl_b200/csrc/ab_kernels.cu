@@ -175,11 +175,11 @@ static int qr_inst(ssm_ctx *c, int64_t ntiles, const AbArgs &a, bool with_rhs, b
             using LD = RingLoader<D::NFA, R, RHS_ ? 1 : 0, +1>;                                                  \
             const int ns = pick_stages(c, LD::STAGE_BYTES);                                                      \
             const size_t smem = LD::smem_bytes(ns);                                                              \
-            auto kern = ab_qr_kernel<L, U, R, RHS_, SQ_, RingLoader>;                                            \
+            auto kern = ab_qr_kernel<L, U, R, RHS_, SQ_, RingLoaderD>;                                            \
             SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qr_ring"));                                               \
             kern<<<grid, block, smem, c->stream>>>(a, ns);                                                       \
         } else {                                                                                                 \
-            ab_qr_kernel<L, U, R, RHS_, SQ_, DirectLoader><<<grid, block, 0, c->stream>>>(a, 0);                 \
+            ab_qr_kernel<L, U, R, RHS_, SQ_, DirectLoaderD><<<grid, block, 0, c->stream>>>(a, 0);                 \
         }                                                                                                        \
     }
     SSM_QR_CASE(false, true)
@@ -199,11 +199,11 @@ static int qt_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
         using LD = RingLoader<L + 1, 1, 0, +1>;
         const int ns = pick_stages(c, LD::STAGE_BYTES);
         const size_t smem = LD::smem_bytes(ns);
-        auto kern = ab_qt_kernel<L, RingLoader>;
+        auto kern = ab_qt_kernel<L, RingLoaderD>;
         SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qt_ring"));
         kern<<<grid, block, smem, c->stream>>>(a, ns);
     } else {
-        ab_qt_kernel<L, DirectLoader><<<grid, block, 0, c->stream>>>(a, 0);
+        ab_qt_kernel<L, DirectLoaderD><<<grid, block, 0, c->stream>>>(a, 0);
     }
     c->launches++;
     SSM_CUDA(cudaGetLastError());
@@ -218,11 +218,11 @@ static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
         using LD = RingLoader<D::NFR, R, 1, -1>;
         const int ns = pick_stages(c, LD::STAGE_BYTES);
         const size_t smem = LD::smem_bytes(ns);
-        auto kern = ab_backsolve_kernel<L, U, R, RingLoader>;
+        auto kern = ab_backsolve_kernel<L, U, R, RingLoaderD>;
         SSM_TRY(launch1(c, kern, ntiles, smem, "ab_bs_ring"));
         kern<<<grid, block, smem, c->stream>>>(a, ns);
     } else {
-        ab_backsolve_kernel<L, U, R, DirectLoader><<<grid, block, 0, c->stream>>>(a, 0);
+        ab_backsolve_kernel<L, U, R, DirectLoaderD><<<grid, block, 0, c->stream>>>(a, 0);
     }
     c->launches++;
     SSM_CUDA(cudaGetLastError());

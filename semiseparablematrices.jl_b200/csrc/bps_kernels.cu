@@ -1,0 +1,431 @@
+// bps_kernels.cu — sm_100a kernels of the BandedPlusSemiseparable hot path:
+//   K5 bps_reduce   U'U (and U'b) per system: the one reduction the streaming sweep needs up front
+//   K6 bps_qr       the per-column state-space sweep (semiseparableqr.jl:104-152,315-571) over a shared-memory window
+//                   of row records fed by bulk-async copies (WindowRing, stream_loader.cuh)
+//   K7 bps_qt       lmul!(Q', b) (semiseparableqr.jl:863-919) as a forward streaming pass
+//   K8 bps_bs       ldiv!(UpperTriangular{BPS}, b) (BandedPlusSemiseparableMatrix.jl:53-70)
+// plus the boundary kernels (pack / unpack / generate) and the O(n) matvec / residual (K9).
+// One lane per system, one warp per tile of 32 systems, as in the AlmostBanded path.
+#include "../../include/ssm_rng.h"
+#include "bps_core.cuh"
+#include "ssm_internal.cuh"
+#include "stream_loader.cuh"
+
+namespace ssm {
+
+// compiled kernel shapes (L, M, R, P); a batch is zero-padded to the smallest one that dominates its shape
+#define SSM_BPS_SHAPES(X) X(1, 1, 1, 1) X(2, 2, 2, 2) X(3, 3, 2, 2) X(4, 5, 3, 3)
+
+bool bps_pick_shape(int l, int m, int r, int p, int *tl, int *tm, int *tr, int *tp) {
+#define X(L_, M_, R_, P_) \
+    if (l <= L_ && m <= M_ && r <= R_ && p <= P_) { *tl = L_; *tm = M_; *tr = R_; *tp = P_; return true; }
+    SSM_BPS_SHAPES(X)
+#undef X
+    return false;
+}
+int bps_nfa(int tl, int tm, int tr, int tp) { return tl + tm + 1 + 2 * tr + 2 * tp; }
+int bps_nfo(int tl, int tm, int tr, int tp) { return tl + tr + 1 + tl + tm + 1 + tp + 2 * tr; }
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: per-system reductions over the rows: G = U'U (R x R) and, if rhs != null, t = U'b (R).
+// 4 warps per tile, each sums a quarter of the rows; combined through shared memory.
+// ---------------------------------------------------------------------------------------------------------
+template <int NFA, int FU, int R>
+__global__ void __launch_bounds__(128) bps_reduce_kernel(const double *REC, const double *rhs, double *GT, double *TT, int n, int64_t np,
+                                                         int64_t np_vec) {
+    __shared__ double sh[4][R * R + R][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    const double *rec = REC + (tile * np + BPS_FRONT) * NFA * 32 + lane;
+    const double *bb = rhs ? rhs + tile * np_vec * 32 + lane : nullptr;
+    double G[R][R], t[R];
+#pragma unroll
+    for (int a = 0; a < R; ++a) { t[a] = 0.0;
+#pragma unroll
+        for (int c = 0; c < R; ++c) G[a][c] = 0.0; }
+    const int chunk = (n + 3) / 4, i0 = w * chunk, i1 = min(n, i0 + chunk);
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+        double u[R];
+#pragma unroll
+        for (int a = 0; a < R; ++a) u[a] = __ldg(rec + ((int64_t)i * NFA + FU + a) * 32);
+        if (GT) {
+#pragma unroll
+            for (int a = 0; a < R; ++a)
+#pragma unroll
+                for (int c = a; c < R; ++c) G[a][c] = fma(u[a], u[c], G[a][c]);
+        }
+        if (bb) { const double bi = bb[(int64_t)i * 32];
+#pragma unroll
+            for (int a = 0; a < R; ++a) t[a] = fma(u[a], bi, t[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < R; ++a) { sh[w][R * R + a][lane] = t[a];
+#pragma unroll
+        for (int c = 0; c < R; ++c) sh[w][a * R + c][lane] = (c >= a) ? G[a][c] : G[c][a]; }
+    __syncthreads();
+    for (int e = w; e < R * R + R; e += 4) {
+        const double s = (sh[0][e][lane] + sh[1][e][lane]) + (sh[2][e][lane] + sh[3][e][lane]);
+        if (e < R * R) { if (GT) GT[(tile * (R * R) + e) * 32 + lane] = s; }
+        else if (TT) TT[(tile * R + (e - R * R)) * 32 + lane] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6: QR sweep
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BPS_NST = 16;   // window ring depth: M rows back + L rows ahead + look-ahead
+
+template <int L, int M, int R, int P>
+__global__ void __launch_bounds__(32) bps_qr_kernel(const double *REC, const double *GT, double *OUT, int n, int64_t np, int64_t npo) {
+    using D = BpsDims<L, M, R, P>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    WindowRing<D::NFA, BPS_NST> win;
+    // sequence index k <-> row k - M; record of row rho sits at BPS_FRONT + rho
+    win.init(REC + (tile * np + BPS_FRONT - M) * D::NFA * 32, smem, (int64_t)n + L + M);
+    double gt[R * R];
+#pragma unroll
+    for (int e = 0; e < R * R; ++e) gt[e] = __ldg(GT + (tile * (R * R) + e) * 32 + lane);
+    BpsState<L, M, R, P> st;
+    bps_init<L, M, R, P>(st, gt);
+    double *out = OUT + tile * npo * D::NFO * 32 + lane;
+    for (int k = 0; k < L + M; ++k) win.wait(k);          // rows -M .. L-1
+    for (int q = 0; q < n; ++q) {
+        win.wait((int64_t)q + L + M);                      // row q+L
+        double o[D::NFO];
+        bps_step<L, M, R, P>(st, [&](int rel, int f) { return win.rec((int64_t)q + rel + M)[f * 32]; }, q == n - 1, o);
+#pragma unroll
+        for (int f = 0; f < D::NFO; ++f) out[((int64_t)q * D::NFO + f) * 32] = o[f];
+        win.release(q);                                    // row q-M leaves the window
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K7: b <- Q'b
+// ---------------------------------------------------------------------------------------------------------
+template <int L, int M, int R, int P, template <int, int, int, int, int, int, int> class Loader>
+__global__ void __launch_bounds__(32) bps_qt_kernel(const double *REC, const double *OUT, const double *GT, const double *TT,
+                                                    const double *rhs_in, double *rhs, int n, int64_t np, int64_t npo, int64_t npv, int nstage) {
+    using D = BpsDims<L, M, R, P>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const double *urec = REC + ((tile * np + BPS_FRONT) * D::NFA + D::FU) * 32 + lane;   // U fields of row 0
+    const double *qrec = OUT + (tile * npo * D::NFO + D::OB) * 32 + lane;                 // Q part of row 0
+    const double *rin = rhs_in + tile * npv * 32 + lane;
+    double *ro = rhs + tile * npv * 32 + lane;
+    double gt[R * R], tt[R];
+#pragma unroll
+    for (int e = 0; e < R * R; ++e) gt[e] = __ldg(GT + (tile * (R * R) + e) * 32 + lane);
+#pragma unroll
+    for (int a = 0; a < R; ++a) tt[a] = TT[(tile * R + a) * 32 + lane];
+    double uw[L + 1][R];                                   // U rows q .. q+L
+#pragma unroll
+    for (int s = 0; s < L; ++s)
+#pragma unroll
+        for (int a = 0; a < R; ++a) uw[s][a] = __ldg(urec + ((int64_t)s * D::NFA + a) * 32);
+    BpsQtState<L, R> st;
+    bps_qt_init<L, R>(st, gt, tt, [&](int row, int a) { return uw[row][a]; }, [&](int row) { return rin[(int64_t)row * 32]; });
+    Loader<R, D::NFQ, 1, +1, D::NFA, D::NFO, 1> ld;
+    ld.init(urec + (int64_t)L * D::NFA * 32, qrec, rin + (int64_t)L * 32, smem, nstage, n);
+    for (int q = 0; q < n; ++q) {
+        double un[R], qq[D::NFQ], bb[1];
+        ld.acquire(q, un, qq, bb);
+#pragma unroll
+        for (int a = 0; a < R; ++a) uw[L][a] = un[a];
+        const double c = bps_qt_step<L, R>(st, [&](int rel, int a) { return uw[rel][a]; }, qq + D::OV, qq + D::OB, qq[D::OT], bb[0], q == n - 1);
+        ro[(int64_t)q * 32] = c;
+#pragma unroll
+        for (int s = 0; s < L; ++s)
+#pragma unroll
+            for (int a = 0; a < R; ++a) uw[s][a] = uw[s + 1][a];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K8: x <- R \ c with R = triu(B) + triu([alpha beta] [S A'U]', 1)
+// ---------------------------------------------------------------------------------------------------------
+template <int L, int M, int R, int P, template <int, int, int, int, int, int, int> class Loader>
+__global__ void __launch_bounds__(32) bps_bs_kernel(const double *REC, const double *OUT, const double *rhs_in, double *rhs, int n,
+                                                    int64_t np, int64_t npo, int64_t npv, int nstage) {
+    using D = BpsDims<L, M, R, P>;
+    constexpr int LM = L + M, PW = P + R;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const double *srec = REC + ((tile * np + BPS_FRONT + (n - 1)) * D::NFA + D::FS) * 32 + lane;     // S fields of row n-1
+    const double *rrec = OUT + ((tile * npo + (n - 1)) * D::NFO + D::OD) * 32 + lane;                // R part of row n-1
+    const double *rin = rhs_in + (tile * npv + (n - 1)) * 32 + lane;
+    double *ro = rhs + tile * npv * 32 + lane;
+    BpsBsState<LM, PW> st;
+    bps_bs_init<LM, PW>(st);
+    Loader<D::NFRP, P, 1, -1, D::NFO, D::NFA, 1> ld;
+    ld.init(rrec, srec, rin, smem, nstage, n);
+    for (int g = 0; g < n; ++g) {
+        const int j = n - 1 - g;
+        double rp[D::NFRP], sp[P], cc[1], sfull[PW];
+        ld.acquire(g, rp, sp, cc);
+#pragma unroll
+        for (int c = 0; c < P; ++c) sfull[c] = sp[c];
+#pragma unroll
+        for (int a = 0; a < R; ++a) sfull[P + a] = rp[LM + 1 + P + R + a];
+        const double x = bps_bs_step<LM, PW>(st, rp, rp + LM + 1, sfull, cc[0]);
+        ro[(int64_t)j * 32] = x;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// boundary kernels (runtime dims = the padded kernel shape): thread = (tile, row, lane)
+// ---------------------------------------------------------------------------------------------------------
+struct BpsShape { int n, l, m, r, p, tl, tm, tr, tp; };
+
+__global__ void bps_pack_kernel(double *REC, const double *B, int64_t sb, const double *U, const double *V, int64_t suv, const double *W,
+                                const double *S, int64_t sws, BpsShape sh, int64_t nb, int64_t np) {
+    const int lane = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y, tile = blockIdx.y, s = tile * TILE + lane;
+    if (i >= sh.n) return;
+    const int nfa = sh.tl + sh.tm + 1 + 2 * sh.tr + 2 * sh.tp, nfb = sh.tl + sh.tm + 1;
+    double *rec = REC + ((tile * np + BPS_FRONT + i) * nfa) * 32 + lane;
+    const bool live = s < nb;
+    for (int d = 0; d < nfb; ++d) {
+        const int64_t j = i - sh.tl + d;
+        double v = 0.0;
+        if (live) { if (j >= 0 && j < sh.n && j - i <= sh.m && i - j <= sh.l) v = B[s * sb + (sh.m + i - j) + (int64_t)(sh.l + sh.m + 1) * j]; }
+        else v = (d == sh.tl) ? 1.0 : 0.0;       // padding lanes: identity systems
+        rec[d * 32] = v;
+    }
+    for (int a = 0; a < sh.tr; ++a) {
+        rec[(nfb + a) * 32] = (live && a < sh.r) ? U[s * suv + i + (int64_t)sh.n * a] : 0.0;
+        rec[(nfb + sh.tr + a) * 32] = (live && a < sh.r) ? V[s * suv + i + (int64_t)sh.n * a] : 0.0;
+    }
+    for (int c = 0; c < sh.tp; ++c) {
+        rec[(nfb + 2 * sh.tr + c) * 32] = (live && c < sh.p) ? W[s * sws + i + (int64_t)sh.n * c] : 0.0;
+        rec[(nfb + 2 * sh.tr + sh.tp + c) * 32] = (live && c < sh.p) ? S[s * sws + i + (int64_t)sh.n * c] : 0.0;
+    }
+}
+
+__global__ void bps_generate_kernel(double *REC, BpsShape sh, int64_t nb, int64_t np, uint64_t seed) {
+    const int lane = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y, tile = blockIdx.y, s = tile * TILE + lane;
+    if (i >= sh.n) return;
+    const int nfa = sh.tl + sh.tm + 1 + 2 * sh.tr + 2 * sh.tp, nfb = sh.tl + sh.tm + 1;
+    double *rec = REC + ((tile * np + BPS_FRONT + i) * nfa) * 32 + lane;
+    const bool live = s < nb;
+    const uint64_t key = ssm_syskey(seed, (uint64_t)s);
+    const double su = 1.0 / sqrt((double)(sh.r > 0 ? sh.r : 1) * (double)sh.n), sw = 1.0 / sqrt((double)(sh.p > 0 ? sh.p : 1) * (double)sh.n);
+    for (int d = 0; d < nfb; ++d) {
+        const int64_t j = i - sh.tl + d;
+        double v = (d == sh.tl) ? 1.0 : 0.0;
+        if (live) v = (j >= 0 && j < sh.n && j - i <= sh.m && i - j <= sh.l) ? ssm_bps_band_elem(key, sh.n, sh.l, sh.m, (int)(sh.m + i - j), (int)j) : 0.0;
+        rec[d * 32] = v;
+    }
+    for (int a = 0; a < sh.tr; ++a) {
+        rec[(nfb + a) * 32] = (live && a < sh.r) ? ssm_bps_gen_elem(key, 1, sh.n, sh.r, (int)i, a, su) : 0.0;
+        rec[(nfb + sh.tr + a) * 32] = (live && a < sh.r) ? ssm_bps_gen_elem(key, 2, sh.n, sh.r, (int)i, a, su) : 0.0;
+    }
+    for (int c = 0; c < sh.tp; ++c) {
+        rec[(nfb + 2 * sh.tr + c) * 32] = (live && c < sh.p) ? ssm_bps_gen_elem(key, 3, sh.n, sh.p, (int)i, c, sw) : 0.0;
+        rec[(nfb + 2 * sh.tr + sh.tp + c) * 32] = (live && c < sh.p) ? ssm_bps_gen_elem(key, 4, sh.n, sh.p, (int)i, c, sw) : 0.0;
+    }
+}
+
+// factors -> reference layout of the ORIGINAL shape: B (l, l+m) band storage (2l+m+1) x n; U,V n x r; W,S n x (p+r); tau n
+__global__ void bpsqr_unpack_kernel(const double *REC, const double *OUT, double *B, int64_t sb, double *U, double *V, int64_t suv, double *W,
+                                    double *S, int64_t sws, double *tau, int64_t st, BpsShape sh, int64_t nb, int64_t np, int64_t npo) {
+    const int lane = threadIdx.x;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.y + threadIdx.y, tile = blockIdx.y, s = tile * TILE + lane;
+    if (q >= sh.n || s >= nb) return;
+    const int nfa = sh.tl + sh.tm + 1 + 2 * sh.tr + 2 * sh.tp, nfb = sh.tl + sh.tm + 1;
+    const int nfo = sh.tl + sh.tr + 1 + sh.tl + sh.tm + 1 + sh.tp + 2 * sh.tr;
+    const int OB = 0, OV = sh.tl, OT = sh.tl + sh.tr, OD = OT + 1, OWA = OD + sh.tl + sh.tm + 1, OWB = OWA + sh.tp, OSU = OWB + sh.tr;
+    const double *rec = REC + ((tile * np + BPS_FRONT + q) * nfa) * 32 + lane;
+    const double *o = OUT + ((tile * npo + q) * nfo) * 32 + lane;
+    const int mw = sh.l + sh.m, nd = 2 * sh.l + sh.m + 1, n = sh.n;
+    if (B) {
+        for (int t = 0; t <= mw; ++t) if (q + t < n) B[s * sb + (mw - t) + (int64_t)nd * (q + t)] = o[(OD + t) * 32];
+        for (int i = 1; i <= sh.l; ++i) if (q + i < n) B[s * sb + (mw + i) + (int64_t)nd * q] = o[(OB + i - 1) * 32];
+    }
+    for (int a = 0; a < sh.r; ++a) {
+        if (U) U[s * suv + q + (int64_t)n * a] = rec[(nfb + a) * 32];
+        if (V) V[s * suv + q + (int64_t)n * a] = o[(OV + a) * 32];
+        if (W) W[s * sws + q + (int64_t)n * (sh.p + a)] = o[(OWB + a) * 32];
+        if (S) S[s * sws + q + (int64_t)n * (sh.p + a)] = o[(OSU + a) * 32];
+    }
+    for (int c = 0; c < sh.p; ++c) {
+        if (W) W[s * sws + q + (int64_t)n * c] = o[(OWA + c) * 32];
+        if (S) S[s * sws + q + (int64_t)n * c] = rec[(nfb + 2 * sh.tr + sh.tp + c) * 32];
+    }
+    if (tau) tau[s * st + q] = o[OT * 32];
+}
+
+// K9: y = A x (BandedPlusSemiseparableMatrix.jl:21-41); optionally relres = ||b - A x|| / ||b||
+__global__ void __launch_bounds__(32) bps_mul_kernel(const double *REC, const double *x_, double *y_, const double *b_, double *relres, BpsShape sh,
+                                                     int64_t nb, int64_t np, int64_t npv) {
+    const int lane = threadIdx.x;
+    const int64_t tile = blockIdx.x, s = tile * TILE + lane;
+    const int nfa = sh.tl + sh.tm + 1 + 2 * sh.tr + 2 * sh.tp, nfb = sh.tl + sh.tm + 1, n = sh.n;
+    const double *rec = REC + (tile * np + BPS_FRONT) * nfa * 32 + lane;
+    const double *x = x_ + tile * npv * 32 + lane;
+    double Stx[SSM_MAX_RANK], Vtx[SSM_MAX_RANK];
+    for (int c = 0; c < SSM_MAX_RANK; ++c) { Stx[c] = 0.0; Vtx[c] = 0.0; }
+    for (int i = 0; i < n; ++i) { const double xi = x[(int64_t)i * 32];
+        for (int c = 0; c < sh.tp; ++c) Stx[c] = fma(rec[((int64_t)i * nfa + nfb + 2 * sh.tr + sh.tp + c) * 32], xi, Stx[c]); }
+    double num = 0.0, den = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const double *rk = rec + (int64_t)k * nfa * 32;
+        const double xk = x[(int64_t)k * 32];
+        double acc = 0.0;
+        for (int d = 0; d < nfb; ++d) { const int64_t j = k - sh.tl + d; if (j >= 0 && j < n) acc = fma(rk[d * 32], x[j * 32], acc); }
+        for (int c = 0; c < sh.tp; ++c) Stx[c] = fma(-xk, rk[(nfb + 2 * sh.tr + sh.tp + c) * 32], Stx[c]);
+        for (int a = 0; a < sh.tr; ++a) acc = fma(rk[(nfb + a) * 32], Vtx[a], acc);
+        for (int c = 0; c < sh.tp; ++c) acc = fma(rk[(nfb + 2 * sh.tr + c) * 32], Stx[c], acc);
+        for (int a = 0; a < sh.tr; ++a) Vtx[a] = fma(xk, rk[(nfb + sh.tr + a) * 32], Vtx[a]);
+        if (y_) y_[(tile * npv + k) * 32 + lane] = acc;
+        if (b_) { const double bk = b_[(tile * npv + k) * 32 + lane], dl = bk - acc; num = fma(dl, dl, num); den = fma(bk, bk, den); }
+    }
+    if (relres && s < nb) relres[s] = sqrt(num) / sqrt(den);
+}
+
+// ldiv!(UpperTriangular(A), b) on an unfactored BPS (test_bandedplussemiseparable.jl:17)
+__global__ void __launch_bounds__(32) bps_upper_generic_kernel(const double *REC, double *rhs_, BpsShape sh, int64_t np, int64_t npv) {
+    const int lane = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int nfa = sh.tl + sh.tm + 1 + 2 * sh.tr + 2 * sh.tp, nfb = sh.tl + sh.tm + 1, n = sh.n;
+    const double *rec = REC + (tile * np + BPS_FRONT) * nfa * 32 + lane;
+    double *rhs = rhs_ + tile * npv * 32 + lane;
+    double sx[SSM_MAX_RANK];
+    for (int c = 0; c < SSM_MAX_RANK; ++c) sx[c] = 0.0;
+    for (int j = n - 1; j >= 0; --j) {
+        const double *rj = rec + (int64_t)j * nfa * 32;
+        double acc = rhs[(int64_t)j * 32];
+        for (int c = 0; c < sh.tp; ++c) acc = fma(-rj[(nfb + 2 * sh.tr + c) * 32], sx[c], acc);
+        for (int t = 1; t <= sh.tm && j + t < n; ++t) acc = fma(-rj[(sh.tl + t) * 32], rhs[(int64_t)(j + t) * 32], acc);
+        const double xj = acc / rj[sh.tl * 32];
+        rhs[(int64_t)j * 32] = xj;
+        for (int c = 0; c < sh.tp; ++c) sx[c] = fma(rj[(nfb + 2 * sh.tr + sh.tp + c) * 32], xj, sx[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------
+static BpsShape shape_of(const ssm_bps *A) { return BpsShape{A->n, A->l, A->m, A->r, A->p, A->tl, A->tm, A->tr, A->tp}; }
+static BpsShape shape_of(const ssm_bpsqr *F) { return BpsShape{F->n, F->l, F->m, F->r, F->p, F->tl, F->tm, F->tr, F->tp}; }
+static dim3 rows_grid(int n, int64_t ntiles) { return dim3((unsigned)((n + 7) / 8), (unsigned)ntiles); }
+
+int launch_bps_pack(ssm_ctx *c, ssm_bps *A, const double *B, int64_t sb, const double *U, const double *V, int64_t suv, const double *W,
+                    const double *S, int64_t sws) {
+    bps_pack_kernel<<<rows_grid(A->n, A->ntiles), dim3(32, 8), 0, c->stream>>>(A->REC->p, B, sb, U, V, suv, W, S, sws, shape_of(A), A->nb, A->np);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_bps_generate(ssm_ctx *c, ssm_bps *A, uint64_t seed) {
+    bps_generate_kernel<<<rows_grid(A->n, A->ntiles), dim3(32, 8), 0, c->stream>>>(A->REC->p, shape_of(A), A->nb, A->np, seed);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_bpsqr_unpack(ssm_ctx *c, const ssm_bpsqr *F, double *B, int64_t sb, double *U, double *V, int64_t suv, double *W, double *S,
+                        int64_t sws, double *tau, int64_t st) {
+    bpsqr_unpack_kernel<<<rows_grid(F->n, F->ntiles), dim3(32, 8), 0, c->stream>>>(F->REC->p, F->OUT->p, B, sb, U, V, suv, W, S, sws, tau, st,
+                                                                                    shape_of(F), F->nb, F->np, F->npo);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int L, int M, int R, int P>
+static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
+    using D = BpsDims<L, M, R, P>;
+    bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)A->ntiles, 128, 0, c->stream>>>(A->REC->p, nullptr, F->GT->p, nullptr, A->n, A->np, 0);
+    c->launches++;
+    const size_t smem = WindowRing<D::NFA, BPS_NST>::smem_bytes();
+    auto kern = bps_qr_kernel<L, M, R, P>;
+    SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_bps_qr(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
+#define X(L_, M_, R_, P_) if (A->tl == L_ && A->tm == M_ && A->tr == R_ && A->tp == P_) return qr_shape<L_, M_, R_, P_>(c, A, F);
+    SSM_BPS_SHAPES(X)
+#undef X
+    set_error("no BPS kernel for padded shape (%d,%d,%d,%d)", A->tl, A->tm, A->tr, A->tp);
+    return SSM_E_UNSUPPORTED;
+}
+
+static int bps_stages(const ssm_ctx *c, size_t stage_bytes) {
+    if (c->pipeline_stages > 0) return c->pipeline_stages;
+    int s = (int)(24000 / (stage_bytes + 8));
+    return s < 2 ? 2 : (s > 8 ? 8 : s);
+}
+
+template <int L, int M, int R, int P>
+static int qt_shape(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs, int64_t npv) {
+    using D = BpsDims<L, M, R, P>;
+    bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)F->ntiles, 128, 0, c->stream>>>(F->REC->p, rhs_in, nullptr, F->TT->p, F->n, F->np, npv);
+    c->launches++;
+    if (c->ab_variant == 1) {
+        bps_qt_kernel<L, M, R, P, DirectLoader><<<(unsigned)F->ntiles, 32, 0, c->stream>>>(F->REC->p, F->OUT->p, F->GT->p, F->TT->p, rhs_in, rhs, F->n,
+                                                                                           F->np, F->npo, npv, 0);
+    } else {
+        using LD = RingLoader<R, D::NFQ, 1, +1, D::NFA, D::NFO, 1>;
+        const int ns = bps_stages(c, LD::STAGE_BYTES);
+        const size_t smem = LD::smem_bytes(ns);
+        auto kern = bps_qt_kernel<L, M, R, P, RingLoader>;
+        if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)F->ntiles, 32, smem, c->stream>>>(F->REC->p, F->OUT->p, F->GT->p, F->TT->p, rhs_in, rhs, F->n, F->np, F->npo, npv, ns);
+    }
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+template <int L, int M, int R, int P>
+static int bs_shape(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs, int64_t npv) {
+    using D = BpsDims<L, M, R, P>;
+    if (c->ab_variant == 1) {
+        bps_bs_kernel<L, M, R, P, DirectLoader><<<(unsigned)F->ntiles, 32, 0, c->stream>>>(F->REC->p, F->OUT->p, rhs_in, rhs, F->n, F->np, F->npo, npv, 0);
+    } else {
+        using LD = RingLoader<D::NFRP, P, 1, -1, D::NFO, D::NFA, 1>;
+        const int ns = bps_stages(c, LD::STAGE_BYTES);
+        const size_t smem = LD::smem_bytes(ns);
+        auto kern = bps_bs_kernel<L, M, R, P, RingLoader>;
+        if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)F->ntiles, 32, smem, c->stream>>>(F->REC->p, F->OUT->p, rhs_in, rhs, F->n, F->np, F->npo, npv, ns);
+    }
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_bps_qt(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs) {
+    const int64_t npv = (int64_t)F->n + PAD;
+#define X(L_, M_, R_, P_) if (F->tl == L_ && F->tm == M_ && F->tr == R_ && F->tp == P_) return qt_shape<L_, M_, R_, P_>(c, F, rhs_in, rhs, npv);
+    SSM_BPS_SHAPES(X)
+#undef X
+    return SSM_E_UNSUPPORTED;
+}
+int launch_bps_backsolve(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs) {
+    const int64_t npv = (int64_t)F->n + PAD;
+#define X(L_, M_, R_, P_) if (F->tl == L_ && F->tm == M_ && F->tr == R_ && F->tp == P_) return bs_shape<L_, M_, R_, P_>(c, F, rhs_in, rhs, npv);
+    SSM_BPS_SHAPES(X)
+#undef X
+    return SSM_E_UNSUPPORTED;
+}
+int launch_bps_mul(ssm_ctx *c, const ssm_bps *A, const double *x, double *y, const double *b, double *relres) {
+    bps_mul_kernel<<<(unsigned)A->ntiles, 32, 0, c->stream>>>(A->REC->p, x, y, b, relres, shape_of(A), A->nb, A->np, (int64_t)A->n + PAD);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_bps_upper_ldiv(ssm_ctx *c, const ssm_bps *A, double *rhs) {
+    bps_upper_generic_kernel<<<(unsigned)A->ntiles, 32, 0, c->stream>>>(A->REC->p, rhs, shape_of(A), A->np, (int64_t)A->n + PAD);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ssm

@@ -90,7 +90,38 @@ struct ssm_abqr {
     ssm::DevBufPtr V;           // shared with the operand batch (never written by the path)
 };
 
+// BandedPlusSemiseparable operands.  (l,m,r,p) is the caller's shape; (tl,tm,tr,tp) >= it is the compiled kernel
+// shape the batch is zero-padded to (a BPS matrix with zero extra bands / generator columns is the same matrix).
+struct ssm_bps {
+    ssm_ctx *ctx; int n, l, m, r, p, tl, tm, tr, tp; int64_t nb, ntiles, np;
+    ssm::DevBufPtr REC;         // [ntiles][np][nfa][32], record (FRONT + row): B0 row (tl+tm+1) | U (tr) | V (tr) | W (tp) | S (tp)
+};
+struct ssm_bpsqr {
+    ssm_ctx *ctx; int n, l, m, r, p, tl, tm, tr, tp; int64_t nb, ntiles, np, npo;
+    ssm::DevBufPtr REC;         // shared with the operand batch (U and S[:,1:p] are part of the factorisation)
+    ssm::DevBufPtr OUT;         // [ntiles][npo][nfo][32], record row: tail (tl) | Vnew (tr) | tau || pivot,d (tl+tm+1) | alpha (tp) | beta (tr) | A'U (tr)
+    ssm::DevBufPtr GT;          // [ntiles][tr*tr][32]  U'U of each system
+    ssm::DevBufPtr TT;          // [ntiles][tr][32]     U'b scratch of lmul!(Q', b)
+};
+
 namespace ssm {
+
+constexpr int BPS_FRONT = 8;    // zero records in front of row 0 (the sweep looks tm <= 8 rows back)
+
+// bps_kernels.cu
+bool bps_pick_shape(int l, int m, int r, int p, int *tl, int *tm, int *tr, int *tp);
+int bps_nfa(int tl, int tm, int tr, int tp);
+int bps_nfo(int tl, int tm, int tr, int tp);
+int launch_bps_pack(ssm_ctx *c, ssm_bps *A, const double *B, int64_t sb, const double *U, const double *V, int64_t suv,
+                    const double *W, const double *S, int64_t sws);
+int launch_bps_generate(ssm_ctx *c, ssm_bps *A, uint64_t seed);
+int launch_bps_qr(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F);
+int launch_bpsqr_unpack(ssm_ctx *c, const ssm_bpsqr *F, double *B, int64_t sb, double *U, double *V, int64_t suv, double *W,
+                        double *S, int64_t sws, double *tau, int64_t st);
+int launch_bps_qt(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs);
+int launch_bps_backsolve(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs);
+int launch_bps_mul(ssm_ctx *c, const ssm_bps *A, const double *x, double *y, const double *b, double *relres);
+int launch_bps_upper_ldiv(ssm_ctx *c, const ssm_bps *A, double *rhs);
 
 // kernel-argument bundles (plain pointers; passed by value)
 struct AbArgs {

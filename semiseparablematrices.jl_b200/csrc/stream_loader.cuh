@@ -53,7 +53,8 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 
 // ---- DirectLoader -------------------------------------------------------------------------------------
-template <int NF0, int NF1, int NF2, int DIR>
+// STRs = distance between consecutive records of stream s, in fields (default: dense records, STRs = NFs)
+template <int NF0, int NF1, int NF2, int DIR, int STR0 = NF0, int STR1 = NF1, int STR2 = NF2>
 struct DirectLoader {
     const double *p0, *p1, *p2;   // lane-adjusted pointers to record (OFFs) of each stream
     int64_t nsteps;
@@ -66,7 +67,7 @@ struct DirectLoader {
         for (int f = 0; f < NF1; ++f) n1[f] = p1[f * 32];
 #pragma unroll
         for (int f = 0; f < NF2; ++f) n2[f] = p2[f * 32];
-        p0 += DIR * NF0 * 32; p1 += DIR * NF1 * 32; p2 += DIR * NF2 * 32;
+        p0 += DIR * STR0 * 32; p1 += DIR * STR1 * 32; p2 += DIR * STR2 * 32;
     }
     __device__ __forceinline__ void init(const double *b0, const double *b1, const double *b2, void *, int, int64_t total_steps) {
         p0 = b0; p1 = b1; p2 = b2; nsteps = total_steps;
@@ -85,7 +86,7 @@ struct DirectLoader {
 };
 
 // ---- RingLoader ---------------------------------------------------------------------------------------
-template <int NF0, int NF1, int NF2, int DIR>
+template <int NF0, int NF1, int NF2, int DIR, int STR0 = NF0, int STR1 = NF1, int STR2 = NF2>
 struct RingLoader {
     static constexpr int STAGE_DOUBLES = (NF0 + NF1 + NF2) * 32;
     static constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
@@ -106,9 +107,9 @@ struct RingLoader {
         const uint32_t bar = bar0 + 8u * s;
         double *dst = ring + (size_t)s * STAGE_DOUBLES;
         mbar_expect_tx(bar, STAGE_BYTES);
-        if (NF0 > 0) bulk_g2s(smem_u32(dst), g0 + (int64_t)DIR * g * NF0 * 32, NF0 * 256, bar);
-        if (NF1 > 0) bulk_g2s(smem_u32(dst + NF0 * 32), g1 + (int64_t)DIR * g * NF1 * 32, NF1 * 256, bar);
-        if (NF2 > 0) bulk_g2s(smem_u32(dst + (NF0 + NF1) * 32), g2 + (int64_t)DIR * g * NF2 * 32, NF2 * 256, bar);
+        if (NF0 > 0) bulk_g2s(smem_u32(dst), g0 + (int64_t)DIR * g * STR0 * 32, NF0 * 256, bar);
+        if (NF1 > 0) bulk_g2s(smem_u32(dst + NF0 * 32), g1 + (int64_t)DIR * g * STR1 * 32, NF1 * 256, bar);
+        if (NF2 > 0) bulk_g2s(smem_u32(dst + (NF0 + NF1) * 32), g2 + (int64_t)DIR * g * STR2 * 32, NF2 * 256, bar);
     }
     // b0..b2: lane-adjusted pointers as for DirectLoader (lane offset removed here)
     __device__ __forceinline__ void init(const double *b0, const double *b1, const double *b2, void *smem, int nst,
@@ -141,6 +142,51 @@ struct RingLoader {
         __syncwarp();   // every lane has its copy in registers before the stage is re-armed
         if (lane == 0 && g + nstage < nsteps) issue(g + nstage, s);
         if (++cur == nstage) { cur = 0; parity ^= 1u; }
+    }
+};
+
+// dense-record aliases (usable as 4-parameter template template arguments)
+template <int NF0, int NF1, int NF2, int DIR> using DirectLoaderD = DirectLoader<NF0, NF1, NF2, DIR>;
+template <int NF0, int NF1, int NF2, int DIR> using RingLoaderD = RingLoader<NF0, NF1, NF2, DIR>;
+
+// ---- WindowRing ---------------------------------------------------------------------------------------
+// A sliding window of whole records that stay in shared memory while the sweep needs them (the BPS sweep looks
+// M rows back and L rows ahead).  Record k of the sequence lives in slot k mod NST (NST a power of two) from
+// the moment its bulk copy lands until release(k) re-arms the slot with record k+NST.  Lanes read fields in
+// place: rec(k)[f*32] is conflict-free (lane-fastest records).
+template <int NF, int NST>
+struct WindowRing {
+    static_assert((NST & (NST - 1)) == 0, "NST must be a power of two");
+    static constexpr uint32_t REC_BYTES = NF * 256;
+    const double *g;      // tile base of record 0 of the sequence (not lane adjusted)
+    double *ring;
+    uint32_t bar0;
+    int lane;
+    int64_t nseq;
+    static __host__ __device__ size_t smem_bytes() { return (size_t)NST * REC_BYTES + (size_t)NST * 8; }
+    __device__ __forceinline__ void issue(int64_t k) {
+        const int s = (int)(k & (NST - 1));
+        const uint32_t bar = bar0 + 8u * s;
+        mbar_expect_tx(bar, REC_BYTES);
+        bulk_g2s(smem_u32(ring + (size_t)s * NF * 32), g + k * NF * 32, REC_BYTES, bar);
+    }
+    __device__ __forceinline__ void init(const double *tile_first_record, void *smem, int64_t total) {
+        lane = threadIdx.x & 31;
+        g = tile_first_record; nseq = total;
+        ring = reinterpret_cast<double *>(smem);
+        bar0 = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)NST * REC_BYTES);
+        if (lane == 0) {
+            for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8u * s, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        if (lane == 0) for (int64_t k = 0; k < NST && k < total; ++k) issue(k);
+    }
+    __device__ __forceinline__ void wait(int64_t k) { mbar_wait(bar0 + 8u * (uint32_t)(k & (NST - 1)), (uint32_t)((k / NST) & 1)); }
+    __device__ __forceinline__ const double *rec(int64_t k) const { return ring + (size_t)(k & (NST - 1)) * NF * 32 + lane; }
+    __device__ __forceinline__ void release(int64_t k) {
+        __syncwarp();
+        if (lane == 0 && k + NST < nseq) issue(k + NST);
     }
 };
 

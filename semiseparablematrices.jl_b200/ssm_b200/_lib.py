@@ -73,6 +73,7 @@ _SIGS = {
     "ssm_bpsqr_lmul_qt": (C.c_int, [c_vp, c_vp]),
     "ssm_bpsqr_upper_ldiv": (C.c_int, [c_vp, c_vp]),
     "ssm_bpsqr_ldiv": (C.c_int, [c_vp, c_vp]),
+    "ssm_bpsqr_solve": (C.c_int, [c_vp, c_vp, c_vp]),
     "ssm_bps_mul": (C.c_int, [c_vp, c_vp, c_vp]),
     "ssm_bps_residual": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ssm_bps_upper_ldiv": (C.c_int, [c_vp, c_vp]),

@@ -91,3 +91,35 @@ def R_from_factors(F, Uf, V, l, ub):
 
 def relerr(x, ref):
     return float(np.linalg.norm(np.asarray(x) - np.asarray(ref)) / np.linalg.norm(ref))
+
+
+def bps_zero_corners(B, l, m):
+    n = B.shape[-2]
+    for j in range(n):
+        for d in range(l + m + 1):
+            k = j + d - m
+            if k < 0 or k >= n:
+                B[..., j, d] = 0.0
+    return B
+
+
+def bps_randn(rng, n, l, m, r, p, nb=None, dominant=0.0):
+    """brandn(n,n,l,m) band + randn generators (test_qr.jl:6-12); `dominant` adds to |diag| to tame conditioning."""
+    lead = () if nb is None else (nb,)
+    B = bps_zero_corners(rng.standard_normal(lead + (n, l + m + 1)), l, m)
+    if dominant:
+        B[..., m] += dominant * np.sign(B[..., m])
+    U = rng.standard_normal(lead + (r, n)); V = rng.standard_normal(lead + (r, n))
+    W = rng.standard_normal(lead + (p, n)); S = rng.standard_normal(lead + (p, n))
+    b = rng.standard_normal(lead + (n,))
+    return B, U, V, W, S, b
+
+
+def explicit_qt(qr_, tau, b):
+    """test_qr.jl:40-46: apply (I - tau_i y y') for i = 1..n-1 with y = e_i + F[i+1:n, i]."""
+    n = len(b)
+    out = np.array(b, dtype=float)
+    for i in range(n - 1):
+        y = np.zeros(n); y[i] = 1.0; y[i + 1:] = qr_[i + 1:, i]
+        out = out - tau[i] * y * (y @ out)
+    return out

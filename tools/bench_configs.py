@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's bench contract): the other BASELINE.json configs on ONE GPU.
+
+  python tools/bench_configs.py c3            BPS QR, n=4096, l=m=3, r=p=2, 16,384 systems  (configs[2])
+  python tools/bench_configs.py c5            almost-banded sweep n=256..8192, 1M systems total (configs[4]), this GPU's share
+  python tools/bench_configs.py c2 [--variant V --stages S]   per-kernel timing of config 2 (tuning aid)
+
+Prints one JSON line per measurement; timing = CUDA events on the library's stream, 3 warm-ups, mean of `--steps`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT, ROOT / "semiseparablematrices.jl_b200"):
+    sys.path.insert(0, str(p))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import ssm_b200 as ssm  # noqa: E402
+from ssm_b200 import bps  # noqa: E402
+
+PEAK = 6544.3
+try:
+    PEAK = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, steps, warm=3):
+    stream = torch.cuda.current_stream()
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def c3(args, ctx):
+    n, l, m, r, p, nb, seed = 4096, 3, 3, 2, 2, args.nb or 16384, 20261019 + 2
+    A = bps.BandedPlusSemiseparableMatrix.generate(n, l, m, r, p, nb, seed, ctx=ctx)
+    b = ssm.Vec(ctx, n, nb).generate(seed, array_id=5)
+    x = ssm.Vec(ctx, n, nb)
+    F = bps.qr(A)
+    t_qr = timeit(lambda: F.refactor(A), args.steps)
+    t_sv = timeit(lambda: F.solve(b, out=x), args.steps)
+    rr = A.residual(x, b)
+    qr_bytes = 8 * n * (3 * l + 2 * m + 5 * r + 3 * p + 3) * nb
+    sv_bytes = 8 * n * (2 * l + m + 4 * r + 2 * p + 4) * nb
+    print(json.dumps({"config": "c3 BPS qr n=4096 l=m=3 r=p=2", "systems": nb, "qr_ms": t_qr, "solve_ms": t_sv,
+                      "qr_systems_per_s": nb / (t_qr * 1e-3), "qr_GBps_algorithmic": qr_bytes / t_qr / 1e6, "qr_frac_of_measured_peak": qr_bytes / t_qr / 1e6 / PEAK,
+                      "solve_GBps_algorithmic": sv_bytes / t_sv / 1e6, "solve_frac_of_measured_peak": sv_bytes / t_sv / 1e6 / PEAK,
+                      "relres_max": float(rr.max()), "relres_median": float(np.median(rr))}))
+
+
+def c2(args, ctx):
+    n, l, u, r, nb, seed = args.n or 1024, 2, 2, 2, args.nb or 65536, 20261019 + 1
+    A = ssm.AlmostBandedMatrix.generate(n, l, u, r, nb, seed, ctx=ctx)
+    b = ssm.Vec(ctx, n, nb).generate(seed)
+    x = ssm.Vec(ctx, n, nb)
+    F = ssm.qr(A)
+    t_qr = timeit(lambda: F.refactor(A), args.steps)
+    t_sv = timeit(lambda: F.solve(b, out=x), args.steps)
+    t_fused = timeit(lambda: A.solve(b, out=x), args.steps)
+    rr = A.residual(x, b)
+    qr_bytes = 8 * n * (3 * l + 2 * u + 3 * r + 3) * nb
+    sv_bytes = 8 * n * (2 * l + u + 2 * r + 4) * nb
+    fused_bytes = 8 * n * (l + u + 2 * r + 3) * nb
+    print(json.dumps({"config": f"almost-banded n={n} l=u=2 r=2", "systems": nb, "variant": args.variant, "stages": args.stages,
+                      "qr_ms": t_qr, "ldiv_ms": t_sv, "fused_solve_ms": t_fused, "qr_plus_ldiv_systems_per_s": nb / ((t_qr + t_sv) * 1e-3),
+                      "qr_frac": qr_bytes / t_qr / 1e6 / PEAK, "ldiv_frac": sv_bytes / t_sv / 1e6 / PEAK,
+                      "qr_plus_ldiv_frac": (qr_bytes + sv_bytes) / (t_qr + t_sv) / 1e6 / PEAK,
+                      "fused_strict_frac": fused_bytes / t_fused / 1e6 / PEAK, "fused_systems_per_s": nb / (t_fused * 1e-3),
+                      "relres_max": float(rr.max())}))
+
+
+def c5(args, ctx):
+    """configs[4]: n = 256 .. 8192, 2^20 systems in total; this GPU's share = total / world (default world=1)."""
+    groups = [(256, 524288), (512, 262144), (1024, 131072), (2048, 65536), (4096, 32768), (8192, 32768)]
+    tot_sys, tot_ms = 0, 0.0
+    for n, nbt in groups:
+        nb = nbt // args.world
+        args.n, args.nb = n, nb
+        A = ssm.AlmostBandedMatrix.generate(n, 2, 2, 2, nb, 20261019 + 4, ctx=ctx)
+        b = ssm.Vec(ctx, n, nb).generate(20261019 + 4)
+        x = ssm.Vec(ctx, n, nb)
+        F = ssm.qr(A)
+        t = timeit(lambda: (F.refactor(A), F.solve(b, out=x)), args.steps)
+        rr = A.residual(x, b)
+        byts = 8 * n * 33 * nb
+        print(json.dumps({"config": "c5", "n": n, "systems": nb, "ms": t, "systems_per_s": nb / (t * 1e-3), "frac_of_measured_peak": byts / t / 1e6 / PEAK,
+                          "relres_max": float(rr.max())}))
+        tot_sys += nb; tot_ms += t
+        del A, b, x, F
+    print(json.dumps({"config": "c5 total", "systems": tot_sys, "ms": tot_ms, "systems_per_s": tot_sys / (tot_ms * 1e-3)}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", choices=["c2", "c3", "c5"])
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--nb", type=int, default=0)
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--world", type=int, default=1)
+    args = ap.parse_args()
+    ctx = ssm.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    if args.variant:
+        ctx.set_option("ab_variant", args.variant)
+    if args.stages:
+        ctx.set_option("pipeline_stages", args.stages)
+    {"c2": c2, "c3": c3, "c5": c5}[args.which](args, ctx)
