@@ -1,0 +1,282 @@
+# SemiseparableB200.jl — Julia glue that routes SemiseparableMatrices.jl's structured QR / solve hot path into
+# libssmb200.so (C ABI: include/ssm_b200.h) through `ccall`.  Load it AFTER `using SemiseparableMatrices`:
+#
+#     using SemiseparableMatrices; include("SemiseparableB200.jl"); using .SemiseparableB200
+#
+# It only adds more specific methods (Float64 element type, Matrix storage) for the generic functions the
+# reference already extends, so `qr(A)`, `ldiv!(F, b)`, `F \ b`, `A \ b`, `F.Q' * b`, `F.R \ b` keep their
+# names, argument meaning, return types and error behaviour.  There is no CPU fallback: if the library cannot
+# be loaded the first call throws.  NOTE: no `julia` binary exists in the build image, so this file is not
+# executed by the test-suite; the ctypes twin (ssm_b200/_lib.py) binds the same symbols 1:1 and IS tested.
+#
+# Overridden reference methods (file:line in the reference's src/):
+#   _almostbanded_qr(_, A)                             AlmostBandedMatrix.jl:130-133  (widen + qr!)
+#   _almostbanded_qr!(A, τ)                            AlmostBandedMatrix.jl:135-172
+#   ldiv!(::QR{<:Any,<:AlmostBandedMatrix}, ::Vector / ::Matrix)   AlmostBandedMatrix.jl:187-199
+#   materialize!(MatLdivVec{TriangularLayout{'U',·,AlmostBandedLayout}})   AlmostBandedMatrix.jl:242-256
+#   qr(::BandedPlusSemiseparableMatrix)                semiseparableqr.jl:128-131
+#   lmul!(::AdjointQ{…QRPackedQ{…BPS}}, ::StridedVector)            semiseparableqr.jl:863-905
+#   ldiv!(::UpperTriangular{…BPS}, ::StridedVector)    BandedPlusSemiseparableMatrix.jl:53-70
+#   batched extras (no reference equivalent; a batch is a Vector of matrices): qr_batch, solve_batch
+module SemiseparableB200
+
+using LinearAlgebra, BandedMatrices, LazyArrays, ArrayLayouts, MatrixFactorizations
+using SemiseparableMatrices
+import SemiseparableMatrices: AlmostBandedMatrix, AlmostBandedLayout, BandedPlusSemiseparableMatrix, bandpart, fillpart,
+                              almostbandwidths, _almostbanded_qr, _almostbanded_qr!
+import LinearAlgebra: qr, ldiv!, lmul!, AdjointQ
+import MatrixFactorizations: QR, QRPackedQ
+import ArrayLayouts: materialize!, MatLdivVec, TriangularLayout, triangulardata
+import LazyArrays: arguments
+
+const libssm = get(ENV, "SSM_B200_LIB", joinpath(@__DIR__, "..", "lib", "libssmb200.so"))
+
+const Ctx = Ptr{Cvoid}
+const DEVICE = Ref{Cint}(parse(Cint, get(ENV, "SSM_B200_DEVICE", "0")))
+const CTX = Ref{Ctx}(C_NULL)
+
+struct SSMError <: Exception
+    code::Cint
+    msg::String
+end
+Base.showerror(io::IO, e::SSMError) = print(io, "libssmb200 error ", e.code, ": ", e.msg)
+
+last_error() = unsafe_string(ccall((:ssm_last_error, libssm), Cstring, ()))
+
+# status -> exception, as the reference throws (include/ssm_b200.h "Return value")
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = last_error()
+    rc == -2 && throw(DimensionMismatch(msg))                       # SSM_E_SHAPE
+    rc == -4 && throw(ErrorException(msg))                          # SSM_E_STATE (semiseparableqr.jl:105-107)
+    rc < 0 && throw(ArgumentError(msg))
+    throw(SSMError(rc, msg))                                        # CUDA runtime failure
+end
+
+function context()
+    if CTX[] == C_NULL
+        h = Ref{Ctx}(C_NULL)
+        check(ccall((:ssm_ctx_create, libssm), Cint, (Cint, Ptr{Ctx}), DEVICE[], h))
+        CTX[] = h[]
+        atexit(() -> (CTX[] != C_NULL && ccall((:ssm_ctx_destroy, libssm), Cint, (Ctx,), CTX[]); CTX[] = C_NULL))
+    end
+    CTX[]
+end
+
+# ---- thin RAII wrappers around the opaque handles -------------------------------------------------------------------
+mutable struct Handle
+    p::Ptr{Cvoid}
+    destroy::Symbol
+    function Handle(p, destroy)
+        h = new(p, destroy)
+        finalizer(x -> x.p != C_NULL && _destroy(x), h)
+        h
+    end
+end
+function _destroy(h::Handle)
+    if h.destroy === :ab;        ccall((:ssm_ab_destroy, libssm), Cint, (Ptr{Cvoid},), h.p)
+    elseif h.destroy === :abqr;  ccall((:ssm_abqr_destroy, libssm), Cint, (Ptr{Cvoid},), h.p)
+    elseif h.destroy === :bps;   ccall((:ssm_bps_destroy, libssm), Cint, (Ptr{Cvoid},), h.p)
+    elseif h.destroy === :bpsqr; ccall((:ssm_bpsqr_destroy, libssm), Cint, (Ptr{Cvoid},), h.p)
+    elseif h.destroy === :vec;   ccall((:ssm_vec_destroy, libssm), Cint, (Ptr{Cvoid},), h.p)
+    end
+    h.p = C_NULL
+    nothing
+end
+
+function device_vec(b::AbstractVector{Float64}, nb::Integer=1)
+    n = length(b) ÷ nb
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ssm_vec_create, libssm), Cint, (Ctx, Cint, Int64, Ptr{Ptr{Cvoid}}), context(), n, nb, h))
+    v = Handle(h[], :vec)
+    GC.@preserve b check(ccall((:ssm_vec_set, libssm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), v.p, pointer(b), 0))
+    v
+end
+fetch_vec!(b::AbstractVector{Float64}, v::Handle) =
+    GC.@preserve b check(ccall((:ssm_vec_get, libssm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), v.p, pointer(b), 0))
+
+# ---- AlmostBandedMatrix ---------------------------------------------------------------------------------------------
+const DenseAB = AlmostBandedMatrix{Float64,Matrix{Float64},Matrix{Float64},Matrix{Float64}}
+
+# operands in the reference layout: bands.data is (l+u+1) x n column-major, U is n x r, V is r x n
+function upload(bdata::Matrix{Float64}, U::Matrix{Float64}, V::Matrix{Float64}, l::Integer, u::Integer)
+    n = size(bdata, 2); r = size(U, 2)
+    (size(bdata, 1) == l + u + 1 && size(U, 1) == n && size(V) == (r, n)) ||
+        error("Data and fill must be compatible size")                                   # AlmostBandedMatrix.jl:14-16
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ssm_ab_create, libssm), Cint, (Ctx, Cint, Cint, Cint, Cint, Int64, Ptr{Ptr{Cvoid}}), context(), n, l, u, r, 1, h))
+    A = Handle(h[], :ab)
+    GC.@preserve bdata U V check(ccall((:ssm_ab_set, libssm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64), A.p, pointer(bdata), 0, pointer(U), 0, pointer(V), 0))
+    A
+end
+
+# qr on the device, then F.factors / F.τ written straight into reference-layout storage:
+#   factors: (2l+u+1) x n band data with bandwidths (l, l+u); U: n x r (overwritten); τ: n
+function device_qr!(fdata::Matrix{Float64}, Uout::Matrix{Float64}, τ::Vector{Float64}, A::Handle)
+    f = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ssm_ab_qr, libssm), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), A.p, f))
+    F = Handle(f[], :abqr)
+    GC.@preserve fdata Uout τ check(ccall((:ssm_abqr_get, libssm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64), F.p, pointer(fdata), 0, pointer(Uout), 0, pointer(τ), 0))
+    F
+end
+
+# device factor objects of live QR results, so ldiv!(F, b) does not re-upload the factors (WeakKeyDict: freed with F.factors)
+const FACTORS = WeakKeyDict{Any,Tuple{Handle,Handle}}()
+
+# qr(A) / factorize(A) / A \ b  (AlmostBandedMatrix.jl:125-133).  A is not mutated (test_almostbanded.jl:146).
+function _almostbanded_qr(_, A::DenseAB)
+    l, u = almostbandwidths(A)
+    B, L = bandpart(A), fillpart(A)
+    U, V = arguments(L)
+    n = size(A, 2)
+    size(A, 1) == n || return invoke(_almostbanded_qr, Tuple{Any,Any}, nothing, A)        # rectangular: reference path
+    dA = upload(Matrix(B.data), Matrix(U), Matrix(V), l, u)
+    R = AlmostBandedMatrix{Float64}(undef, (n, n), (l, l + u), size(U, 2))                # widened result (:30-38)
+    Rb, RL = bandpart(R), fillpart(R)
+    RU, RV = arguments(RL)
+    copyto!(RV, V)
+    τ = zeros(Float64, n)
+    dF = device_qr!(Rb.data, RU, τ, dA)
+    F = QR(R, τ)
+    FACTORS[R] = (dA, dF)
+    F
+end
+
+# in-place form (:135-172): A already widened to (l, l+u) by the caller, bands u+1..l+u hold the fill values
+function _almostbanded_qr!(A::DenseAB, τ::Vector{Float64})
+    B, L = bandpart(A), fillpart(A)
+    l, ū = bandwidths(B)
+    u = ū - l
+    (u >= 0 && size(A, 1) == size(A, 2)) || return invoke(_almostbanded_qr!, Tuple{AbstractMatrix{Float64},AbstractVector{Float64}}, A, τ)
+    U, V = arguments(L)
+    dA = upload(B.data[l+1:end, :], U, V, l, u)                   # rows of bands -l..u of the widened storage
+    dF = device_qr!(B.data, U, τ, dA)
+    FACTORS[A] = (dA, dF)
+    A, τ
+end
+
+function device_factor(F::QR{<:Any,<:DenseAB})
+    get!(FACTORS, F.factors) do
+        # a factor object built elsewhere (e.g. deserialised): re-create the device copy from its reference-layout fields
+        error("SemiseparableB200: factorisation was not produced by the B200 path; call qr(A) again")
+    end
+end
+
+# ldiv!(F, b) (:187-192) and the matrix right-hand side form (:194-199), in place, returns b
+function ldiv!(F::QR{<:Any,<:DenseAB}, b::Vector{Float64})
+    _, dF = device_factor(F)
+    length(b) == size(F.factors, 1) || throw(DimensionMismatch("right-hand side has length $(length(b)), matrix has $(size(F.factors,1)) rows"))
+    v = device_vec(b)
+    check(ccall((:ssm_abqr_ldiv, libssm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dF.p, v.p))
+    fetch_vec!(b, v)
+    b
+end
+function ldiv!(F::QR{<:Any,<:DenseAB}, B::Matrix{Float64})
+    for j in axes(B, 2)
+        col = B[:, j]
+        ldiv!(F, col)
+        B[:, j] = col
+    end
+    B
+end
+
+# ldiv!(UpperTriangular(R), b) / UnitUpperTriangular on a FACTORED object (:215-256)
+for (UNIT, unitflag) in (('N', 0), ('U', 1))
+    @eval function materialize!(M::MatLdivVec{TriangularLayout{'U',$UNIT,AlmostBandedLayout},<:Any,<:Any,<:Vector{Float64}})
+        R, x = M.A, M.B
+        A = triangulardata(R)
+        A isa DenseAB || return invoke(materialize!, Tuple{MatLdivVec{TriangularLayout{'U',$UNIT,AlmostBandedLayout}}}, M)
+        l, u = almostbandwidths(A)
+        U, V = arguments(fillpart(A))
+        dA = upload(Matrix(bandpart(A).data), Matrix(U), Matrix(V), l, u)
+        v = device_vec(x)
+        check(ccall((:ssm_ab_tri_ldiv, libssm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), dA.p, v.p, 1, $unitflag))
+        fetch_vec!(x, v)
+        x
+    end
+end
+
+# ---- batched entry points (no reference equivalent; same-shaped systems stacked along the last axis) -----------------
+"""
+    solve_batch(bands::Array{Float64,3}, U::Array{Float64,3}, V::Array{Float64,3}, b::Matrix{Float64}, (l,u)) -> x
+
+`x[:,s] = AlmostBandedMatrix(bands[:,:,s], U[:,:,s]*V[:,:,s]) \\ b[:,s]` for every system s, through the chunk-pipelined
+host path `ssm_ab_solve_host` (H2D + pack + qr + ldiv! + D2H).
+"""
+function solve_batch(bands::Array{Float64,3}, U::Array{Float64,3}, V::Array{Float64,3}, b::Matrix{Float64}, (l, u))
+    w, n, nb = size(bands)
+    r = size(U, 2)
+    (w == l + u + 1 && size(U) == (n, r, nb) && size(V) == (r, n, nb) && size(b) == (n, nb)) ||
+        throw(DimensionMismatch("Data and fill must be compatible size"))
+    x = similar(b)
+    GC.@preserve bands U V b x check(ccall((:ssm_ab_solve_host, libssm), Cint,
+        (Ctx, Cint, Cint, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        context(), n, l, u, r, nb, pointer(bands), pointer(U), pointer(V), pointer(b), pointer(x)))
+    x
+end
+
+# ---- BandedPlusSemiseparableMatrix ----------------------------------------------------------------------------------
+const BPSFACTORS = WeakKeyDict{Any,Tuple{Handle,Handle}}()
+
+function upload(A::BandedPlusSemiseparableMatrix{Float64})
+    n = size(A, 1); l, m = bandwidths(A.B); r = size(A.U, 2); p = size(A.W, 2)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ssm_bps_create, libssm), Cint, (Ctx, Cint, Cint, Cint, Cint, Cint, Int64, Ptr{Ptr{Cvoid}}), context(), n, l, m, r, p, 1, h))
+    dA = Handle(h[], :bps)
+    Bd = A.B.data
+    GC.@preserve A check(ccall((:ssm_bps_set, libssm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+        dA.p, pointer(Bd), 0, pointer(A.U), pointer(A.V), 0, pointer(A.W), pointer(A.S), 0))
+    dA
+end
+
+# qr(A) (semiseparableqr.jl:128-131): QR(BandedPlusSemiseparableMatrix(B (l,l+m), (U,Vnew), ([α β],[S AᵀU])), τ)
+function qr(A::BandedPlusSemiseparableMatrix{Float64})
+    n = size(A, 1); l, m = bandwidths(A.B); r = size(A.U, 2); p = size(A.W, 2)
+    dA = upload(A)
+    f = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ssm_bps_qr, libssm), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), dA.p, f))
+    dF = Handle(f[], :bpsqr)
+    B = BandedMatrix{Float64}(undef, (n, n), (l, l + m))
+    U = Matrix{Float64}(undef, n, r); V = similar(U)
+    W = Matrix{Float64}(undef, n, p + r); S = similar(W)
+    τ = zeros(Float64, n)
+    GC.@preserve B U V W S τ check(ccall((:ssm_bpsqr_get, libssm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+        dF.p, pointer(B.data), 0, pointer(U), pointer(V), 0, pointer(W), pointer(S), 0, pointer(τ), 0))
+    factors = BandedPlusSemiseparableMatrix(B, (U, V), (W, S))
+    BPSFACTORS[factors] = (dA, dF)
+    QR(factors, τ)
+end
+
+function bps_device_factor(factors)
+    haskey(BPSFACTORS, factors) || error("SemiseparableB200: factorisation was not produced by the B200 path; call qr(A) again")
+    BPSFACTORS[factors]
+end
+
+# lmul!(F.Q', b) (semiseparableqr.jl:863-905)
+function lmul!(adjQ::AdjointQ{<:Any,<:QRPackedQ{<:Any,<:BandedPlusSemiseparableMatrix{Float64}}}, b::Vector{Float64})
+    _, dF = bps_device_factor(parent(adjQ).factors)
+    v = device_vec(b)
+    check(ccall((:ssm_bpsqr_lmul_qt, libssm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dF.p, v.p))
+    fetch_vec!(b, v)
+    b
+end
+
+# ldiv!(F.R, b) (BandedPlusSemiseparableMatrix.jl:53-70): factored object -> stored factors; otherwise upload the operand
+function ldiv!(R::UpperTriangular{<:Any,<:BandedPlusSemiseparableMatrix{Float64}}, b::Vector{Float64})
+    F = parent(R)
+    v = device_vec(b)
+    if haskey(BPSFACTORS, F)
+        check(ccall((:ssm_bpsqr_upper_ldiv, libssm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), BPSFACTORS[F][2].p, v.p))
+    else
+        dA = upload(F)
+        check(ccall((:ssm_bps_upper_ldiv, libssm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dA.p, v.p))
+    end
+    fetch_vec!(b, v)
+    b
+end
+
+end # module
