@@ -138,6 +138,23 @@ int  ssm_bps_residual(const ssm_bps *A, const ssm_vec *x, const ssm_vec *b, doub
 /* ldiv!(UpperTriangular(A), b) on an unfactored BPS (test_bandedplussemiseparable.jl:17)                   */
 int  ssm_bps_upper_ldiv(const ssm_bps *A, ssm_vec *b);
 
+/* ---- one LARGE AlmostBandedMatrix system, chunked along the n axis (BASELINE config 4) ------------------------
+ * `A \ b` (AlmostBandedMatrix.jl:125-133,187-199) for a single system whose sequential sweep cannot fill a GPU:
+ * a partitioned orthogonal factorisation over P row chunks.  Returns the reference's SOLUTION
+ * (rel. error <= 1e-12 on well-conditioned systems), not its factors.  Operands in the reference layout, host or device. */
+typedef struct ssm_abc ssm_abc;
+int  ssm_abc_create(ssm_ctx *ctx, int64_t n, int l, int u, int r, ssm_abc **A);
+int  ssm_abc_destroy(ssm_abc *A);
+int  ssm_abc_set(ssm_abc *A, const double *bands, const double *U, const double *V);
+int  ssm_abc_generate(ssm_abc *A, uint64_t seed, int dist);            /* system index 0 of the shared generator  */
+int  ssm_abc_vec_generate(ssm_abc *A, double *b_dev, uint64_t seed);   /* b = 2u-1 (array id 3), device pointer    */
+/* x <- A \ b; b, x: n doubles, host or device, x may alias b; nchunks = 0 picks ~2048 rows per chunk            */
+int  ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks);
+int  ssm_abc_residual(ssm_abc *A, const double *x, const double *b, double *relres);
+int  ssm_abc_chunks(const ssm_abc *A);                                 /* P of the last solve                      */
+/* inspection for tests: what = 0 level-0 reduced blocks, 1 separator solution, 2 R-row records, 3 operand records */
+int  ssm_abc_debug_get(ssm_abc *A, int what, double *out, int64_t count);
+
 #ifdef __cplusplus
 }
 #endif

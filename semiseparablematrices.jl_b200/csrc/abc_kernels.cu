@@ -1,0 +1,735 @@
+// abc_kernels.cu — K10: ONE large AlmostBandedMatrix system, chunked along the n axis (BASELINE config 4:
+// n = 2^24, l = u = 4, r = 2).  Replaces, for a single system whose sequential sweep (AlmostBandedMatrix.jl:144-170,
+// :224-238) cannot fill a GPU, the whole `A \ b` (AlmostBandedMatrix.jl:125-133, 187-199) by a stable partitioned
+// orthogonal factorisation that returns the same SOLUTION (the factors are not the reference's):
+//
+//   stage 1  abc_qr      one WARP per row chunk: Householder elimination of the chunk's interior columns.  Lanes hold the
+//                        COLUMNS of the active block (window | generator | separator coefficients | tail coefficients | rhs),
+//                        reflectors are broadcast with shuffles; rows and window columns rotate through fixed slots/lanes
+//                        so nothing moves when the window slides.
+//   stage 2  abc_merge   cyclic reduction of the block-bidiagonal separator system F_c z_c + G_c z_{c+1} = h_c by QR of
+//                        [G_a; F_b], one warp per merge, log2(P) launches; abc_root solves the last block; abc_expand
+//                        recovers the eliminated separators top-down.
+//   stage 3  abc_bs      one warp per chunk: back-substitution of the interior unknowns (one 22-double record per row,
+//                        dot product with the lane-resident multipliers, butterfly reduction).
+//
+// The numpy restatement tests/emul/sof_reference.py documents the algebra and is the CPU check of this file.
+// Layout (row-major, one system): REC[n+pad][lp+1+r] = A[i, i-l .. i+u] | U[i, :];  V[n+pad][r];  lp = l + u.
+#include "../../include/ssm_rng.h"
+#include "ssm_internal.cuh"
+
+namespace ssm {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int ABC_PAD = 64;
+
+struct AbcArgs {
+    const double *REC, *V, *b;   // operands
+    double *FR;                  // [n][NC] R-row records, canonical column order
+    double *E0;                  // [P][W][2W+1] level-0 reduced blocks [F | G | h]
+    const double *Z;             // [(P+1)][W] separator solution (stage 3)
+    double *x;
+    int64_t n; int l, u; int P;
+};
+
+__host__ __device__ __forceinline__ int64_t chunk_start(int64_t n, int P, int c) { return ((int64_t)c * n) / P; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage 1
+// ---------------------------------------------------------------------------------------------------------------
+template <int LP, int R>
+struct AbcDims {
+    static constexpr int PW = LP + 1;                 // window columns = band-row slots
+    static constexpr int NR = LP + 1 + R;             // active rows (band slots + tail rows)
+    static constexpr int NC = 2 * LP + 2 * R + 2;     // active columns = lanes in use
+    static constexpr int G0 = PW, C0 = PW + R, T0 = PW + R + LP, B0 = NC - 1;
+    static constexpr int NF = PW + R;                 // fields of an operand row record
+    static constexpr int W = LP + R;                  // separator block size
+    static_assert(NC <= 32, "active block must fit one warp");
+    static_assert(3 * W + 1 <= 32, "merge block must fit one warp");
+};
+
+template <int LP, int R>
+__global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
+    using D = AbcDims<LP, R>;
+    constexpr int PW = D::PW, NR = D::NR, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, NF = D::NF, W = D::W;
+    __shared__ double stage[4][NR][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int c = blockIdx.x * 4 + wib;
+    if (c >= a.P) return;
+    const int64_t r0 = chunk_start(a.n, a.P, c), r1 = chunk_start(a.n, a.P, c + 1);
+    const int m = (int)(r1 - r0), nsteps = m - LP;
+    const int u = a.u;
+    const bool isW = lane < PW, isG = lane >= G0 && lane < C0, isC = lane >= C0 && lane < T0, isT = lane >= T0 && lane < B0, isB = lane == B0;
+    const double *rec0 = a.REC + r0 * NF;
+    const double *v0 = a.V + (r0 + u) * (R > 0 ? R : 1);      // V row of local column 0
+    const double *b0 = a.b + r0;
+    double A[NR];
+#pragma unroll
+    for (int s = 0; s < NR; ++s) A[s] = 0.0;
+
+    // ---- prologue: band rows 0..LP-1 (slot = row) and the R tail rows (slots PW..) ----
+#pragma unroll
+    for (int ip = 0; ip < LP; ++ip) {
+        const double *rec = rec0 + (int64_t)ip * NF;
+        double val = 0.0;
+        if (isW && lane <= ip) val = rec[LP - ip + lane];
+        if (isG) val = rec[PW + lane - G0];
+        if (isC && ip <= lane - C0) val = rec[lane - C0 - ip];
+        if (isB) val = b0[ip];
+        double f = 0.0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const double g = __shfl_sync(FULL, val, G0 + q);
+            const double vq = (isW && lane < m) ? v0[(int64_t)lane * R + q] : 0.0;
+            f = fma(g, vq, f);
+        }
+        if (isW && lane > ip) val = f;
+        A[ip] = val;
+    }
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+        double val = 0.0;
+        if (isW && lane < m) val = -v0[(int64_t)lane * R + t];
+        if (isG && lane - G0 == t) val = -1.0;
+        if (isT && lane - T0 == t) val = 1.0;
+        A[PW + t] = val;
+    }
+
+    // value of the entering row (local row k + LP) for this lane, phase PH = k mod PW
+    auto load_enter = [&](int k, int PH) -> double {
+        const double *rec = rec0 + (int64_t)(k + LP) * NF;
+        double val = 0.0;
+        if (isW) { int d = lane - PH; if (d < 0) d += PW; val = rec[d]; }
+        if (isG) val = rec[PW + lane - G0];
+        if (isB) val = b0[k + LP];
+        return val;
+    };
+    auto load_v = [&](int jn, int q) -> double { return (jn < m) ? v0[(int64_t)jn * R + q] : 0.0; };
+
+    double nxt = nsteps > 0 ? load_enter(0, 0) : 0.0;
+    double *fr = a.FR + r0 * NC;
+    for (int kb = 0; kb < nsteps; kb += PW) {
+#pragma unroll
+        for (int PH = 0; PH < PW; ++PH) {
+            const int k = kb + PH;
+            if (k < nsteps) {
+                const int es = (PH + LP) % PW;          // slot of the entering row
+                A[es] = nxt;
+                if (k + 1 < nsteps) nxt = load_enter(k + 1, (PH + 1) % PW);
+                double vn[R > 0 ? R : 1];
+#pragma unroll
+                for (int q = 0; q < R; ++q) vn[q] = load_v(k + LP + 1, q);
+                // reflector from the pivot column (held by lane PH), LinearAlgebra.reflector! convention
+                double x[NR];
+#pragma unroll
+                for (int s = 0; s < NR; ++s) x[s] = __shfl_sync(FULL, A[s], PH);
+                double ssq0 = 0.0, ssq1 = 0.0;
+#pragma unroll
+                for (int s = 0; s < NR; s += 2) { ssq0 = fma(x[s], x[s], ssq0); if (s + 1 < NR) ssq1 = fma(x[s + 1], x[s + 1], ssq1); }
+                const double ssq = ssq0 + ssq1;
+                const double xp = x[PH];
+                const double nu = copysign(sqrt(ssq), xp);
+                const double xi = xp + nu;
+                const bool nz = ssq != 0.0;
+                const double inv = nz ? 1.0 / xi : 0.0;
+                const double tau = nz ? xi / nu : 0.0;
+                double d0 = A[PH], d1 = 0.0;
+#pragma unroll
+                for (int s = 0; s < NR; ++s) {
+                    if (s == PH) continue;
+                    x[s] *= inv;                         // v_s
+                    if (s & 1) d1 = fma(x[s], A[s], d1); else d0 = fma(x[s], A[s], d0);
+                }
+                const double dot = (d0 + d1) * tau;
+#pragma unroll
+                for (int s = 0; s < NR; ++s) A[s] = (s == PH) ? A[s] - dot : fma(-x[s], dot, A[s]);
+                if (lane == PH) A[PH] = nz ? -nu : xp;
+                // emit the finished row (canonical order: window entry of column k+t at position t)
+                if (lane < NC) {
+                    int pos = lane;
+                    if (isW) { pos = lane - PH; if (pos < 0) pos += PW; }
+                    fr[(int64_t)k * NC + pos] = A[PH];
+                }
+                // the window slides: local column k+LP+1 replaces the pivot column in lane PH (fill region of every surviving row)
+#pragma unroll
+                for (int s = 0; s < NR; ++s) {
+                    if (s == PH) continue;
+                    double f = 0.0;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) f = fma(__shfl_sync(FULL, A[s], G0 + q), vn[q], f);
+                    if (lane == PH) A[s] = f;
+                }
+            }
+        }
+    }
+    // ---- leftover rows -> level-0 reduced block  [F = C_L | Tprev,  G = window(S_{c+1}) | generator,  h] ----
+#pragma unroll
+    for (int s = 0; s < NR; ++s) stage[wib][s][lane] = A[s];
+    __syncwarp();
+    int dst = -1;
+    if (isW) {                                   // lane holds local column jp == lane (mod PW) in [m-LP, m-1], if any
+        int jp = (m - LP) + ((lane - (m - LP)) % PW + PW) % PW;
+        if (jp <= m - 1) dst = W + (jp - (m - LP));
+    } else if (isG) dst = W + LP + (lane - G0);
+    else if (isC) dst = lane - C0;
+    else if (isT) dst = LP + (lane - T0);
+    else if (isB) dst = 2 * W;
+    double *E = a.E0 + (int64_t)c * W * (2 * W + 1);
+    if (dst >= 0) {
+        for (int row = 0; row < W; ++row) {
+            const int slot = row < LP ? (m - LP + row) % PW : PW + (row - LP);
+            E[row * (2 * W + 1) + dst] = stage[wib][slot][lane];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage 2: merge two adjacent blocks, eliminating the separator between them
+//   Ein  : level blocks [W][2W+1] = [F | G | h];  merge i combines blocks 2i, 2i+1
+//   TOP  : [W][3W+1] = [Rhat | Fhat | Ghat | hhat]  (z_M = Rhat^-1 (hhat - Fhat z_L - Ghat z_R))
+// ---------------------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(128) abc_merge_kernel(const double *Ein, double *Eout, double *TOP, int nin) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int nout = (nin + 1) / 2;
+    if (i >= nout) return;
+    constexpr int EW = 2 * W + 1, TW = 3 * W + 1;
+    const double *Ea = Ein + (int64_t)(2 * i) * W * EW;
+    if (2 * i + 1 >= nin) {                      // odd block passes through
+        for (int t = lane; t < W * EW; t += 32) Eout[(int64_t)i * W * EW + t] = Ea[t];
+        return;
+    }
+    const double *Eb = Ea + W * EW;
+    double M[2 * W];
+#pragma unroll
+    for (int s = 0; s < W; ++s) {
+        double top = 0.0, bot = 0.0;
+        if (lane < W) { top = Ea[s * EW + W + lane]; bot = Eb[s * EW + lane]; }               // z_M: G_a over F_b
+        else if (lane < 2 * W) top = Ea[s * EW + (lane - W)];                                  // z_L: F_a
+        else if (lane < 3 * W) bot = Eb[s * EW + W + (lane - 2 * W)];                          // z_R: G_b
+        else if (lane == 3 * W) { top = Ea[s * EW + 2 * W]; bot = Eb[s * EW + 2 * W]; }
+        M[s] = top; M[W + s] = bot;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        double x[2 * W];
+        double ssq = 0.0;
+#pragma unroll
+        for (int s = j; s < 2 * W; ++s) { x[s] = __shfl_sync(FULL, M[s], j); ssq = fma(x[s], x[s], ssq); }
+        const double xp = x[j];
+        const double nu = copysign(sqrt(ssq), xp);
+        const double xi = xp + nu;
+        const bool nz = ssq != 0.0;
+        const double inv = nz ? 1.0 / xi : 0.0;
+        const double tau = nz ? xi / nu : 0.0;
+        double dot = M[j];
+#pragma unroll
+        for (int s = j + 1; s < 2 * W; ++s) { x[s] *= inv; dot = fma(x[s], M[s], dot); }
+        dot *= tau;
+        M[j] -= dot;
+#pragma unroll
+        for (int s = j + 1; s < 2 * W; ++s) M[s] = fma(-x[s], dot, M[s]);
+        if (lane == j) {
+            M[j] = nz ? -nu : xp;
+#pragma unroll
+            for (int s = j + 1; s < 2 * W; ++s) M[s] = 0.0;
+        }
+    }
+    if (lane < TW) {
+        double *T = TOP + (int64_t)i * W * TW;
+#pragma unroll
+        for (int s = 0; s < W; ++s) T[s * TW + lane] = M[s];
+    }
+    if (lane >= W && lane < TW) {
+        double *Eo = Eout + (int64_t)i * W * EW;
+#pragma unroll
+        for (int s = 0; s < W; ++s) Eo[s * EW + (lane - W)] = M[W + s];
+    }
+}
+
+// root: one block [F | G | h] over (z_0, z_P).  Real unknowns: z_0 entries l..W-1 (separator columns >= 0 and the
+// free tail T_{-1}) and z_P entries 0..l-1 (separator columns < n); everything else is a phantom and stays 0.
+template <int W>
+__global__ void __launch_bounds__(32) abc_root_kernel(const double *E, double *Z, int P, int l) {
+    __shared__ double Rm[W][W + 1];
+    const int lane = threadIdx.x;
+    constexpr int EW = 2 * W + 1;
+    const int n0 = W - l;                         // unknowns taken from z_0
+    double M[W];
+#pragma unroll
+    for (int s = 0; s < W; ++s) {
+        double v = 0.0;
+        if (lane < n0) v = E[s * EW + l + lane];
+        else if (lane < W) v = E[s * EW + W + (lane - n0)];
+        else if (lane == W) v = E[s * EW + 2 * W];
+        M[s] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        double x[W];
+        double ssq = 0.0;
+#pragma unroll
+        for (int s = j; s < W; ++s) { x[s] = __shfl_sync(FULL, M[s], j); ssq = fma(x[s], x[s], ssq); }
+        const double xp = x[j];
+        const double nu = copysign(sqrt(ssq), xp);
+        const double xi = xp + nu;
+        const bool nz = ssq != 0.0;
+        const double inv = nz ? 1.0 / xi : 0.0;
+        const double tau = nz ? xi / nu : 0.0;
+        double dot = M[j];
+#pragma unroll
+        for (int s = j + 1; s < W; ++s) { x[s] *= inv; dot = fma(x[s], M[s], dot); }
+        dot *= tau;
+        M[j] -= dot;
+#pragma unroll
+        for (int s = j + 1; s < W; ++s) M[s] = fma(-x[s], dot, M[s]);
+        if (lane == j) {
+            M[j] = nz ? -nu : xp;
+#pragma unroll
+            for (int s = j + 1; s < W; ++s) M[s] = 0.0;
+        }
+    }
+    if (lane <= W) {
+#pragma unroll
+        for (int s = 0; s < W; ++s) Rm[s][lane] = M[s];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double sol[W];
+        for (int j = W - 1; j >= 0; --j) {
+            double acc = Rm[j][W];
+            for (int t = j + 1; t < W; ++t) acc = fma(-Rm[j][t], sol[t], acc);
+            sol[j] = acc / Rm[j][j];
+        }
+        for (int t = 0; t < W; ++t) { Z[t] = 0.0; Z[(int64_t)P * W + t] = 0.0; }
+        for (int t = 0; t < n0; ++t) Z[l + t] = sol[t];
+        for (int t = n0; t < W; ++t) Z[(int64_t)P * W + (t - n0)] = sol[t];
+    }
+}
+
+// expansion of one level: merge i of a level whose blocks span `span` chunks recovers z at chunk index (2i+1)*span
+template <int W>
+__global__ void __launch_bounds__(128) abc_expand_kernel(const double *TOP, double *Z, int nmerge, int span, int P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmerge) return;
+    constexpr int TW = 3 * W + 1;
+    const double *T = TOP + (int64_t)i * W * TW;
+    const int64_t iL = (int64_t)2 * i * span, iM = iL + span;
+    int64_t iR = iM + span; if (iR > P) iR = P;
+    const double *zL = Z + iL * W, *zR = Z + iR * W;
+    double zl[W], zr[W], sol[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) { zl[t] = zL[t]; zr[t] = zR[t]; }
+#pragma unroll
+    for (int j = W - 1; j >= 0; --j) {
+        double acc = T[j * TW + 3 * W];
+#pragma unroll
+        for (int t = 0; t < W; ++t) acc = fma(-T[j * TW + W + t], zl[t], acc);
+#pragma unroll
+        for (int t = 0; t < W; ++t) acc = fma(-T[j * TW + 2 * W + t], zr[t], acc);
+#pragma unroll
+        for (int t = j + 1; t < W; ++t) acc = fma(-T[j * TW + t], sol[t], acc);
+        sol[j] = acc / T[j * TW + j];
+    }
+#pragma unroll
+    for (int t = 0; t < W; ++t) Z[iM * W + t] = sol[t];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage 3: interior back-substitution, one warp per chunk
+// ---------------------------------------------------------------------------------------------------------------
+template <int LP, int R>
+__global__ void __launch_bounds__(128) abc_bs_kernel(const AbcArgs a) {
+    using D = AbcDims<LP, R>;
+    constexpr int PW = D::PW, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, W = D::W;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= a.P) return;
+    const int64_t r0 = chunk_start(a.n, a.P, c), r1 = chunk_start(a.n, a.P, c + 1);
+    const int m = (int)(r1 - r0), nsteps = m - LP;
+    const int u = a.u, l = a.l;
+    const bool isW = lane < PW, isG = lane >= G0 && lane < C0, isC = lane >= C0 && lane < T0, isT = lane >= T0 && lane < B0, isB = lane == B0;
+    const double *zc = a.Z + (int64_t)c * W, *zn = zc + W;
+    const double *v0 = a.V + (r0 + u) * (R > 0 ? R : 1);
+    double *xloc = a.x + r0 + u;                        // x of local column 0
+    // separator columns: S_{c+1} = local columns m-LP .. m-1 (global r1-l .. r1+u-1); chunk 0 also owns S_0's real columns
+    if (lane < LP) { const int64_t g = r1 - l + lane; if (g >= 0 && g < a.n) a.x[g] = zn[lane]; }
+    if (c == 0 && lane < LP) { const int64_t g = r0 - l + lane; if (g >= 0 && g < a.n) a.x[g] = zc[lane]; }
+    // multipliers: position t = 1..LP holds x_{k+t}; generator lanes hold s; C_L / Tprev lanes hold z_c; rhs lane holds -1
+    double mult = 0.0;
+    if (isW && lane >= 1) mult = zn[lane - 1];
+    if (isG) mult = zn[LP + (lane - G0)];
+    if (isC) mult = zc[lane - C0];
+    if (isT) mult = zc[LP + (lane - T0)];
+    if (isB) mult = -1.0;
+    const double *fr = a.FR + r0 * NC;
+    double rec = (nsteps > 0 && lane < NC) ? fr[(int64_t)(nsteps - 1) * NC + lane] : 0.0;
+    for (int k = nsteps - 1; k >= 0; --k) {
+        const double cur = rec;
+        if (k > 0 && lane < NC) rec = fr[(int64_t)(k - 1) * NC + lane];
+        const double vleave = isG ? v0[(int64_t)(k + LP) * R + (lane - G0)] : 0.0;   // V of the column that leaves the window next
+        double p = (lane >= 1 && lane < NC) ? cur * mult : 0.0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+        const double rkk = __shfl_sync(FULL, cur, 0);
+        const double xk = -p / rkk;
+        if (lane == 0) xloc[k] = xk;
+        // next row (k-1): window becomes x_k .. x_{k-1+LP}; x_{k+LP} moves into the running tail sum s
+        const double xout = __shfl_sync(FULL, mult, LP);
+        const double up = __shfl_up_sync(FULL, mult, 1);
+        if (isG) mult = fma(vleave, xout, mult);
+        if (isW && lane >= 2) mult = up;
+        if (lane == 1) mult = xk;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// boundary kernels: pack (reference layout -> row records), generator, residual
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void abc_pack_kernel(double *REC, double *Vd, const double *bands, const double *U, const double *V, int64_t n, int l, int u, int r) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int lp = l + u, nf = lp + 1 + r;
+    for (int d = 0; d <= lp; ++d) {
+        const int64_t j = i - l + d;
+        REC[i * nf + d] = (j >= 0 && j < n) ? bands[(int64_t)(u + i - j) + j * (lp + 1)] : 0.0;
+    }
+    for (int q = 0; q < r; ++q) { REC[i * nf + lp + 1 + q] = U[i + (int64_t)q * n]; Vd[i * r + q] = V[(int64_t)q + i * r]; }
+}
+__global__ void abc_generate_kernel(double *REC, double *Vd, int64_t n, int l, int u, int r, uint64_t seed, int dist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = ssm_syskey(seed, 0);
+    const int lp = l + u, nf = lp + 1 + r;
+    for (int d = 0; d <= lp; ++d) {
+        const int64_t j = i - l + d;
+        REC[i * nf + d] = (j >= 0 && j < n) ? ssm_ab_band_elem(key, dist, (int)n, l, u, r, lp - d, (int)j) : 0.0;
+    }
+    for (int q = 0; q < r; ++q) {
+        REC[i * nf + lp + 1 + q] = ssm_ab_U_elem(key, dist, (int)n, r, (int)i, q);
+        Vd[i * r + q] = ssm_ab_V_elem(key, dist, (int)n, r, q, (int)i);
+    }
+}
+__global__ void abc_vec_generate_kernel(double *b, int64_t n, uint64_t seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = ssm_ab_b_elem(ssm_syskey(seed, 0), (int)i);
+}
+
+// residual: seg sums of V_j x_j, exclusive suffix over segments, then per-row suffix inside each segment
+constexpr int RSEG = 2048;     // rows per CTA (256 threads x 8 rows)
+__global__ void __launch_bounds__(256) abc_res_partial_kernel(const double *Vd, const double *x, double *part, int64_t n, int r) {
+    __shared__ double sh[8][SSM_MAX_RANK];
+    const int64_t g0 = (int64_t)blockIdx.x * RSEG;
+    double acc[SSM_MAX_RANK] = {0, 0, 0, 0};
+    for (int t = threadIdx.x; t < RSEG; t += 256) {
+        const int64_t j = g0 + t;
+        if (j < n) { const double xj = x[j]; for (int q = 0; q < r; ++q) acc[q] = fma(Vd[j * r + q], xj, acc[q]); }
+    }
+    for (int q = 0; q < r; ++q) {
+        double v = acc[q];
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < r) { double v = 0.0; for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x]; part[(int64_t)blockIdx.x * SSM_MAX_RANK + threadIdx.x] = v; }
+}
+__global__ void __launch_bounds__(256) abc_res_scan_kernel(double *part, int nseg, int r, double *acc2) {
+    // exclusive suffix scan over the segment sums: thread t owns a contiguous range, block-level suffix in shared memory
+    __shared__ double sh[256];
+    const int tid = threadIdx.x, per = (nseg + 255) / 256;
+    const int g0 = min(nseg, tid * per), g1 = min(nseg, g0 + per);
+    for (int q = 0; q < r; ++q) {
+        double s = 0.0;
+        for (int g = g0; g < g1; ++g) s += part[(int64_t)g * SSM_MAX_RANK + q];
+        sh[tid] = s;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {
+            const double add = (tid + off < 256) ? sh[tid + off] : 0.0;
+            __syncthreads();
+            sh[tid] += add;
+            __syncthreads();
+        }
+        double suf = (tid + 1 < 256) ? sh[tid + 1] : 0.0;
+        __syncthreads();
+        for (int g = g1 - 1; g >= g0; --g) { const double v = part[(int64_t)g * SSM_MAX_RANK + q]; part[(int64_t)g * SSM_MAX_RANK + q] = suf; suf += v; }
+    }
+    if (tid == 0) { acc2[0] = 0.0; acc2[1] = 0.0; }
+}
+__global__ void __launch_bounds__(256) abc_res_kernel(const double *REC, const double *Vd, const double *x, const double *b, const double *part,
+                                                      double *acc2, int64_t n, int l, int u, int r) {
+    __shared__ double sh[256][SSM_MAX_RANK];
+    __shared__ double red[2][8];
+    const int lp = l + u, nf = lp + 1 + r;
+    const int64_t g0 = (int64_t)blockIdx.x * RSEG, g1 = min(n, g0 + RSEG);
+    const int tid = threadIdx.x;
+    // thread t owns columns g0 + 8t .. g0 + 8t + 7: its sum, then block suffix scan
+    double mine[SSM_MAX_RANK] = {0, 0, 0, 0};
+    for (int e = 0; e < 8; ++e) { const int64_t j = g0 + tid * 8 + e; if (j < g1) { const double xj = x[j]; for (int q = 0; q < r; ++q) mine[q] = fma(Vd[j * r + q], xj, mine[q]); } }
+    for (int q = 0; q < r; ++q) sh[tid][q] = mine[q];
+    __syncthreads();
+    // suffix (exclusive) over threads, simple log-step scan
+    for (int off = 1; off < 256; off <<= 1) {
+        double add[SSM_MAX_RANK];
+        for (int q = 0; q < r; ++q) add[q] = (tid + off < 256) ? sh[tid + off][q] : 0.0;
+        __syncthreads();
+        for (int q = 0; q < r; ++q) sh[tid][q] += add[q];
+        __syncthreads();
+    }
+    // sh[tid] = inclusive suffix from thread tid; Suf(k) for k = first column of thread tid+1 is sh[tid+1] + segment suffix
+    double suf[SSM_MAX_RANK];
+    for (int q = 0; q < r; ++q) suf[q] = ((tid + 1 < 256) ? sh[tid + 1][q] : 0.0) + part[(int64_t)blockIdx.x * SSM_MAX_RANK + q];
+    // walk own rows descending; S(i) = Suf(i+u+1).  Start with Suf(k0) where k0 = g0 + 8(tid+1), then add columns down to i+u+1
+    double num = 0.0, den = 0.0;
+    int64_t kcur = g0 + (int64_t)(tid + 1) * 8;           // suf = Suf(kcur) restricted ... columns >= kcur (within or beyond the segment)
+    if (kcur > g1) kcur = g1;
+    for (int e = 7; e >= 0; --e) {
+        const int64_t i = g0 + tid * 8 + e;
+        if (i >= g1) continue;
+        const int64_t need = i + u + 1;                   // want Suf(need)
+        double s[SSM_MAX_RANK];
+        for (int q = 0; q < r; ++q) s[q] = suf[q];
+        if (need >= kcur) {                               // remove columns kcur .. need-1
+            for (int64_t j = kcur; j < need && j < n; ++j) { const double xj = x[j]; for (int q = 0; q < r; ++q) s[q] = fma(-Vd[j * r + q], xj, s[q]); }
+        } else {                                          // add columns need .. kcur-1
+            for (int64_t j = need; j < kcur; ++j) { const double xj = x[j]; for (int q = 0; q < r; ++q) s[q] = fma(Vd[j * r + q], xj, s[q]); }
+        }
+        double ax = 0.0;
+        for (int d = 0; d <= lp; ++d) { const int64_t j = i - l + d; if (j >= 0 && j < n) ax = fma(REC[i * nf + d], x[j], ax); }
+        for (int q = 0; q < r; ++q) ax = fma(REC[i * nf + lp + 1 + q], s[q], ax);
+        const double bi = b[i], dl = bi - ax;
+        num = fma(dl, dl, num); den = fma(bi, bi, den);
+    }
+    for (int o = 16; o >= 1; o >>= 1) { num += __shfl_xor_sync(FULL, num, o); den += __shfl_xor_sync(FULL, den, o); }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = num; red[1][tid >> 5] = den; }
+    __syncthreads();
+    if (tid == 0) { double a0 = 0, a1 = 0; for (int w = 0; w < 8; ++w) { a0 += red[0][w]; a1 += red[1][w]; } atomicAdd(&acc2[0], a0); atomicAdd(&acc2[1], a1); }
+}
+
+}  // namespace ssm
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+using namespace ssm;
+
+struct ssm_abc {
+    ssm_ctx *ctx; int64_t n; int l, u, r, lp, w, nf, nc;
+    DevBufPtr REC, V;                 // operands
+    DevBufPtr FR, E, TOP, Z, tmp;     // workspace of the last solve (allocated on first use)
+    int P = 0;
+};
+
+#define SSM_CHECK_ARG(cond, msg) do { if (!(cond)) { set_error("%s: %s", __func__, msg); return SSM_E_ARG; } } while (0)
+
+#define SSM_ABC_SHAPES(X) X(1, 1) X(1, 2) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(4, 2) X(6, 2) X(8, 2)
+
+static bool abc_supported(int lp, int r) {
+#define X(LP_, R_) if (lp == LP_ && r == R_) return true;
+    SSM_ABC_SHAPES(X)
+#undef X
+    return false;
+}
+
+// device pointer for a caller array of `count` doubles (host arrays are staged into `hold`)
+static int to_device(ssm_ctx *c, const double *p, size_t count, DevBufPtr &hold, const double **out) {
+    if (!p) { *out = nullptr; return 0; }
+    if (is_device_ptr(p)) { *out = p; return 0; }
+    SSM_TRY(dev_alloc(c->device, count, false, c->stream, hold));
+    SSM_CUDA(cudaMemcpyAsync(hold->p, p, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    *out = hold->p;
+    return 0;
+}
+
+static int abc_default_chunks(const ssm_abc *A) {
+    // ~2048 rows per chunk; at least 2*lp+2 rows each; enough warps to cover the SMs when n allows
+    int64_t P = A->n / 2048;
+    const int64_t pmax = A->n / (2 * A->lp + 2 + 8);
+    if (P > 16384) P = 16384;
+    if (P > pmax) P = pmax;
+    if (P < 1) P = 1;
+    return (int)P;
+}
+
+template <int LP, int R>
+static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
+    ssm_ctx *c = A->ctx;
+    using D = AbcDims<LP, R>;
+    constexpr int W = D::W, EW = 2 * W + 1, TW = 3 * W + 1;
+    AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P};
+    const unsigned gchunks = (unsigned)((P + 3) / 4);
+    abc_qr_kernel<LP, R><<<gchunks, 128, 0, c->stream>>>(a);
+    c->launches++;
+    // levels: level t has nlev[t] blocks stored at E + off[t]
+    std::vector<int> cnt; std::vector<int64_t> eoff, toff;
+    int cur = P; int64_t eo = 0, to = 0;
+    cnt.push_back(cur); eoff.push_back(0);
+    while (cur > 1) {
+        const int nout = (cur + 1) / 2;
+        const int64_t nexto = eo + (int64_t)cur * W * EW;
+        abc_merge_kernel<W><<<(unsigned)((nout + 3) / 4), 128, 0, c->stream>>>(A->E->p + eo, A->E->p + nexto, A->TOP->p + to, cur);
+        c->launches++;
+        toff.push_back(to);
+        to += (int64_t)(cur / 2) * W * TW;
+        eo = nexto; cur = nout;
+        cnt.push_back(cur); eoff.push_back(eo);
+    }
+    abc_root_kernel<W><<<1, 32, 0, c->stream>>>(A->E->p + eo, A->Z->p, P, A->l);
+    c->launches++;
+    for (int t = (int)toff.size() - 1; t >= 0; --t) {
+        const int nmerge = cnt[t] / 2;
+        if (nmerge == 0) continue;
+        abc_expand_kernel<W><<<(unsigned)((nmerge + 127) / 128), 128, 0, c->stream>>>(A->TOP->p + toff[t], A->Z->p, nmerge, 1 << t, P);
+        c->launches++;
+    }
+    abc_bs_kernel<LP, R><<<gchunks, 128, 0, c->stream>>>(a);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int ssm_abc_create(ssm_ctx *c, int64_t n, int l, int u, int r, ssm_abc **out) {
+    SSM_CHECK_ARG(c && out, "null argument");
+    SSM_CHECK_ARG(n >= 1 && l >= 0 && u >= 0 && r >= 0, "bad sizes");
+    if (n > (int64_t)0x7fffffff - 1024) { set_error("ssm_abc_create: n too large"); return SSM_E_UNSUPPORTED; }
+    if (!abc_supported(l + u, r)) { set_error("ssm_abc: (l+u, r) = (%d, %d) has no compiled chunked kernel", l + u, r); return SSM_E_UNSUPPORTED; }
+    auto *A = new ssm_abc();
+    A->ctx = c; A->n = n; A->l = l; A->u = u; A->r = r; A->lp = l + u; A->w = A->lp + r; A->nf = A->lp + 1 + r; A->nc = 2 * A->lp + 2 * r + 2;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+    int rc = dev_alloc(c->device, (size_t)(n + ABC_PAD) * A->nf, true, c->stream, A->REC);
+    if (!rc) rc = dev_alloc(c->device, (size_t)(n + ABC_PAD) * (r > 0 ? r : 1), true, c->stream, A->V);
+    cudaSetDevice(prev);
+    if (rc) { delete A; return rc; }
+    *out = A;
+    return 0;
+}
+int ssm_abc_destroy(ssm_abc *A) { if (A) { cudaStreamSynchronize(A->ctx->stream); delete A; } return 0; }
+
+int ssm_abc_generate(ssm_abc *A, uint64_t seed, int dist) {
+    SSM_CHECK_ARG(A, "null argument");
+    ssm_ctx *c = A->ctx;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+    abc_generate_kernel<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, A->n, A->l, A->u, A->r, seed, dist);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "abc_generate_kernel", __FILE__, __LINE__);
+    return 0;
+}
+
+int ssm_abc_set(ssm_abc *A, const double *bands, const double *U, const double *V) {
+    SSM_CHECK_ARG(A && bands && (A->r == 0 || (U && V)), "null argument");
+    ssm_ctx *c = A->ctx;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+    DevBufPtr hb, hu, hv;
+    const double *db, *du, *dv;
+    int rc = to_device(c, bands, (size_t)(A->lp + 1) * A->n, hb, &db);
+    if (!rc) rc = to_device(c, A->r ? U : nullptr, (size_t)A->n * A->r, hu, &du);
+    if (!rc) rc = to_device(c, A->r ? V : nullptr, (size_t)A->n * A->r, hv, &dv);
+    if (!rc) {
+        abc_pack_kernel<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, db, du, dv, A->n, A->l, A->u, A->r);
+        c->launches++;
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "abc_pack_kernel", __FILE__, __LINE__);
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int ssm_abc_vec_generate(ssm_abc *A, double *b_dev, uint64_t seed) {
+    SSM_CHECK_ARG(A && b_dev && is_device_ptr(b_dev), "b must be a device pointer");
+    ssm_ctx *c = A->ctx;
+    abc_vec_generate_kernel<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(b_dev, A->n, seed);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// A \ b for one large system: x <- A \ b (b, x: n doubles, host or device; x may alias b).  nchunks = 0 picks a default.
+int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
+    SSM_CHECK_ARG(A && b && x, "null argument");
+    ssm_ctx *c = A->ctx;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+    int P = nchunks > 0 ? nchunks : abc_default_chunks(A);
+    const int64_t pmax = A->n / (2 * A->lp + 2);
+    if (P > pmax) P = (int)(pmax < 1 ? 1 : pmax);
+    int rc = 0;
+    if (A->n < 2 * A->lp + 2) { set_error("ssm_abc_solve: n = %lld is too small for the chunked path (use the batched path)", (long long)A->n); rc = SSM_E_UNSUPPORTED; }
+    const int W = A->w;
+    if (!rc && (!A->FR || A->P != P)) {
+        A->FR.reset(); A->E.reset(); A->TOP.reset(); A->Z.reset();
+        rc = dev_alloc(c->device, (size_t)A->n * A->nc, false, c->stream, A->FR);
+        if (!rc) rc = dev_alloc(c->device, (size_t)(2 * (int64_t)P + 64) * W * (2 * W + 1), true, c->stream, A->E);
+        if (!rc) rc = dev_alloc(c->device, (size_t)((int64_t)P + 64) * W * (3 * W + 1), true, c->stream, A->TOP);
+        if (!rc) rc = dev_alloc(c->device, (size_t)((int64_t)P + 2) * W, true, c->stream, A->Z);
+        A->P = P;
+    }
+    DevBufPtr hb, hx;
+    const double *db = nullptr; double *dx = nullptr;
+    if (!rc) rc = to_device(c, b, (size_t)A->n, hb, &db);
+    const bool xhost = !is_device_ptr(x);
+    if (!rc) {
+        if (xhost) { rc = dev_alloc(c->device, (size_t)A->n, false, c->stream, hx); dx = hx ? hx->p : nullptr; }
+        else dx = x;
+    }
+    if (!rc) {
+        rc = SSM_E_UNSUPPORTED;
+#define X(LP_, R_) if (A->lp == LP_ && A->r == R_) rc = abc_solve_inst<LP_, R_>(A, db, dx, P);
+        SSM_ABC_SHAPES(X)
+#undef X
+    }
+    if (!rc && xhost) {
+        cudaError_t e = cudaMemcpyAsync(x, dx, (size_t)A->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "D2H x", __FILE__, __LINE__);
+    }
+    if (!rc && (xhost || hb)) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+// relres = ||b - A x||_2 / ||b||_2 with A applied through its structure (AlmostBandedMatrix.jl:84-90)
+int ssm_abc_residual(ssm_abc *A, const double *x, const double *b, double *relres) {
+    SSM_CHECK_ARG(A && x && b && relres, "null argument");
+    ssm_ctx *c = A->ctx;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+    DevBufPtr hx, hb;
+    const double *dx, *db;
+    int rc = to_device(c, x, (size_t)A->n, hx, &dx);
+    if (!rc) rc = to_device(c, b, (size_t)A->n, hb, &db);
+    const int nseg = (int)((A->n + RSEG - 1) / RSEG);
+    if (!rc) rc = dev_alloc(c->device, (size_t)nseg * SSM_MAX_RANK + 2, true, c->stream, A->tmp);
+    if (!rc) {
+        double *part = A->tmp->p, *acc2 = part + (size_t)nseg * SSM_MAX_RANK;
+        abc_res_partial_kernel<<<nseg, 256, 0, c->stream>>>(A->V->p, dx, part, A->n, A->r);
+        abc_res_scan_kernel<<<1, 256, 0, c->stream>>>(part, nseg, A->r, acc2);
+        abc_res_kernel<<<nseg, 256, 0, c->stream>>>(A->REC->p, A->V->p, dx, db, part, acc2, A->n, A->l, A->u, A->r);
+        c->launches += 3;
+        double h[2] = {0, 0};
+        cudaError_t e = cudaMemcpyAsync(h, acc2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "abc residual", __FILE__, __LINE__);
+        else *relres = sqrt(h[0]) / sqrt(h[1]);
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+// inspection (tests): copy the level-0 reduced blocks / separator solution / R records of the last solve to the host
+int ssm_abc_debug_get(ssm_abc *A, int what, double *out, int64_t count) {
+    SSM_CHECK_ARG(A && out, "null argument");
+    DevBufPtr src = what == 0 ? A->E : what == 1 ? A->Z : what == 2 ? A->FR : A->REC;
+    if (!src) { set_error("ssm_abc_debug_get: no solve has run"); return SSM_E_STATE; }
+    if ((size_t)count > src->count) count = (int64_t)src->count;
+    SSM_CUDA(cudaMemcpyAsync(out, src->p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, A->ctx->stream));
+    SSM_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    return 0;
+}
+int ssm_abc_chunks(const ssm_abc *A) { return A ? A->P : 0; }
+
+}  // extern "C"

@@ -77,6 +77,15 @@ _SIGS = {
     "ssm_bps_mul": (C.c_int, [c_vp, c_vp, c_vp]),
     "ssm_bps_residual": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ssm_bps_upper_ldiv": (C.c_int, [c_vp, c_vp]),
+    "ssm_abc_create": (C.c_int, [c_vp, i64, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
+    "ssm_abc_destroy": (C.c_int, [c_vp]),
+    "ssm_abc_set": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "ssm_abc_generate": (C.c_int, [c_vp, u64, C.c_int]),
+    "ssm_abc_vec_generate": (C.c_int, [c_vp, c_vp, u64]),
+    "ssm_abc_solve": (C.c_int, [c_vp, c_vp, c_vp, C.c_int]),
+    "ssm_abc_residual": (C.c_int, [c_vp, c_vp, c_vp, C.POINTER(C.c_double)]),
+    "ssm_abc_chunks": (C.c_int, [c_vp]),
+    "ssm_abc_debug_get": (C.c_int, [c_vp, C.c_int, c_vp, i64]),
 }
 
 

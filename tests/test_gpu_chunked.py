@@ -1,0 +1,108 @@
+"""GPU tier: one large AlmostBandedMatrix system through the chunked n-axis path (K10, ssm_abc_*), against dense LAPACK,
+the numpy restatement of the same algebra (stage by stage), the reference-restating oracle, and — at BASELINE.json
+configs[3]'s full size n = 2^24 — the oracle's sequential sweep plus the structured residual.
+Tolerance: relative solution error <= 1e-12 (north_star)."""
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).parent / "emul"))
+import oracle  # noqa: E402
+from helpers import readme_expz  # noqa: E402
+from sof_reference import chunk_bounds, chunk_reduce, dense, solve_chunked  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def chunked():
+    from ssm_b200 import chunked
+    return chunked
+
+
+def _rand(rng, n, l, u, r):
+    bands = rng.standard_normal((n, l + u + 1)); U = rng.standard_normal((r, n)); V = rng.standard_normal((n, r)) / np.sqrt(n)
+    bands[:, u] += 2 * (l + u + 1) * np.sign(bands[:, u])          # well conditioned: the bar is 1e-12 on the solution
+    for j in range(n):
+        for d in range(l + u + 1):
+            k = j + d - u
+            if k < 0 or k >= n:
+                bands[j, d] = 0.0
+    return bands, U, V, rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("n,l,u,r,P", [(64, 2, 2, 2, 4), (50, 1, 0, 1, 3), (97, 4, 4, 2, 4), (40, 2, 0, 2, 2), (33, 1, 1, 1, 1),
+                                       (200, 3, 1, 2, 8), (500, 2, 2, 2, 16), (777, 4, 4, 2, 7), (130, 1, 1, 2, 5), (64, 2, 1, 1, 3)])
+def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P):
+    rng = np.random.default_rng(n * 13 + P)
+    bands, U, V, b = _rand(rng, n, l, u, r)
+    A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
+    x = A.solve(b, nchunks=P)
+    assert A.chunks == P
+    lp, w = l + u, l + u + r
+    # stage 1 output: level-0 reduced blocks [F | G | h] per chunk, against the numpy restatement (rows may differ by
+    # nothing: same reflector convention and order)
+    E = A._debug(0, P * w * (2 * w + 1)).reshape(P, w, 2 * w + 1)
+    bnd = chunk_bounds(n, P)
+    for c in range(P):
+        _, left = chunk_reduce(bands, U, V, b, l, u, bnd[c], bnd[c + 1])
+        G0, C0, T0 = lp + 1, lp + 1 + r, lp + 1 + r + lp
+        ref = np.hstack([left[:, C0:C0 + lp], left[:, T0:T0 + r], left[:, 0:lp], left[:, G0:G0 + r], left[:, -1:]])
+        assert np.allclose(E[c], ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max()), (c, np.abs(E[c] - ref).max())
+    x0 = np.linalg.solve(dense(bands, U, V, l, u), b)
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) <= 1e-12
+    assert A.residual(x, b) <= 1e-13
+
+
+def test_chunked_readme_known_answer(chunked, ctx):
+    (l, u, r), bands, U, V, b = readme_expz(20)
+    A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
+    for P in (1, 2, 3):
+        x = A.solve(b, nchunks=P)
+        ref = np.array([1 / math.factorial(k) for k in range(16)])
+        # normwise: the partitioned factorisation is backward stable, not componentwise accurate on the graded tail
+        assert np.linalg.norm(x[:16] - ref) / np.linalg.norm(ref) <= 1e-14
+
+
+@pytest.mark.parametrize("n,l,u,r,dist", [(100_000, 4, 4, 2, 1), (100_000, 2, 2, 2, 0), (262_144, 1, 0, 1, 0), (65_537, 4, 4, 2, 0)])
+def test_chunked_matches_oracle_sweep(chunked, ctx, n, l, u, r, dist):
+    import torch
+    seed = 20261019 + 3
+    bands, U, V, b = oracle.ab_generate(n, l, u, r, 1, seed=seed, dist=dist)
+    ox = oracle.ab_solve(bands, U, V, b, l, u)[0]
+    A = chunked.LargeAlmostBandedMatrix.generate(n, l, u, r, seed, dist=dist, ctx=ctx)
+    rec = A._debug(3, 8 * (l + u + 1 + r)).reshape(8, l + u + 1 + r)          # generator = oracle's, bit for bit
+    for i in range(8):
+        for d in range(l + u + 1):
+            j = i - l + d
+            assert rec[i, d] == (bands[0, j, u + i - j] if 0 <= j < n else 0.0)
+    bd = A.generate_rhs(torch.empty(n, dtype=torch.float64, device="cuda"), seed)
+    assert np.array_equal(bd.cpu().numpy(), b[0])
+    x = A.solve(bd)
+    xs = x.cpu().numpy()
+    assert np.linalg.norm(xs - ox) / np.linalg.norm(ox) <= 1e-12
+    assert A.residual(x, bd) <= 1e-13
+    # host-pointer entry and explicit operands give the same answer as the device-generated ones
+    A2 = chunked.LargeAlmostBandedMatrix(bands[0], (U[0], V[0]), (l, u), ctx=ctx)
+    x2 = A2.solve(b[0], nchunks=A.chunks)
+    assert np.array_equal(x2, xs)
+
+
+def test_config4_full_size(chunked, ctx):
+    """BASELINE.json configs[3]: single large almost-banded spectral system, n = 16,777,216, l = u = 4, r = 2."""
+    import torch
+    n, l, u, r, seed = 1 << 24, 4, 4, 2, 20261019 + 3
+    A = chunked.LargeAlmostBandedMatrix.generate(n, l, u, r, seed, dist=1, ctx=ctx)
+    b = A.generate_rhs(torch.empty(n, dtype=torch.float64, device="cuda"), seed)
+    x = A.solve(b)
+    assert A.residual(x, b) <= 1e-13
+    bands, U, V, bb = oracle.ab_generate(n, l, u, r, 1, seed=seed, dist=1)
+    ox = oracle.ab_solve(bands, U, V, bb, l, u)[0]
+    xs = x.cpu().numpy()
+    assert np.linalg.norm(xs - ox) / np.linalg.norm(ox) <= 1e-12
+    # a different chunking gives the same solution to rounding
+    x2 = A.solve(b, nchunks=1000).cpu().numpy()
+    assert np.linalg.norm(x2 - ox) / np.linalg.norm(ox) <= 1e-12

@@ -2,6 +2,7 @@
 """Secondary measurements (not the driver's bench contract): the other BASELINE.json configs on ONE GPU.
 
   python tools/bench_configs.py c3            BPS QR, n=4096, l=m=3, r=p=2, 16,384 systems  (configs[2])
+  python tools/bench_configs.py c4            one large system n=2^24, l=u=4, r=2, chunked n-axis path (configs[3])
   python tools/bench_configs.py c5            almost-banded sweep n=256..8192, 1M systems total (configs[4]), this GPU's share
   python tools/bench_configs.py c2 [--variant V --stages S]   per-kernel timing of config 2 (tuning aid)
 
@@ -104,19 +105,39 @@ def c5(args, ctx):
     print(json.dumps({"config": "c5 total", "systems": tot_sys, "ms": tot_ms, "systems_per_s": tot_sys / (tot_ms * 1e-3)}))
 
 
+def c4(args, ctx):
+    """configs[3]: one large almost-banded system, n = 2^24, l = u = 4, r = 2, chunked n-axis path (K10)."""
+    from ssm_b200 import chunked
+    n, l, u, r, seed = args.n or (1 << 24), 4, 4, 2, 20261019 + 3
+    A = chunked.LargeAlmostBandedMatrix.generate(n, l, u, r, seed, dist=1, ctx=ctx)
+    b = A.generate_rhs(torch.empty(n, dtype=torch.float64, device="cuda"), seed)
+    x = torch.empty_like(b)
+    for P in ([args.chunks] if args.chunks else [0, 2048, 4096, 16384, 32768]):
+        t = timeit(lambda: A.solve(b, out=x, nchunks=P, sync=False), args.steps)
+        torch.cuda.synchronize()
+        rr = A.residual(x, b)
+        qrldiv = 8 * n * (5 * l + 3 * u + 5 * r + 7)         # SURVEY 8(d): qr + ldiv! algorithmic bytes
+        fused = 8 * n * (l + u + 2 * r + 3)                  # fused A\\b (no factor output)
+        print(json.dumps({"config": f"c4 single system n={n} l=u=4 r=2 (bc)", "chunks": A.chunks, "ms": t, "systems_per_s": 1e3 / t,
+                          "columns_per_s": n / (t * 1e-3), "GBps_qr_plus_ldiv_algorithmic": qrldiv / t / 1e6,
+                          "frac_of_measured_peak_qr_plus_ldiv": qrldiv / t / 1e6 / PEAK, "frac_of_measured_peak_fused_strict": fused / t / 1e6 / PEAK,
+                          "relres": rr}))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["c2", "c3", "c5"])
+    ap.add_argument("which", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--nb", type=int, default=0)
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--world", type=int, default=1)
+    ap.add_argument("--chunks", type=int, default=0)
     args = ap.parse_args()
     ctx = ssm.Context(0, stream=torch.cuda.current_stream().cuda_stream)
     if args.variant:
         ctx.set_option("ab_variant", args.variant)
     if args.stages:
         ctx.set_option("pipeline_stages", args.stages)
-    {"c2": c2, "c3": c3, "c5": c5}[args.which](args, ctx)
+    {"c2": c2, "c3": c3, "c4": c4, "c5": c5}[args.which](args, ctx)
