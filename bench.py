@@ -196,19 +196,14 @@ def main():
 
     import numpy as np
     import torch
-    import torch.distributed as dist
     import ssm_b200 as ssm
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    from ssm_b200 import sharder
+    job = sharder.Job(backend="nccl", device=torch.device("cuda", local_rank))   # barrier + max-over-ranks only: no data-path collective
+    barrier = job.barrier
 
     n, l, u, r, nb = N_SYS, L_BW, U_BW, RANK_R, args.nb
     stream = torch.cuda.current_stream()
@@ -249,10 +244,7 @@ def main():
     total_ms = ev[0][0].elapsed_time(ev[-1][2])
     qr_ms = [e[0].elapsed_time(e[1]) for e in ev]
     ld_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = job.max_over_ranks(total_ms)
     ms_per_step = total_ms_max / args.steps
     value = world * nb / (ms_per_step * 1e-3)
 
@@ -306,10 +298,7 @@ def main():
             ssm.solve_host(n, l, u, r, *pins, x=xout, ctx=ectx)   # synchronises before returning
         dt = time.perf_counter() - t0
         barrier()
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item()) / args.e2e_steps
+        dt = job.max_over_ranks(dt) / args.e2e_steps
         xs = xout.numpy()
         xd = x.get() if nb_e == nb else None
         e2e = {"value": world * nb_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(nb_e * (l + u + 1 + 2 * r + 1) * n * 8),
@@ -336,8 +325,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches), "parity": parity,
         }
         print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    job.close()
 
 
 if __name__ == "__main__":

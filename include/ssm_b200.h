@@ -111,6 +111,12 @@ int  ssm_ab_residual(const ssm_ab *A, const ssm_vec *x, const ssm_vec *b, double
 /* One-shot HOST-buffer path (end-to-end): H2D + pack + qr + ldiv! + D2H, chunk-pipelined over streams.    */
 int  ssm_ab_solve_host(ssm_ctx *ctx, int n, int l, int u, int r, int64_t nb, const double *bands,
                        const double *U, const double *V, const double *b, double *x);
+/* Batch sharder (north_star: independent systems split across the GPUs of one box, no NCCL; the host buffers are the
+ * gather).  Shard g of G owns systems [s0, s1), cut at multiples of 32; ssm_ab_solve_host_sharded runs ssm_ab_solve_host on
+ * every listed device from its own host thread and returns when all shards are done.                                   */
+int  ssm_shard_range(int64_t nb, int g, int G, int64_t *s0, int64_t *s1);
+int  ssm_ab_solve_host_sharded(int ndev, const int *devices, int n, int l, int u, int r, int64_t nb, const double *bands,
+                               const double *U, const double *V, const double *b, double *x);
 
 /* ---- BandedPlusSemiseparableMatrix (src/BandedPlusSemiseparableMatrix.jl, src/semiseparableqr.jl) -- */
 /* BandedPlusSemiseparableMatrix(B,(U,V),(W,S)) + size check (BandedPlusSemiseparableMatrix.jl:10-16)      */

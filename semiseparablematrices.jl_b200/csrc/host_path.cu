@@ -104,3 +104,62 @@ extern "C" int ssm_ab_solve_host(ssm_ctx *c, int n, int l, int u, int r, int64_t
     cudaSetDevice(prev);
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Batch sharder: independent systems are split contiguously across the GPUs of one box, one host thread + one
+// ssm_ctx (stream, chunk pipeline) per GPU, no collective — the host buffers ARE the gather (north_star).
+// ---------------------------------------------------------------------------------------------------------
+#include <mutex>
+#include <thread>
+#include <map>
+
+namespace {
+std::mutex g_shard_mu;
+std::map<std::pair<int, int>, ssm_ctx *> g_shard_ctx;   // one lazily created context per (shard, device), kept for the process lifetime
+
+ssm_ctx *shard_ctx(int shard, int device, int *rc) {
+    std::lock_guard<std::mutex> lk(g_shard_mu);
+    auto it = g_shard_ctx.find({shard, device});
+    if (it != g_shard_ctx.end()) { *rc = 0; return it->second; }
+    ssm_ctx *c = nullptr;
+    *rc = ssm_ctx_create(device, &c);
+    if (*rc) return nullptr;
+    g_shard_ctx[{shard, device}] = c;
+    return c;
+}
+}  // namespace
+
+// systems [s0, s1) of a batch of nb go to shard g of G:  s0 = g*nb/G rounded down to a multiple of 32 (tile size)
+extern "C" int ssm_shard_range(int64_t nb, int g, int G, int64_t *s0, int64_t *s1) {
+    if (!s0 || !s1 || G < 1 || g < 0 || g >= G || nb < 0) { set_error("ssm_shard_range: bad arguments"); return SSM_E_ARG; }
+    auto cut = [&](int k) -> int64_t { if (k >= G) return nb; int64_t c = (nb * k) / G; c -= c % TILE; return c; };
+    *s0 = cut(g); *s1 = cut(g + 1);
+    return 0;
+}
+
+extern "C" int ssm_ab_solve_host_sharded(int ndev, const int *devices, int n, int l, int u, int r, int64_t nb, const double *bands,
+                                         const double *U, const double *V, const double *b, double *x) {
+    if (ndev < 1 || !devices) { set_error("ssm_ab_solve_host_sharded: need at least one device"); return SSM_E_ARG; }
+    if (!bands || !b || !x || (r > 0 && (!U || !V)) || n < 1 || nb < 1) { set_error("ssm_ab_solve_host_sharded: bad arguments"); return SSM_E_ARG; }
+    const size_t eb = (size_t)(l + u + 1) * n, eu = (size_t)n * r;
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::string> errs(ndev);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ndev; ++g) {
+        th.emplace_back([&, g]() {
+            int64_t s0 = 0, s1 = 0;
+            ssm_shard_range(nb, g, ndev, &s0, &s1);
+            if (s1 <= s0) return;
+            int rc = 0;
+            ssm_ctx *c = shard_ctx(g, devices[g], &rc);
+            if (!rc) rc = ssm_ab_solve_host(c, n, l, u, r, s1 - s0, bands + (size_t)s0 * eb, r ? U + (size_t)s0 * eu : nullptr,
+                                            r ? V + (size_t)s0 * eu : nullptr, b + (size_t)s0 * n, x + (size_t)s0 * n);
+            rcs[g] = rc;
+            if (rc) errs[g] = ssm_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < ndev; ++g)
+        if (rcs[g]) { set_error("shard %d (device %d): %s", g, devices[g], errs[g].c_str()); return rcs[g]; }
+    return 0;
+}

@@ -77,6 +77,8 @@ _SIGS = {
     "ssm_bps_mul": (C.c_int, [c_vp, c_vp, c_vp]),
     "ssm_bps_residual": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ssm_bps_upper_ldiv": (C.c_int, [c_vp, c_vp]),
+    "ssm_shard_range": (C.c_int, [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]),
+    "ssm_ab_solve_host_sharded": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ssm_abc_create": (C.c_int, [c_vp, i64, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
     "ssm_abc_destroy": (C.c_int, [c_vp]),
     "ssm_abc_set": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),

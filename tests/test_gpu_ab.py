@@ -239,3 +239,20 @@ def test_full_size_config2_properties(ssm, ctx, variant):
     for s in idx[::8]:
         ob, oU, oV, obv = (a[0] for a in oracle.ab_generate(n, l, u, r, 1, seed, s0=int(s)))
         assert relerr(xh[s], oracle.ab_solve(ob, oU, oV, obv, l, u)) <= 1e-12
+
+
+def test_sharded_host_solve_matches_single_device(ssm, ctx):
+    """batch sharder: two shards (both on device 0 here; one per GPU on a multi-GPU box) == unsharded host solve, bit for bit"""
+    import torch
+    from ssm_b200 import sharder
+    n, l, u, r, nb = 128, 2, 2, 2, 777
+    bands, U, V, b = oracle.ab_generate(n, l, u, r, nb, seed=20261023)
+    x1 = ssm.solve_host(n, l, u, r, bands, U, V, b, ctx=ctx)
+    ndev = torch.cuda.device_count()
+    devs = [0, 1 % ndev] if ndev > 1 else [0, 0]
+    x2 = sharder.solve_host_sharded(devs, n, l, u, r, bands, U, V, b)
+    assert np.array_equal(x1, x2)
+    x3 = sharder.solve_host_sharded(list(range(ndev)) * 2, n, l, u, r, bands, U, V, b)
+    assert np.array_equal(x1, x3)
+    ox = oracle.ab_solve(bands, U, V, b, l, u)
+    assert max(relerr(x2[s], ox[s]) for s in range(nb)) <= 1e-12
