@@ -30,9 +30,32 @@ struct AbcArgs {
     const double *Z;             // [(P+1)][W] separator solution (stage 3)
     double *x;
     int64_t n; int l, u; int P;
+    int m0, jx, pw;              // chunk c has m0 + pw*(c < jx) rows: every chunk length is == lp (mod lp+1), see abc_layout()
 };
 
-__host__ __device__ __forceinline__ int64_t chunk_start(int64_t n, int P, int c) { return ((int64_t)c * n) / P; }
+// Regular chunks: the system is padded with < lp+1 identity rows to n' = P*m0 + jx*pw so that every chunk eliminates a
+// multiple of pw = lp+1 columns (the sweep is unrolled by pw; no remainder code, no divergence around the shuffles).
+__host__ __device__ __forceinline__ int64_t chunk_start(const AbcArgs &a, int c) { return (int64_t)c * a.m0 + (int64_t)a.pw * (c < a.jx ? c : a.jx); }
+
+// fp64 reciprocal / reciprocal square root without the IEEE slow paths: hardware seed (MUFU, ~2^-22) + two Newton steps
+// (relative error ~1 ulp).  The chunked path returns a solution, not reference-identical factors, so 1-2 ulp is immaterial.
+__device__ __forceinline__ double fast_rcp(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // stage 1
@@ -50,20 +73,21 @@ struct AbcDims {
 };
 
 template <int LP, int R>
-__global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
+__global__ void __launch_bounds__(128, 4) abc_qr_kernel(const AbcArgs a) {
     using D = AbcDims<LP, R>;
     constexpr int PW = D::PW, NR = D::NR, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, NF = D::NF, W = D::W;
     __shared__ double stage[4][NR][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int c = blockIdx.x * 4 + wib;
     if (c >= a.P) return;
-    const int64_t r0 = chunk_start(a.n, a.P, c), r1 = chunk_start(a.n, a.P, c + 1);
-    const int m = (int)(r1 - r0), nsteps = m - LP;
+    const int64_t r0 = chunk_start(a, c);
+    const int m = a.m0 + (c < a.jx ? PW : 0), nsteps = m - LP;      // nsteps is a multiple of PW
     const int u = a.u;
     const bool isW = lane < PW, isG = lane >= G0 && lane < C0, isC = lane >= C0 && lane < T0, isT = lane >= T0 && lane < B0, isB = lane == B0;
     const double *rec0 = a.REC + r0 * NF;
     const double *v0 = a.V + (r0 + u) * (R > 0 ? R : 1);      // V row of local column 0
     const double *b0 = a.b + r0;
+    const int64_t brows = a.n - r0;                           // rows of b that exist from r0 on (pad rows have b = 0)
     double A[NR];
 #pragma unroll
     for (int s = 0; s < NR; ++s) A[s] = 0.0;
@@ -76,12 +100,12 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         if (isW && lane <= ip) val = rec[LP - ip + lane];
         if (isG) val = rec[PW + lane - G0];
         if (isC && ip <= lane - C0) val = rec[lane - C0 - ip];
-        if (isB) val = b0[ip];
+        if (isB && ip < brows) val = b0[ip];
         double f = 0.0;
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const double g = __shfl_sync(FULL, val, G0 + q);
-            const double vq = (isW && lane < m) ? v0[(int64_t)lane * R + q] : 0.0;
+            const double vq = isW ? v0[(int64_t)lane * R + q] : 0.0;
             f = fma(g, vq, f);
         }
         if (isW && lane > ip) val = f;
@@ -90,76 +114,81 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
 #pragma unroll
     for (int t = 0; t < R; ++t) {
         double val = 0.0;
-        if (isW && lane < m) val = -v0[(int64_t)lane * R + t];
+        if (isW) val = -v0[(int64_t)lane * R + t];
         if (isG && lane - G0 == t) val = -1.0;
         if (isT && lane - T0 == t) val = 1.0;
         A[PW + t] = val;
     }
 
-    // value of the entering row (local row k + LP) for this lane, phase PH = k mod PW
-    auto load_enter = [&](int k, int PH) -> double {
-        const double *rec = rec0 + (int64_t)(k + LP) * NF;
-        double val = 0.0;
-        if (isW) { int d = lane - PH; if (d < 0) d += PW; val = rec[d]; }
-        if (isG) val = rec[PW + lane - G0];
-        if (isB) val = b0[k + LP];
-        return val;
-    };
-    auto load_v = [&](int jn, int q) -> double { return (jn < m) ? v0[(int64_t)jn * R + q] : 0.0; };
-
-    double nxt = nsteps > 0 ? load_enter(0, 0) : 0.0;
-    double *fr = a.FR + r0 * NC;
+    // Per-lane stream of the entering rows: window / generator lanes walk the row records, the rhs lane walks b, all other
+    // lanes re-read one zero (a V pad row), so the load needs no predicate.  Window lanes read field d = (lane - k) mod PW,
+    // which is also the position of their entry in the emitted record.
+    int d = isW ? lane : 0;                                   // phase 0
+    const double *ep; int estride;
+    if (isW || isG) { ep = rec0 + (int64_t)LP * NF + (isG ? PW + lane - G0 : 0); estride = NF; }
+    else if (isB) { ep = b0 + LP; estride = 1; }
+    else { ep = a.V + (a.n + 8) * (R > 0 ? R : 1); estride = 0; }
+    const double *vp = v0 + (int64_t)(LP + 1) * R;            // V row of the column entering after step 0
+    double vnx[R > 0 ? R : 1];
+#pragma unroll
+    for (int q = 0; q < R; ++q) vnx[q] = vp[q];
+    double *fr = a.FR + r0 * NC + (isW ? 0 : lane);
+    const bool emit = lane < NC;
+    int64_t brem = brows - LP;                                // rhs lane: rows of b left
+    double nxt = (isB && brem <= 0) ? 0.0 : ep[isW ? d : 0];
     for (int kb = 0; kb < nsteps; kb += PW) {
 #pragma unroll
         for (int PH = 0; PH < PW; ++PH) {
-            const int k = kb + PH;
-            if (k < nsteps) {
-                const int es = (PH + LP) % PW;          // slot of the entering row
-                A[es] = nxt;
-                if (k + 1 < nsteps) nxt = load_enter(k + 1, (PH + 1) % PW);
-                double vn[R > 0 ? R : 1];
+            const int es = (PH + LP) % PW;                    // slot of the entering row
+            A[es] = nxt;
+            // prefetch the row entering at the next step (rows past the chunk are the next chunk's or the identity pad)
+            ep += estride; --brem;
+            const int dn = isW ? (d == 0 ? LP : d - 1) : 0;
+            nxt = (isB && brem <= 0) ? 0.0 : ep[dn];
+            double vn[R > 0 ? R : 1];
+            vp += R;
 #pragma unroll
-                for (int q = 0; q < R; ++q) vn[q] = load_v(k + LP + 1, q);
-                // reflector from the pivot column (held by lane PH), LinearAlgebra.reflector! convention
-                double x[NR];
+            for (int q = 0; q < R; ++q) { vn[q] = vnx[q]; vnx[q] = vp[q]; }   // one step ahead (the row past the chunk is the next chunk's / pad)
+            // reflector from the pivot column (held by lane PH), LinearAlgebra.reflector! convention
+            double x[NR];
 #pragma unroll
-                for (int s = 0; s < NR; ++s) x[s] = __shfl_sync(FULL, A[s], PH);
-                double ssq0 = 0.0, ssq1 = 0.0;
+            for (int s = 0; s < NR; ++s) x[s] = __shfl_sync(FULL, A[s], PH);
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
-                for (int s = 0; s < NR; s += 2) { ssq0 = fma(x[s], x[s], ssq0); if (s + 1 < NR) ssq1 = fma(x[s + 1], x[s + 1], ssq1); }
-                const double ssq = ssq0 + ssq1;
-                const double xp = x[PH];
-                const double nu = copysign(sqrt(ssq), xp);
-                const double xi = xp + nu;
-                const bool nz = ssq != 0.0;
-                const double inv = nz ? 1.0 / xi : 0.0;
-                const double tau = nz ? xi / nu : 0.0;
-                double d0 = A[PH], d1 = 0.0;
+            for (int s = 0; s < NR; ++s) { if (s % 3 == 0) q0 = fma(x[s], x[s], q0); else if (s % 3 == 1) q1 = fma(x[s], x[s], q1); else q2 = fma(x[s], x[s], q2); }
+            const double ssq = (q0 + q1) + q2;
+            const double xp = x[PH];
+            const bool nz = ssq != 0.0;
+            const double rs = fast_rsqrt(ssq);
+            double nrm = ssq * rs;
+            nrm = fma(fma(-nrm, nrm, ssq), 0.5 * rs, nrm);    // one correction step: sqrt to ~1 ulp
+            const double nu = copysign(nrm, xp);
+            const double xi = xp + nu;
+            const double inv = nz ? fast_rcp(xi) : 0.0;
+            const double tau = nz ? xi * copysign(rs, xp) : 0.0;
+            double d0 = A[PH], d1 = 0.0, d2 = 0.0;
 #pragma unroll
-                for (int s = 0; s < NR; ++s) {
-                    if (s == PH) continue;
-                    x[s] *= inv;                         // v_s
-                    if (s & 1) d1 = fma(x[s], A[s], d1); else d0 = fma(x[s], A[s], d0);
-                }
-                const double dot = (d0 + d1) * tau;
+            for (int s = 0; s < NR; ++s) {
+                if (s == PH) continue;
+                x[s] *= inv;                                  // v_s
+                if (s % 3 == 0) d0 = fma(x[s], A[s], d0); else if (s % 3 == 1) d1 = fma(x[s], A[s], d1); else d2 = fma(x[s], A[s], d2);
+            }
+            const double dot = ((d0 + d1) + d2) * tau;
 #pragma unroll
-                for (int s = 0; s < NR; ++s) A[s] = (s == PH) ? A[s] - dot : fma(-x[s], dot, A[s]);
-                if (lane == PH) A[PH] = nz ? -nu : xp;
-                // emit the finished row (canonical order: window entry of column k+t at position t)
-                if (lane < NC) {
-                    int pos = lane;
-                    if (isW) { pos = lane - PH; if (pos < 0) pos += PW; }
-                    fr[(int64_t)k * NC + pos] = A[PH];
-                }
-                // the window slides: local column k+LP+1 replaces the pivot column in lane PH (fill region of every surviving row)
+            for (int s = 0; s < NR; ++s) A[s] = (s == PH) ? A[s] - dot : fma(-x[s], dot, A[s]);
+            if (lane == PH) A[PH] = nz ? -nu : xp;
+            // emit the finished row (canonical order: window entry of column k+t at position t)
+            if (emit) fr[isW ? d : 0] = A[PH];
+            fr += NC;
+            d = dn;
+            // the window slides: local column k+LP+1 replaces the pivot column in lane PH (fill region of every surviving row)
 #pragma unroll
-                for (int s = 0; s < NR; ++s) {
-                    if (s == PH) continue;
-                    double f = 0.0;
+            for (int s = 0; s < NR; ++s) {
+                if (s == PH) continue;
+                double f = 0.0;
 #pragma unroll
-                    for (int q = 0; q < R; ++q) f = fma(__shfl_sync(FULL, A[s], G0 + q), vn[q], f);
-                    if (lane == PH) A[s] = f;
-                }
+                for (int q = 0; q < R; ++q) f = fma(__shfl_sync(FULL, A[s], G0 + q), vn[q], f);
+                if (lane == PH) A[s] = f;
             }
         }
     }
@@ -168,7 +197,7 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     for (int s = 0; s < NR; ++s) stage[wib][s][lane] = A[s];
     __syncwarp();
     int dst = -1;
-    if (isW) {                                   // lane holds local column jp == lane (mod PW) in [m-LP, m-1], if any
+    if (isW) {                                   // lane holds local column jp == lane (mod PW) in [m-LP, m]; column m is not part of the chunk
         int jp = (m - LP) + ((lane - (m - LP)) % PW + PW) % PW;
         if (jp <= m - 1) dst = W + (jp - (m - LP));
     } else if (isG) dst = W + LP + (lane - G0);
@@ -340,57 +369,132 @@ __global__ void __launch_bounds__(128) abc_expand_kernel(const double *TOP, doub
 // ---------------------------------------------------------------------------------------------------------------
 // stage 3: interior back-substitution, one warp per chunk
 // ---------------------------------------------------------------------------------------------------------------
+// Blocked: LANES = ROWS.  A block of 32 consecutive R rows is staged in shared memory (cp.async, double buffered, so the next
+// block streams in while this one is solved); everything that does not depend on the recurrence (separator and tail terms,
+// reciprocal of the diagonal) is done by all 32 lanes at once, and the in-block recurrence costs one broadcast + a handful of
+// FMAs per row: when x_j is known every lane k < j adds it with coefficient R[k,j] (j - k <= LP, band) or Ufinal[k,:].V[:,j]
+// (j - k > LP, fill).
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int LP, int R>
 __global__ void __launch_bounds__(128) abc_bs_kernel(const AbcArgs a) {
     using D = AbcDims<LP, R>;
     constexpr int PW = D::PW, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, W = D::W;
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    static_assert(NC % 2 == 0, "records are whole 16-byte units");
+    constexpr int RQ = R > 0 ? R : 1;
+    constexpr int BLK = 32 * NC;                               // doubles per staged block; row stride NC is even, so lane i reading
+                                                               // word i*(NC-1)+const is conflict free per half warp
+    __shared__ __align__(16) double sm[4][2][BLK];
+    __shared__ double smv[4][(32 + LP) * RQ];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int c = blockIdx.x * 4 + wib;
     if (c >= a.P) return;
-    const int64_t r0 = chunk_start(a.n, a.P, c), r1 = chunk_start(a.n, a.P, c + 1);
-    const int m = (int)(r1 - r0), nsteps = m - LP;
+    const int64_t r0 = chunk_start(a, c);
+    const int m = a.m0 + (c < a.jx ? PW : 0), nsteps = m - LP;
+    const int64_t r1 = r0 + m;
     const int u = a.u, l = a.l;
-    const bool isW = lane < PW, isG = lane >= G0 && lane < C0, isC = lane >= C0 && lane < T0, isT = lane >= T0 && lane < B0, isB = lane == B0;
     const double *zc = a.Z + (int64_t)c * W, *zn = zc + W;
-    const double *v0 = a.V + (r0 + u) * (R > 0 ? R : 1);
-    double *xloc = a.x + r0 + u;                        // x of local column 0
+    const double *v0 = a.V + (r0 + u) * RQ;
+    double *xloc = a.x + r0 + u;                               // x of local column 0
+    const int64_t xrows = a.n - (r0 + u);                      // local columns that exist in the caller's x
     // separator columns: S_{c+1} = local columns m-LP .. m-1 (global r1-l .. r1+u-1); chunk 0 also owns S_0's real columns
     if (lane < LP) { const int64_t g = r1 - l + lane; if (g >= 0 && g < a.n) a.x[g] = zn[lane]; }
     if (c == 0 && lane < LP) { const int64_t g = r0 - l + lane; if (g >= 0 && g < a.n) a.x[g] = zc[lane]; }
-    // multipliers: position t = 1..LP holds x_{k+t}; generator lanes hold s; C_L / Tprev lanes hold z_c; rhs lane holds -1
-    double mult = 0.0;
-    if (isW && lane >= 1) mult = zn[lane - 1];
-    if (isG) mult = zn[LP + (lane - G0)];
-    if (isC) mult = zc[lane - C0];
-    if (isT) mult = zc[LP + (lane - T0)];
-    if (isB) mult = -1.0;
-    const double *fr = a.FR + r0 * NC;
-    double rec = (nsteps > 0 && lane < NC) ? fr[(int64_t)(nsteps - 1) * NC + lane] : 0.0;
-    for (int k = nsteps - 1; k >= 0; --k) {
-        const double cur = rec;
-        if (k > 0 && lane < NC) rec = fr[(int64_t)(k - 1) * NC + lane];
-        const double vleave = isG ? v0[(int64_t)(k + LP) * R + (lane - G0)] : 0.0;   // V of the column that leaves the window next
-        double p = (lane >= 1 && lane < NC) ? cur * mult : 0.0;
+    double zl[W];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
-        const double rkk = __shfl_sync(FULL, cur, 0);
-        const double xk = -p / rkk;
-        if (lane == 0) xloc[k] = xk;
-        // next row (k-1): window becomes x_k .. x_{k-1+LP}; x_{k+LP} moves into the running tail sum s
-        const double xout = __shfl_sync(FULL, mult, LP);
-        const double up = __shfl_up_sync(FULL, mult, 1);
-        if (isG) mult = fma(vleave, xout, mult);
-        if (isW && lane >= 2) mult = up;
-        if (lane == 1) mult = xk;
+    for (int t = 0; t < W; ++t) zl[t] = zc[t];
+    // xw: lane t < LP holds x of local column kend + t (the LP columns right of the current block); sb = tail sum over columns >= kend + LP
+    double xw = lane < LP ? zn[lane] : 0.0;
+    double sb[RQ];
+#pragma unroll
+    for (int q = 0; q < R; ++q) sb[q] = zn[LP + q];
+    const double *fr = a.FR + r0 * NC;
+    const int nblk = (nsteps + 31) / 32;
+    auto prefetch = [&](int bi) {                               // rows past nsteps are never used (their lanes idle); FR is padded
+        const double *src = fr + (int64_t)bi * BLK;
+        double *dst = sm[wib][bi & 1];
+#pragma unroll
+        for (int t = 0; t < NC / 2; ++t) cp_async16(dst + 2 * (t * 32 + lane), src + 2 * (t * 32 + lane));
+        cp_async_commit();
+    };
+    prefetch(nblk - 1);
+    for (int bi = nblk - 1; bi >= 0; --bi) {
+        const int k0 = bi * 32, kend = min(k0 + 32, nsteps), k = k0 + lane;
+        // V rows of local columns k0 .. k0+31+LP for the broadcasts below
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            smv[wib][lane * R + q] = v0[(int64_t)(k0 + lane) * R + q];
+            if (lane < LP) smv[wib][(32 + lane) * R + q] = v0[(int64_t)(k0 + 32 + lane) * R + q];
+        }
+        if (bi > 0) { prefetch(bi - 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncwarp();
+        const double *my = sm[wib][bi & 1] + lane * NC;
+        const double *vs = smv[wib];
+        double acc = my[B0];
+#pragma unroll
+        for (int t = 0; t < LP; ++t) acc = fma(-my[C0 + t], zl[t], acc);
+#pragma unroll
+        for (int q = 0; q < R; ++q) acc = fma(-my[T0 + q], zl[LP + q], acc);
+        double g[RQ];
+#pragma unroll
+        for (int q = 0; q < R; ++q) { g[q] = my[G0 + q]; acc = fma(-g[q], sb[q], acc); }
+        const double inv = fast_rcp(my[0]);
+        // (a) the LP known columns right of the block, kend+LP-1 .. kend
+#pragma unroll
+        for (int tt = LP - 1; tt >= 0; --tt) {
+            const int j = kend + tt;
+            const double xj = __shfl_sync(FULL, xw, tt);
+            const int t = j - k;
+            double coef = 0.0;
+#pragma unroll
+            for (int q = 0; q < R; ++q) { const double vq = vs[(j - k0) * R + q]; coef = fma(g[q], vq, coef); if (j >= k0 + LP) sb[q] = fma(vq, xj, sb[q]); }
+            const double band = my[min(t, LP)];               // t >= 1 here
+            if (t <= LP) coef = band;
+            acc = fma(-coef, xj, acc);
+        }
+        // (b) the block's own rows, last first: lane j-k0 owns x_j = acc * inv once every later column has been added
+        double cand = acc * inv;
+        for (int j = kend - 1; j >= k0; --j) {
+            const double xj = __shfl_sync(FULL, cand, j - k0);
+            const int t = j - k;
+            double coef = 0.0;
+#pragma unroll
+            for (int q = 0; q < R; ++q) { const double vq = vs[(j - k0) * R + q]; coef = fma(g[q], vq, coef); if (j >= k0 + LP) sb[q] = fma(vq, xj, sb[q]); }
+            const double band = my[min(max(t, 0), LP)];       // clamped: lanes above the band / below the diagonal read a dummy
+            if (t <= LP) coef = (t >= 1) ? band : 0.0;
+            acc = fma(-coef, xj, acc);
+            cand = acc * inv;
+        }
+        // lanes k <= j never change after their own turn, so cand is x_k
+        if (k < kend && k < xrows) xloc[k] = cand;
+        // next block's right neighbours = local columns k0 .. k0+LP-1: this block's first rows, then (short block) the old window
+        const int nrow = kend - k0;
+        const double nx = __shfl_sync(FULL, cand, lane < LP ? lane : 0);
+        const double ox = __shfl_sync(FULL, xw, (lane >= nrow && lane < LP) ? lane - nrow : 0);
+        xw = lane < LP ? (lane < nrow ? nx : ox) : 0.0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // boundary kernels: pack (reference layout -> row records), generator, residual
 // ---------------------------------------------------------------------------------------------------------------
+// rows n .. n+ABC_PAD-1 are identity rows (the chunked sweep pads the system to a multiple of its unroll period)
+__device__ __forceinline__ bool abc_pad_row(double *REC, double *Vd, int64_t i, int64_t n, int l, int u, int r) {
+    if (i < n) return false;
+    const int lp = l + u, nf = lp + 1 + r;
+    for (int d = 0; d < nf; ++d) REC[i * nf + d] = (d == l) ? 1.0 : 0.0;
+    for (int q = 0; q < r; ++q) Vd[i * r + q] = 0.0;
+    return true;
+}
 __global__ void abc_pack_kernel(double *REC, double *Vd, const double *bands, const double *U, const double *V, int64_t n, int l, int u, int r) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n + ABC_PAD) return;
+    if (abc_pad_row(REC, Vd, i, n, l, u, r)) return;
     const int lp = l + u, nf = lp + 1 + r;
     for (int d = 0; d <= lp; ++d) {
         const int64_t j = i - l + d;
@@ -400,7 +504,8 @@ __global__ void abc_pack_kernel(double *REC, double *Vd, const double *bands, co
 }
 __global__ void abc_generate_kernel(double *REC, double *Vd, int64_t n, int l, int u, int r, uint64_t seed, int dist) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n + ABC_PAD) return;
+    if (abc_pad_row(REC, Vd, i, n, l, u, r)) return;
     const uint64_t key = ssm_syskey(seed, 0);
     const int lp = l + u, nf = lp + 1 + r;
     for (int d = 0; d <= lp; ++d) {
@@ -518,7 +623,7 @@ struct ssm_abc {
     ssm_ctx *ctx; int64_t n; int l, u, r, lp, w, nf, nc;
     DevBufPtr REC, V;                 // operands
     DevBufPtr FR, E, TOP, Z, tmp;     // workspace of the last solve (allocated on first use)
-    int P = 0;
+    int P = 0, m0 = 0, jx = 0;
 };
 
 #define SSM_CHECK_ARG(cond, msg) do { if (!(cond)) { set_error("%s: %s", __func__, msg); return SSM_E_ARG; } } while (0)
@@ -542,6 +647,18 @@ static int to_device(ssm_ctx *c, const double *p, size_t count, DevBufPtr &hold,
     return 0;
 }
 
+// regular chunk layout for P chunks: base length m0 = pw*q - 1, the first jx chunks get pw more rows; P is reduced until q >= 2
+static void abc_layout(int64_t n, int lp, int &P, int &m0, int &jx) {
+    const int pw = lp + 1;
+    if (P < 1) P = 1;
+    while (P > 1 && (n / P + 1) / pw < 2) --P;
+    int64_t q = (n / P + 1) / pw;
+    if (q < 2) q = 2;                                        // tiny n: a single padded chunk
+    m0 = (int)(pw * q - 1);
+    const int64_t rem = n - (int64_t)P * m0;
+    jx = rem > 0 ? (int)((rem + pw - 1) / pw) : 0;
+}
+
 static int abc_default_chunks(const ssm_abc *A) {
     // ~2048 rows per chunk; at least 2*lp+2 rows each; enough warps to cover the SMs when n allows
     int64_t P = A->n / 2048;
@@ -557,7 +674,7 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     ssm_ctx *c = A->ctx;
     using D = AbcDims<LP, R>;
     constexpr int W = D::W, EW = 2 * W + 1, TW = 3 * W + 1;
-    AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P};
+    AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P, A->m0, A->jx, LP + 1};
     const unsigned gchunks = (unsigned)((P + 3) / 4);
     abc_qr_kernel<LP, R><<<gchunks, 128, 0, c->stream>>>(a);
     c->launches++;
@@ -612,7 +729,7 @@ int ssm_abc_generate(ssm_abc *A, uint64_t seed, int dist) {
     SSM_CHECK_ARG(A, "null argument");
     ssm_ctx *c = A->ctx;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
-    abc_generate_kernel<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, A->n, A->l, A->u, A->r, seed, dist);
+    abc_generate_kernel<<<(unsigned)((A->n + ABC_PAD + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, A->n, A->l, A->u, A->r, seed, dist);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     cudaSetDevice(prev);
@@ -630,7 +747,7 @@ int ssm_abc_set(ssm_abc *A, const double *bands, const double *U, const double *
     if (!rc) rc = to_device(c, A->r ? U : nullptr, (size_t)A->n * A->r, hu, &du);
     if (!rc) rc = to_device(c, A->r ? V : nullptr, (size_t)A->n * A->r, hv, &dv);
     if (!rc) {
-        abc_pack_kernel<<<(unsigned)((A->n + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, db, du, dv, A->n, A->l, A->u, A->r);
+        abc_pack_kernel<<<(unsigned)((A->n + ABC_PAD + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, db, du, dv, A->n, A->l, A->u, A->r);
         c->launches++;
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "abc_pack_kernel", __FILE__, __LINE__);
@@ -654,19 +771,20 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
     ssm_ctx *c = A->ctx;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     int P = nchunks > 0 ? nchunks : abc_default_chunks(A);
-    const int64_t pmax = A->n / (2 * A->lp + 2);
-    if (P > pmax) P = (int)(pmax < 1 ? 1 : pmax);
+    int m0 = 0, jx = 0;
+    abc_layout(A->n, A->lp, P, m0, jx);
     int rc = 0;
-    if (A->n < 2 * A->lp + 2) { set_error("ssm_abc_solve: n = %lld is too small for the chunked path (use the batched path)", (long long)A->n); rc = SSM_E_UNSUPPORTED; }
+    if ((int64_t)P * m0 + (int64_t)jx * (A->lp + 1) > A->n + ABC_PAD - 8) { set_error("ssm_abc_solve: internal chunk layout exceeds the padding"); rc = SSM_E_ARG; }
     const int W = A->w;
     if (!rc && (!A->FR || A->P != P)) {
         A->FR.reset(); A->E.reset(); A->TOP.reset(); A->Z.reset();
-        rc = dev_alloc(c->device, (size_t)A->n * A->nc, false, c->stream, A->FR);
+        rc = dev_alloc(c->device, (size_t)(A->n + ABC_PAD + 40) * A->nc, false, c->stream, A->FR);
         if (!rc) rc = dev_alloc(c->device, (size_t)(2 * (int64_t)P + 64) * W * (2 * W + 1), true, c->stream, A->E);
         if (!rc) rc = dev_alloc(c->device, (size_t)((int64_t)P + 64) * W * (3 * W + 1), true, c->stream, A->TOP);
         if (!rc) rc = dev_alloc(c->device, (size_t)((int64_t)P + 2) * W, true, c->stream, A->Z);
         A->P = P;
     }
+    A->m0 = m0; A->jx = jx;
     DevBufPtr hb, hx;
     const double *db = nullptr; double *dx = nullptr;
     if (!rc) rc = to_device(c, b, (size_t)A->n, hb, &db);

@@ -45,6 +45,39 @@ def chunk_bounds(n, P):
     return [(c * n) // P for c in range(P + 1)]
 
 
+def regular_layout(n, lp, P):
+    """The CUDA path's chunk layout (abc_layout in csrc/abc_kernels.cu): every chunk length is == lp (mod lp+1), so each chunk
+    eliminates a multiple of lp+1 columns; the system is padded with < lp+1 identity rows to n' = bounds[-1].
+    Returns (P, bounds)."""
+    pw = lp + 1
+    P = max(P, 1)
+    while P > 1 and (n // P + 1) // pw < 2:
+        P -= 1
+    q = max((n // P + 1) // pw, 2)
+    m0 = pw * q - 1
+    rem = n - P * m0
+    jx = (rem + pw - 1) // pw if rem > 0 else 0
+    return P, [c * m0 + pw * min(c, jx) for c in range(P + 1)]
+
+
+def pad_system(bands, U, V, b, l, u, npad):
+    """append identity rows/columns so that the system has npad >= n rows (x_pad = 0)"""
+    n = bands.shape[0]
+    if npad == n:
+        return bands, U, V, b
+    e = npad - n
+    bp = np.zeros((npad, l + u + 1)); bp[:n] = bands
+    # entries of real columns that referred to rows >= n were zero (outside the matrix); pad columns get a unit diagonal
+    for j in range(max(0, n - l), n):                 # stored corner entries below the original matrix are not part of it
+        for d in range(l + u + 1):
+            if j + d - u >= n:
+                bp[j, d] = 0.0
+    bp[n:, u] = 1.0
+    Up = np.zeros((U.shape[0], npad)); Up[:, :n] = U
+    Vp = np.zeros((npad, V.shape[1])); Vp[:n] = V
+    return bp, Up, Vp, np.concatenate([b, np.zeros(e)])
+
+
 def chunk_reduce(bands, U, V, b, l, u, r0, r1):
     """Stage 1 for one chunk.  Returns (Rrows, left) where Rrows[k] = record of the R row of local column k and
     left = the (lp + r) x (lp + r + lp + r + 1) leftover block [win(S_{c+1}) | gen | C_L | Tprev | rhs]."""
@@ -142,13 +175,22 @@ def qr_rows(M, ncols):
     return M
 
 
-def solve_chunked(bands, U, V, b, l, u, P):
-    """x = A \\ b through P chunks.  bands (n, l+u+1), U (r, n), V (n, r), b (n)."""
+def solve_chunked(bands, U, V, b, l, u, P, regular=False):
+    """x = A \\ b through P chunks.  bands (n, l+u+1), U (r, n), V (n, r), b (n).  regular=True uses the CUDA path's padded
+    chunk layout, otherwise near-equal chunks of the unpadded system."""
+    n_in = bands.shape[0]
+    if regular:
+        P, bnd = regular_layout(n_in, l + u, P)
+        bands, U, V, b = pad_system(bands, U, V, b, l, u, bnd[-1])
+        return _solve_chunked(bands, U, V, b, l, u, P, bnd)[:n_in]
+    return _solve_chunked(bands, U, V, b, l, u, P, chunk_bounds(n_in, P))
+
+
+def _solve_chunked(bands, U, V, b, l, u, P, bnd):
     n = bands.shape[0]
     r = U.shape[0]
     lp = l + u
     w = lp + r
-    bnd = chunk_bounds(n, P)
     R, F, G, h = [], [], [], []
     for c in range(P):
         Rr, left = chunk_reduce(bands, U, V, b, l, u, bnd[c], bnd[c + 1])

@@ -21,8 +21,9 @@ def test_chunked_algebra_matches_dense(n, l, u, r, P):
     b = rng.standard_normal(n)
     A = dense(bands, U, V, l, u)
     x0 = np.linalg.solve(A, b)
-    x = solve_chunked(bands, U, V, b, l, u, P)
-    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) <= 1e-12 * max(1.0, np.linalg.cond(A) / 100)
+    for regular in (False, True):
+        x = solve_chunked(bands, U, V, b, l, u, P, regular=regular)
+        assert np.linalg.norm(x - x0) / np.linalg.norm(x0) <= 1e-12 * max(1.0, np.linalg.cond(A) / 100)
 
 
 def test_chunked_algebra_readme_known_answer():

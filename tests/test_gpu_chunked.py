@@ -12,7 +12,7 @@ import pytest
 sys.path.insert(0, str(Path(__file__).parent / "emul"))
 import oracle  # noqa: E402
 from helpers import readme_expz  # noqa: E402
-from sof_reference import chunk_bounds, chunk_reduce, dense, solve_chunked  # noqa: E402
+from sof_reference import chunk_reduce, dense, pad_system, regular_layout  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -41,14 +41,15 @@ def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P):
     bands, U, V, b = _rand(rng, n, l, u, r)
     A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
     x = A.solve(b, nchunks=P)
-    assert A.chunks == P
     lp, w = l + u, l + u + r
+    P, bnd = regular_layout(n, lp, P)
+    assert A.chunks == P
+    pb, pU, pV, pbv = pad_system(bands, U, V, b, l, u, bnd[-1])
     # stage 1 output: level-0 reduced blocks [F | G | h] per chunk, against the numpy restatement (rows may differ by
     # nothing: same reflector convention and order)
     E = A._debug(0, P * w * (2 * w + 1)).reshape(P, w, 2 * w + 1)
-    bnd = chunk_bounds(n, P)
     for c in range(P):
-        _, left = chunk_reduce(bands, U, V, b, l, u, bnd[c], bnd[c + 1])
+        _, left = chunk_reduce(pb, pU, pV, pbv, l, u, bnd[c], bnd[c + 1])
         G0, C0, T0 = lp + 1, lp + 1 + r, lp + 1 + r + lp
         ref = np.hstack([left[:, C0:C0 + lp], left[:, T0:T0 + r], left[:, 0:lp], left[:, G0:G0 + r], left[:, -1:]])
         assert np.allclose(E[c], ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max()), (c, np.abs(E[c] - ref).max())
@@ -62,6 +63,7 @@ def test_chunked_readme_known_answer(chunked, ctx):
     A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
     for P in (1, 2, 3):
         x = A.solve(b, nchunks=P)
+        assert A.chunks == P
         ref = np.array([1 / math.factorial(k) for k in range(16)])
         # normwise: the partitioned factorisation is backward stable, not componentwise accurate on the graded tail
         assert np.linalg.norm(x[:16] - ref) / np.linalg.norm(ref) <= 1e-14
