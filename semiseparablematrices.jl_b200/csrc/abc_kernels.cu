@@ -21,7 +21,8 @@
 namespace ssm {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int ABC_PAD = 64;
+constexpr int ABC_PAD = 128;
+constexpr int ABC_CPW = 4;      // chunks per warp in stage 1: chunk lengths change only at multiples of this
 
 struct AbcArgs {
     const double *REC, *V, *b;   // operands
@@ -72,87 +73,126 @@ struct AbcDims {
     static_assert(3 * W + 1 <= 32, "merge block must fit one warp");
 };
 
-template <int LP, int R>
-__global__ void __launch_bounds__(128, 4) abc_qr_kernel(const AbcArgs a) {
+// GS lanes cooperate on one chunk, so a warp sweeps 32/GS chunks at once: lane gl of a group holds the columns
+// col = slot*GS + gl, slot = 0..CS-1, of the chunk's active block.  (GS = 32 is one chunk per warp; GS = 8 cuts the shuffle and
+// redundant-reflector cost per chunk by 4 — every shuffle instruction serves four chunks.)  All chunks of one warp have the
+// same length (abc_layout makes jx a multiple of 32/GS), so the groups stay in lock step.
+template <int LP, int R, int GS>
+__global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     using D = AbcDims<LP, R>;
     constexpr int PW = D::PW, NR = D::NR, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, NF = D::NF, W = D::W;
-    __shared__ double stage[4][NR][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int c = blockIdx.x * 4 + wib;
-    if (c >= a.P) return;
+    constexpr int CS = (NC + GS - 1) / GS, CPW = 32 / GS, RQ = R > 0 ? R : 1;
+    __shared__ double stage[4][CS][NR][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane % GS, grp = lane / GS;
+    int c = (blockIdx.x * 4 + wib) * CPW + grp;
+    if ((blockIdx.x * 4 + wib) * CPW >= a.P) return;
+    const bool live = c < a.P;                                // a partial last warp repeats chunk P-1 in its spare groups (no stores)
+    if (!live) c = a.P - 1;
     const int64_t r0 = chunk_start(a, c);
-    const int m = a.m0 + (c < a.jx ? PW : 0), nsteps = m - LP;      // nsteps is a multiple of PW
+    const int m = a.m0 + (c < a.jx ? PW : 0), nsteps = m - LP;      // a multiple of PW, the same for every group of the warp
     const int u = a.u;
-    const bool isW = lane < PW, isG = lane >= G0 && lane < C0, isC = lane >= C0 && lane < T0, isT = lane >= T0 && lane < B0, isB = lane == B0;
     const double *rec0 = a.REC + r0 * NF;
-    const double *v0 = a.V + (r0 + u) * (R > 0 ? R : 1);      // V row of local column 0
+    const double *v0 = a.V + (r0 + u) * RQ;                   // V row of local column 0
     const double *b0 = a.b + r0;
     const int64_t brows = a.n - r0;                           // rows of b that exist from r0 on (pad rows have b = 0)
-    double A[NR];
+    const double *zero = a.V + (a.n + 8) * RQ;                // a V pad row: always 0.0
+
+    // column roles of this lane's slots
+    bool isW[CS], isG[CS], isC[CS], isT[CS], isB[CS];
+    int col[CS];
 #pragma unroll
-    for (int s = 0; s < NR; ++s) A[s] = 0.0;
+    for (int sl = 0; sl < CS; ++sl) {
+        col[sl] = sl * GS + gl;
+        isW[sl] = col[sl] < PW; isG[sl] = col[sl] >= G0 && col[sl] < C0; isC[sl] = col[sl] >= C0 && col[sl] < T0;
+        isT[sl] = col[sl] >= T0 && col[sl] < B0; isB[sl] = col[sl] == B0;
+    }
+    double A[CS][NR];
+#pragma unroll
+    for (int sl = 0; sl < CS; ++sl)
+#pragma unroll
+        for (int s = 0; s < NR; ++s) A[sl][s] = 0.0;
+
+    // generator value q of row slot s, broadcast inside the group
+    auto gen_of = [&](int s, int q) -> double { return __shfl_sync(FULL, A[(G0 + q) / GS][s], (G0 + q) % GS, GS); };
 
     // ---- prologue: band rows 0..LP-1 (slot = row) and the R tail rows (slots PW..) ----
 #pragma unroll
     for (int ip = 0; ip < LP; ++ip) {
         const double *rec = rec0 + (int64_t)ip * NF;
-        double val = 0.0;
-        if (isW && lane <= ip) val = rec[LP - ip + lane];
-        if (isG) val = rec[PW + lane - G0];
-        if (isC && ip <= lane - C0) val = rec[lane - C0 - ip];
-        if (isB && ip < brows) val = b0[ip];
-        double f = 0.0;
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const double g = __shfl_sync(FULL, val, G0 + q);
-            const double vq = isW ? v0[(int64_t)lane * R + q] : 0.0;
-            f = fma(g, vq, f);
+        for (int sl = 0; sl < CS; ++sl) {
+            double val = 0.0;
+            if (isW[sl] && col[sl] <= ip) val = rec[LP - ip + col[sl]];
+            if (isG[sl]) val = rec[PW + col[sl] - G0];
+            if (isC[sl] && ip <= col[sl] - C0) val = rec[col[sl] - C0 - ip];
+            if (isB[sl] && ip < brows) val = b0[ip];
+            A[sl][ip] = val;
         }
-        if (isW && lane > ip) val = f;
-        A[ip] = val;
+        double gq[RQ];
+#pragma unroll
+        for (int q = 0; q < R; ++q) gq[q] = gen_of(ip, q);
+#pragma unroll
+        for (int sl = 0; sl < CS; ++sl) {
+            if (sl * GS >= PW) continue;
+            double f = 0.0;
+#pragma unroll
+            for (int q = 0; q < R; ++q) f = fma(gq[q], isW[sl] ? v0[(int64_t)col[sl] * R + q] : 0.0, f);
+            if (isW[sl] && col[sl] > ip) A[sl][ip] = f;
+        }
     }
 #pragma unroll
-    for (int t = 0; t < R; ++t) {
-        double val = 0.0;
-        if (isW) val = -v0[(int64_t)lane * R + t];
-        if (isG && lane - G0 == t) val = -1.0;
-        if (isT && lane - T0 == t) val = 1.0;
-        A[PW + t] = val;
-    }
+    for (int t = 0; t < R; ++t)
+#pragma unroll
+        for (int sl = 0; sl < CS; ++sl) {
+            double val = 0.0;
+            if (isW[sl]) val = -v0[(int64_t)col[sl] * R + t];
+            if (isG[sl] && col[sl] - G0 == t) val = -1.0;
+            if (isT[sl] && col[sl] - T0 == t) val = 1.0;
+            A[sl][PW + t] = val;
+        }
 
-    // Per-lane stream of the entering rows: window / generator lanes walk the row records, the rhs lane walks b, all other
-    // lanes re-read one zero (a V pad row), so the load needs no predicate.  Window lanes read field d = (lane - k) mod PW,
-    // which is also the position of their entry in the emitted record.
-    int d = isW ? lane : 0;                                   // phase 0
-    const double *ep; int estride;
-    if (isW || isG) { ep = rec0 + (int64_t)LP * NF + (isG ? PW + lane - G0 : 0); estride = NF; }
-    else if (isB) { ep = b0 + LP; estride = 1; }
-    else { ep = a.V + (a.n + 8) * (R > 0 ? R : 1); estride = 0; }
+    // Per-slot stream of the entering rows: window / generator columns walk the row records, the rhs column walks b, all other
+    // columns re-read one zero, so the load needs no predicate.  A window column reads field d = (col - k) mod PW, which is also
+    // the position of its entry in the emitted record.
+    int d[CS]; const double *ep[CS]; int estride[CS]; double nxt[CS]; double *fr[CS]; bool emit[CS];
+    int64_t brem = brows - LP;                                // rows of b left for the rhs column
+#pragma unroll
+    for (int sl = 0; sl < CS; ++sl) {
+        d[sl] = isW[sl] ? col[sl] : 0;                        // phase 0
+        if (isW[sl] || isG[sl]) { ep[sl] = rec0 + (int64_t)LP * NF + (isG[sl] ? PW + col[sl] - G0 : 0); estride[sl] = NF; }
+        else if (isB[sl]) { ep[sl] = b0 + LP; estride[sl] = 1; }
+        else { ep[sl] = zero; estride[sl] = 0; }
+        nxt[sl] = (isB[sl] && brem <= 0) ? 0.0 : ep[sl][d[sl]];
+        fr[sl] = a.FR + r0 * NC + (isW[sl] ? 0 : col[sl]);
+        emit[sl] = live && col[sl] < NC;
+    }
     const double *vp = v0 + (int64_t)(LP + 1) * R;            // V row of the column entering after step 0
-    double vnx[R > 0 ? R : 1];
+    double vnx[RQ];
 #pragma unroll
     for (int q = 0; q < R; ++q) vnx[q] = vp[q];
-    double *fr = a.FR + r0 * NC + (isW ? 0 : lane);
-    const bool emit = lane < NC;
-    int64_t brem = brows - LP;                                // rhs lane: rows of b left
-    double nxt = (isB && brem <= 0) ? 0.0 : ep[isW ? d : 0];
+
     for (int kb = 0; kb < nsteps; kb += PW) {
 #pragma unroll
         for (int PH = 0; PH < PW; ++PH) {
             const int es = (PH + LP) % PW;                    // slot of the entering row
-            A[es] = nxt;
-            // prefetch the row entering at the next step (rows past the chunk are the next chunk's or the identity pad)
-            ep += estride; --brem;
-            const int dn = isW ? (d == 0 ? LP : d - 1) : 0;
-            nxt = (isB && brem <= 0) ? 0.0 : ep[dn];
-            double vn[R > 0 ? R : 1];
+            const int pl = PH % GS, ps = PH / GS;             // lane-in-group / column slot of the pivot column
+            --brem;
+#pragma unroll
+            for (int sl = 0; sl < CS; ++sl) {
+                A[sl][es] = nxt[sl];
+                // prefetch the row entering at the next step (rows past the chunk are the next chunk's or the identity pad)
+                ep[sl] += estride[sl];
+                const int dn = isW[sl] ? (d[sl] == 0 ? LP : d[sl] - 1) : 0;
+                nxt[sl] = (isB[sl] && brem <= 0) ? 0.0 : ep[sl][dn];
+            }
+            double vn[RQ];
             vp += R;
 #pragma unroll
-            for (int q = 0; q < R; ++q) { vn[q] = vnx[q]; vnx[q] = vp[q]; }   // one step ahead (the row past the chunk is the next chunk's / pad)
-            // reflector from the pivot column (held by lane PH), LinearAlgebra.reflector! convention
+            for (int q = 0; q < R; ++q) { vn[q] = vnx[q]; vnx[q] = vp[q]; }   // one step ahead
+            // reflector from the pivot column, LinearAlgebra.reflector! convention
             double x[NR];
 #pragma unroll
-            for (int s = 0; s < NR; ++s) x[s] = __shfl_sync(FULL, A[s], PH);
+            for (int s = 0; s < NR; ++s) x[s] = __shfl_sync(FULL, A[ps][s], pl, GS);
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
             for (int s = 0; s < NR; ++s) { if (s % 3 == 0) q0 = fma(x[s], x[s], q0); else if (s % 3 == 1) q1 = fma(x[s], x[s], q1); else q2 = fma(x[s], x[s], q2); }
@@ -166,49 +206,62 @@ __global__ void __launch_bounds__(128, 4) abc_qr_kernel(const AbcArgs a) {
             const double xi = xp + nu;
             const double inv = nz ? fast_rcp(xi) : 0.0;
             const double tau = nz ? xi * copysign(rs, xp) : 0.0;
-            double d0 = A[PH], d1 = 0.0, d2 = 0.0;
 #pragma unroll
-            for (int s = 0; s < NR; ++s) {
-                if (s == PH) continue;
-                x[s] *= inv;                                  // v_s
-                if (s % 3 == 0) d0 = fma(x[s], A[s], d0); else if (s % 3 == 1) d1 = fma(x[s], A[s], d1); else d2 = fma(x[s], A[s], d2);
+            for (int s = 0; s < NR; ++s) if (s != PH) x[s] *= inv;    // v_s
+#pragma unroll
+            for (int sl = 0; sl < CS; ++sl) {
+                double d0 = A[sl][PH], d1 = 0.0;
+#pragma unroll
+                for (int s = 0; s < NR; ++s) {
+                    if (s == PH) continue;
+                    if (s & 1) d1 = fma(x[s], A[sl][s], d1); else d0 = fma(x[s], A[sl][s], d0);
+                }
+                const double dot = (d0 + d1) * tau;
+#pragma unroll
+                for (int s = 0; s < NR; ++s) A[sl][s] = (s == PH) ? A[sl][s] - dot : fma(-x[s], dot, A[sl][s]);
             }
-            const double dot = ((d0 + d1) + d2) * tau;
-#pragma unroll
-            for (int s = 0; s < NR; ++s) A[s] = (s == PH) ? A[s] - dot : fma(-x[s], dot, A[s]);
-            if (lane == PH) A[PH] = nz ? -nu : xp;
+            if (gl == pl) A[ps][PH] = nz ? -nu : xp;
             // emit the finished row (canonical order: window entry of column k+t at position t)
-            if (emit) fr[isW ? d : 0] = A[PH];
-            fr += NC;
-            d = dn;
-            // the window slides: local column k+LP+1 replaces the pivot column in lane PH (fill region of every surviving row)
+#pragma unroll
+            for (int sl = 0; sl < CS; ++sl) {
+                if (emit[sl]) fr[sl][isW[sl] ? d[sl] : 0] = A[sl][PH];
+                fr[sl] += NC;
+                d[sl] = isW[sl] ? (d[sl] == 0 ? LP : d[sl] - 1) : 0;
+            }
+            // the window slides: local column k+LP+1 replaces the pivot column (fill region of every surviving row)
 #pragma unroll
             for (int s = 0; s < NR; ++s) {
                 if (s == PH) continue;
                 double f = 0.0;
 #pragma unroll
-                for (int q = 0; q < R; ++q) f = fma(__shfl_sync(FULL, A[s], G0 + q), vn[q], f);
-                if (lane == PH) A[s] = f;
+                for (int q = 0; q < R; ++q) f = fma(gen_of(s, q), vn[q], f);
+                if (gl == pl) A[ps][s] = f;
             }
         }
     }
     // ---- leftover rows -> level-0 reduced block  [F = C_L | Tprev,  G = window(S_{c+1}) | generator,  h] ----
 #pragma unroll
-    for (int s = 0; s < NR; ++s) stage[wib][s][lane] = A[s];
+    for (int sl = 0; sl < CS; ++sl)
+#pragma unroll
+        for (int s = 0; s < NR; ++s) stage[wib][sl][s][lane] = A[sl][s];
     __syncwarp();
-    int dst = -1;
-    if (isW) {                                   // lane holds local column jp == lane (mod PW) in [m-LP, m]; column m is not part of the chunk
-        int jp = (m - LP) + ((lane - (m - LP)) % PW + PW) % PW;
-        if (jp <= m - 1) dst = W + (jp - (m - LP));
-    } else if (isG) dst = W + LP + (lane - G0);
-    else if (isC) dst = lane - C0;
-    else if (isT) dst = LP + (lane - T0);
-    else if (isB) dst = 2 * W;
+    if (!live) return;
     double *E = a.E0 + (int64_t)c * W * (2 * W + 1);
-    if (dst >= 0) {
-        for (int row = 0; row < W; ++row) {
-            const int slot = row < LP ? (m - LP + row) % PW : PW + (row - LP);
-            E[row * (2 * W + 1) + dst] = stage[wib][slot][lane];
+#pragma unroll
+    for (int sl = 0; sl < CS; ++sl) {
+        int dst = -1;
+        if (isW[sl]) {                             // window position col holds local column jp == col (mod PW) in [m-LP, m]; column m is not part of the chunk
+            int jp = (m - LP) + ((col[sl] - (m - LP)) % PW + PW) % PW;
+            if (jp <= m - 1) dst = W + (jp - (m - LP));
+        } else if (isG[sl]) dst = W + LP + (col[sl] - G0);
+        else if (isC[sl]) dst = col[sl] - C0;
+        else if (isT[sl]) dst = LP + (col[sl] - T0);
+        else if (isB[sl]) dst = 2 * W;
+        if (dst >= 0) {
+            for (int row = 0; row < W; ++row) {
+                const int slot = row < LP ? (m - LP + row) % PW : PW + (row - LP);
+                E[row * (2 * W + 1) + dst] = stage[wib][sl][slot][lane];
+            }
         }
     }
 }
@@ -657,13 +710,15 @@ static void abc_layout(int64_t n, int lp, int &P, int &m0, int &jx) {
     m0 = (int)(pw * q - 1);
     const int64_t rem = n - (int64_t)P * m0;
     jx = rem > 0 ? (int)((rem + pw - 1) / pw) : 0;
+    jx = ((jx + ABC_CPW - 1) / ABC_CPW) * ABC_CPW;            // all chunks of one stage-1 warp have the same length
+    if (jx > P) jx = P;
 }
 
 static int abc_default_chunks(const ssm_abc *A) {
     // ~2048 rows per chunk; at least 2*lp+2 rows each; enough warps to cover the SMs when n allows
-    int64_t P = A->n / 2048;
+    int64_t P = A->n / 1024;
     const int64_t pmax = A->n / (2 * A->lp + 2 + 8);
-    if (P > 16384) P = 16384;
+    if (P > 32768) P = 32768;
     if (P > pmax) P = pmax;
     if (P < 1) P = 1;
     return (int)P;
@@ -676,7 +731,9 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     constexpr int W = D::W, EW = 2 * W + 1, TW = 3 * W + 1;
     AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P, A->m0, A->jx, LP + 1};
     const unsigned gchunks = (unsigned)((P + 3) / 4);
-    abc_qr_kernel<LP, R><<<gchunks, 128, 0, c->stream>>>(a);
+    constexpr int GS = 8;                                      // lanes per chunk in stage 1 (4 chunks per warp)
+    static_assert(ABC_CPW == 32 / GS, "abc_layout must round jx to the chunks-per-warp of stage 1");
+    abc_qr_kernel<LP, R, GS><<<(unsigned)((P + 4 * ABC_CPW - 1) / (4 * ABC_CPW)), 128, 0, c->stream>>>(a);
     c->launches++;
     // levels: level t has nlev[t] blocks stored at E + off[t]
     std::vector<int> cnt; std::vector<int64_t> eoff, toff;

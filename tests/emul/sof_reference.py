@@ -57,6 +57,7 @@ def regular_layout(n, lp, P):
     m0 = pw * q - 1
     rem = n - P * m0
     jx = (rem + pw - 1) // pw if rem > 0 else 0
+    jx = min(P, -(-jx // 4) * 4)            # chunk lengths change only at multiples of the 4 chunks one stage-1 warp sweeps
     return P, [c * m0 + pw * min(c, jx) for c in range(P + 1)]
 
 
