@@ -495,34 +495,56 @@ __global__ void __launch_bounds__(128) abc_bs_kernel(const AbcArgs a) {
         for (int q = 0; q < R; ++q) acc = fma(-my[T0 + q], zl[LP + q], acc);
         double g[RQ];
 #pragma unroll
-        for (int q = 0; q < R; ++q) { g[q] = my[G0 + q]; acc = fma(-g[q], sb[q], acc); }
+        for (int q = 0; q < R; ++q) g[q] = my[G0 + q];
         const double inv = fast_rcp(my[0]);
+        // sb is the UNIFORM running tail sum: after column j has been added it covers every column >= j.  Lane k takes its fill term
+        // Ufinal[k,:].sb at the moment j = k+LP+1 (everything right of its band); band terms come from its record in shared memory.
+        double sbn[RQ];                                          // tail sum over columns >= k0+LP for the next block
+#pragma unroll
+        for (int q = 0; q < R; ++q) sbn[q] = sb[q];
+        auto add_column = [&](const int j, const double xj, const bool tail) {
+            const int t = j - k;
+            if (tail) {
+                double fill = acc;
+#pragma unroll
+                for (int q = 0; q < R; ++q) { sb[q] = fma(vs[(j - k0) * R + q], xj, sb[q]); fill = fma(-g[q], sb[q], fill); }
+                if (t == LP + 1) acc = fill;
+            }
+            const double band = my[min(max(t, 0), LP)];         // clamped: lanes outside their band read a dummy
+            const double coef = (t >= 1 && t <= LP) ? band : 0.0;
+            acc = fma(-coef, xj, acc);
+        };
+        // lanes whose fill starts right of everything seen in this block (k + LP + 1 >= kend + LP) take the incoming tail sum now
+        if (k + 1 >= kend) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) acc = fma(-g[q], sb[q], acc);
+        }
         // (a) the LP known columns right of the block, kend+LP-1 .. kend
 #pragma unroll
         for (int tt = LP - 1; tt >= 0; --tt) {
-            const int j = kend + tt;
-            const double xj = __shfl_sync(FULL, xw, tt);
-            const int t = j - k;
-            double coef = 0.0;
+            add_column(kend + tt, __shfl_sync(FULL, xw, tt), true);
+            if (kend + tt == k0 + LP) {                          // short block (fewer than LP+1 rows): the next block's tail starts here
 #pragma unroll
-            for (int q = 0; q < R; ++q) { const double vq = vs[(j - k0) * R + q]; coef = fma(g[q], vq, coef); if (j >= k0 + LP) sb[q] = fma(vq, xj, sb[q]); }
-            const double band = my[min(t, LP)];               // t >= 1 here
-            if (t <= LP) coef = band;
-            acc = fma(-coef, xj, acc);
+                for (int q = 0; q < R; ++q) sbn[q] = sb[q];
+            }
         }
         // (b) the block's own rows, last first: lane j-k0 owns x_j = acc * inv once every later column has been added
         double cand = acc * inv;
-        for (int j = kend - 1; j >= k0; --j) {
-            const double xj = __shfl_sync(FULL, cand, j - k0);
-            const int t = j - k;
-            double coef = 0.0;
-#pragma unroll
-            for (int q = 0; q < R; ++q) { const double vq = vs[(j - k0) * R + q]; coef = fma(g[q], vq, coef); if (j >= k0 + LP) sb[q] = fma(vq, xj, sb[q]); }
-            const double band = my[min(max(t, 0), LP)];       // clamped: lanes above the band / below the diagonal read a dummy
-            if (t <= LP) coef = (t >= 1) ? band : 0.0;
-            acc = fma(-coef, xj, acc);
+        int j = kend - 1;
+        for (; j >= k0 + LP; --j) {                              // columns that still feed the tail sum of this or the next block
+            add_column(j, __shfl_sync(FULL, cand, j - k0), true);
             cand = acc * inv;
         }
+        if (kend - 1 >= k0 + LP) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) sbn[q] = sb[q];
+        }
+        for (; j >= k0; --j) {                                   // the first LP rows: band terms only
+            add_column(j, __shfl_sync(FULL, cand, j - k0), false);
+            cand = acc * inv;
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) sb[q] = sbn[q];
         // lanes k <= j never change after their own turn, so cand is x_k
         if (k < kend && k < xrows) xloc[k] = cand;
         // next block's right neighbours = local columns k0 .. k0+LP-1: this block's first rows, then (short block) the old window
@@ -715,8 +737,8 @@ static void abc_layout(int64_t n, int lp, int &P, int &m0, int &jx) {
 }
 
 static int abc_default_chunks(const ssm_abc *A) {
-    // ~2048 rows per chunk; at least 2*lp+2 rows each; enough warps to cover the SMs when n allows
-    int64_t P = A->n / 1024;
+    // ~512 rows per chunk (measured best at n = 2^24: 8192 stage-1 warps of 4 chunks), at most 32768 chunks
+    int64_t P = A->n / 512;
     const int64_t pmax = A->n / (2 * A->lp + 2 + 8);
     if (P > 32768) P = 32768;
     if (P > pmax) P = pmax;
