@@ -234,11 +234,17 @@ static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
 
 // auto (0): measured on B200 at config 2 — the QR sweep is fastest with direct loads (it is register-rich and
 // store-heavy), the two light solve kernels with the bulk-async ring (profiles/README.md)
-static int effective_variant(const ssm_ctx *c, int kernel_default) { return c->ab_variant == 0 ? kernel_default : c->ab_variant; }
+// Below ~7 single-warp CTAs per SM there are too few warps to hide HBM latency behind one-step-ahead register loads, and the ring's
+// deep bulk-async prefetch wins for the QR sweep as well (measured: n=1024 x 16,384 systems 0.81 -> 0.47 ms, n=8192 x 4,096 5.1 -> 3.6 ms).
+static int effective_variant(const ssm_ctx *c, int kernel_default, int64_t ntiles = 1 << 30) {
+    if (c->ab_variant != 0) return c->ab_variant;
+    if (kernel_default == 1 && ntiles <= (int64_t)c->sm_count * 7) return 2;
+    return kernel_default;
+}
 
 int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, bool with_rhs, bool store_q) {
     if (ntiles <= 0) return 0;
-    const int variant = effective_variant(c, 1);
+    const int variant = effective_variant(c, 1, ntiles);
     if (variant != 9) {
 #define X(L_, U_, R_) \
     if (l == L_ && u == U_ && r == R_) return qr_inst<L_, U_, R_>(c, ntiles, a, with_rhs, store_q, variant);

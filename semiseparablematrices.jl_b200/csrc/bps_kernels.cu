@@ -76,28 +76,38 @@ __global__ void __launch_bounds__(128) bps_reduce_kernel(const double *REC, cons
 // ---------------------------------------------------------------------------------------------------------
 constexpr int BPS_NST = 16;   // window ring depth: M rows back + L rows ahead + look-ahead
 
-template <int L, int M, int R, int P>
-__global__ void __launch_bounds__(32) bps_qr_kernel(const double *REC, const double *GT, double *OUT, int n, int64_t np, int64_t npo) {
+// SPLIT = 1: one warp per tile of 32 systems.  SPLIT = 2: a CTA of two warps per tile, each warp owning 16 systems (lanes 16-31
+// shadow lanes 0-15 and do not store), both reading one shared window ring: the sweep is latency bound — a batch of 16,384 systems
+// is only 512 warps, fewer than the 592 warp schedulers of a B200 — so halving the systems per warp doubles the warps in flight at
+// the cost of idle lanes, not of HBM or TMA traffic.
+constexpr int BPS_NST_SPLIT = 12;  // 46 KB per CTA: four CTAs (all 512 tiles of config 3) stay co-resident per SM
+template <int L, int M, int R, int P, int SPLIT>
+__global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, const double *GT, double *OUT, int n, int64_t np, int64_t npo) {
     using D = BpsDims<L, M, R, P>;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int64_t tile = blockIdx.x;
-    WindowRing<D::NFA, BPS_NST> win;
+    const int sl = SPLIT == 1 ? lane : (lane & 15) + 16 * (int)(threadIdx.x >> 5);    // system column of the tile this thread computes
+    const bool writer = SPLIT == 1 || lane < 16;
+    WindowRing<D::NFA, SPLIT == 1 ? BPS_NST : BPS_NST_SPLIT, SPLIT> win;
     // sequence index k <-> row k - M; record of row rho sits at BPS_FRONT + rho
     win.init(REC + (tile * np + BPS_FRONT - M) * D::NFA * 32, smem, (int64_t)n + L + M);
+    win.col = sl;
     double gt[R * R];
 #pragma unroll
-    for (int e = 0; e < R * R; ++e) gt[e] = __ldg(GT + (tile * (R * R) + e) * 32 + lane);
+    for (int e = 0; e < R * R; ++e) gt[e] = __ldg(GT + (tile * (R * R) + e) * 32 + sl);
     BpsState<L, M, R, P> st;
     bps_init<L, M, R, P>(st, gt);
-    double *out = OUT + tile * npo * D::NFO * 32 + lane;
+    double *out = OUT + tile * npo * D::NFO * 32 + sl;
     for (int k = 0; k < L + M; ++k) win.wait(k);          // rows -M .. L-1
     for (int q = 0; q < n; ++q) {
         win.wait((int64_t)q + L + M);                      // row q+L
         double o[D::NFO];
         bps_step<L, M, R, P>(st, [&](int rel, int f) { return win.rec((int64_t)q + rel + M)[f * 32]; }, q == n - 1, o);
+        if (writer) {
 #pragma unroll
-        for (int f = 0; f < D::NFO; ++f) out[((int64_t)q * D::NFO + f) * 32] = o[f];
+            for (int f = 0; f < D::NFO; ++f) out[((int64_t)q * D::NFO + f) * 32] = o[f];
+        }
         win.release(q);                                    // row q-M leaves the window
     }
 }
@@ -342,10 +352,19 @@ static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
     using D = BpsDims<L, M, R, P>;
     bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)A->ntiles, 128, 0, c->stream>>>(A->REC->p, nullptr, F->GT->p, nullptr, A->n, A->np, 0);
     c->launches++;
-    const size_t smem = WindowRing<D::NFA, BPS_NST>::smem_bytes();
-    auto kern = bps_qr_kernel<L, M, R, P>;
-    SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+    // split tiles over two warps while the batch cannot give every warp scheduler ~2 warps (ab_variant 1 / 2 force off / on)
+    const bool split = c->ab_variant == 2 || (c->ab_variant == 0 && A->ntiles < (int64_t)c->sm_count * 8);
+    if (split) {
+        const size_t smem = WindowRing<D::NFA, BPS_NST_SPLIT, 2>::smem_bytes();
+        auto kern = bps_qr_kernel<L, M, R, P, 2>;
+        SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)A->ntiles, 64, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+    } else {
+        const size_t smem = WindowRing<D::NFA, BPS_NST, 1>::smem_bytes();
+        auto kern = bps_qr_kernel<L, M, R, P, 1>;
+        SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+    }
     c->launches++;
     SSM_CUDA(cudaGetLastError());
     return 0;

@@ -154,39 +154,44 @@ template <int NF0, int NF1, int NF2, int DIR> using RingLoaderD = RingLoader<NF0
 // M rows back and L rows ahead).  Record k of the sequence lives in slot k mod NST (NST a power of two) from
 // the moment its bulk copy lands until release(k) re-arms the slot with record k+NST.  Lanes read fields in
 // place: rec(k)[f*32] is conflict-free (lane-fastest records).
-template <int NF, int NST>
+// NW = 1: the ring belongs to one warp.  NW = 2: two warps of one CTA share it — each computes 16 of the tile's 32 systems (set
+// `col`), thread 0 issues the copies, and the slot is re-armed after a CTA barrier (kernels that are latency bound at one warp per
+// tile double their warps in flight this way without moving a byte more).  NST need not be a power of two.
+template <int NF, int NST, int NW = 1>
 struct WindowRing {
-    static_assert((NST & (NST - 1)) == 0, "NST must be a power of two");
     static constexpr uint32_t REC_BYTES = NF * 256;
     const double *g;      // tile base of record 0 of the sequence (not lane adjusted)
     double *ring;
     uint32_t bar0;
-    int lane;
+    int col;              // lane column of the tile this thread reads
+    bool issuer;
     int64_t nseq;
     static __host__ __device__ size_t smem_bytes() { return (size_t)NST * REC_BYTES + (size_t)NST * 8; }
     __device__ __forceinline__ void issue(int64_t k) {
-        const int s = (int)(k & (NST - 1));
+        const int s = (int)(k % NST);
         const uint32_t bar = bar0 + 8u * s;
         mbar_expect_tx(bar, REC_BYTES);
         bulk_g2s(smem_u32(ring + (size_t)s * NF * 32), g + k * NF * 32, REC_BYTES, bar);
     }
+    __device__ __forceinline__ void sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
     __device__ __forceinline__ void init(const double *tile_first_record, void *smem, int64_t total) {
-        lane = threadIdx.x & 31;
+        col = threadIdx.x & 31;
+        issuer = threadIdx.x == 0;
         g = tile_first_record; nseq = total;
         ring = reinterpret_cast<double *>(smem);
         bar0 = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)NST * REC_BYTES);
-        if (lane == 0) {
+        if (issuer) {
             for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8u * s, 1);
             fence_barrier_init();
         }
-        __syncwarp();
-        if (lane == 0) for (int64_t k = 0; k < NST && k < total; ++k) issue(k);
+        sync();
+        if (issuer) for (int64_t k = 0; k < NST && k < total; ++k) issue(k);
     }
-    __device__ __forceinline__ void wait(int64_t k) { mbar_wait(bar0 + 8u * (uint32_t)(k & (NST - 1)), (uint32_t)((k / NST) & 1)); }
-    __device__ __forceinline__ const double *rec(int64_t k) const { return ring + (size_t)(k & (NST - 1)) * NF * 32 + lane; }
+    __device__ __forceinline__ void wait(int64_t k) { mbar_wait(bar0 + 8u * (uint32_t)(k % NST), (uint32_t)((k / NST) & 1)); }
+    __device__ __forceinline__ const double *rec(int64_t k) const { return ring + (size_t)(k % NST) * NF * 32 + col; }
     __device__ __forceinline__ void release(int64_t k) {
-        __syncwarp();
-        if (lane == 0 && k + NST < nseq) issue(k + NST);
+        sync();
+        if (issuer && k + NST < nseq) issue(k + NST);
     }
 };
 
