@@ -113,3 +113,53 @@ class Job:
         if self._dist is not None and self._dist.is_initialized():
             self._dist.destroy_process_group()
             self._dist = None
+
+
+def plan_groups(groups, world: int, min_piece_systems: int = 16384):
+    """Work plan for a sweep over several batch shapes (BASELINE config 5: n = 256 .. 8192, 1M systems).
+
+    ``groups`` = [(n, nb), ...]; cost of a piece = n * systems (the sweeps are O(n) per system and HBM bound).  Splitting EVERY
+    group across all ranks leaves each rank with batches too small to fill a B200 at large n (a sweep is a serial chain per
+    warp: 4,096 systems are 128 warps for 148 SMs), so whole groups are the unit: longest-processing-time-first assignment, and
+    only the largest piece of the most loaded rank is halved (never below ``min_piece_systems``, cuts on 32-system tiles) while
+    that lowers the makespan.  Returns ``plan[rank] = [(group_index, s0, s1), ...]`` — every system exactly once."""
+    pieces = [(gi, 0, nb) for gi, (n, nb) in enumerate(groups)]
+
+    def cost(p):
+        return groups[p[0]][0] * (p[2] - p[1])
+
+    def lpt(ps):
+        loads, plan = [0] * world, [[] for _ in range(world)]
+        for p in sorted(ps, key=cost, reverse=True):
+            r = min(range(world), key=lambda i: loads[i])
+            plan[r].append(p); loads[r] += cost(p)
+        return plan, loads
+
+    plan, loads = lpt(pieces)
+    if world == 1:
+        return [sorted(plan[0])]
+    neutral = 0
+    for _ in range(8 * world + len(groups)):
+        worst = max(range(world), key=lambda i: loads[i])
+        best = None
+        for cand in sorted(plan[worst], key=cost, reverse=True):
+            gi, s0, s1 = cand
+            mid = s0 + (((s1 - s0) // 2) // TILE) * TILE
+            if mid - s0 < min_piece_systems or s1 - mid < min_piece_systems:
+                continue
+            trial = [p for p in pieces if p != cand] + [(gi, s0, mid), (gi, mid, s1)]
+            tplan, tloads = lpt(trial)
+            if best is None or max(tloads) < max(best[2]):
+                best = (trial, tplan, tloads)
+            if max(tloads) < max(loads):
+                break
+        if best is None or max(best[2]) > max(loads):
+            break
+        if max(best[2]) == max(loads):
+            neutral += 1
+            if neutral > 3:
+                break
+        else:
+            neutral = 0
+        pieces, plan, loads = best
+    return [sorted(p) for p in plan]

@@ -30,6 +30,26 @@ def test_shard_ranges_partition_and_match_c_abi():
                 assert max(sizes) - min(sizes) <= 32 + nb % 32
 
 
+def test_group_plan_covers_every_system_once_and_balances():
+    from ssm_b200 import sharder
+    groups = [(256, 524288), (512, 262144), (1024, 131072), (2048, 65536), (4096, 32768), (8192, 32768)]   # BASELINE configs[4]
+    total = sum(n * nb for n, nb in groups)
+    for world in (1, 2, 3, 4, 8):
+        plan = sharder.plan_groups(groups, world)
+        assert len(plan) == world
+        cover = {}
+        for pieces in plan:
+            for gi, s0, s1 in pieces:
+                assert s0 % 32 == 0 and s1 > s0
+                cover.setdefault(gi, []).append((s0, s1))
+        for gi, (n, nb) in enumerate(groups):
+            c = sorted(cover[gi])
+            assert c[0][0] == 0 and c[-1][1] == nb and all(c[i][1] == c[i + 1][0] for i in range(len(c) - 1))
+            assert all(b - a >= 16384 for a, b in c)                  # pieces stay large enough to fill a GPU
+        loads = [sum(groups[gi][0] * (b - a) for gi, a, b in pieces) for pieces in plan]
+        assert max(loads) <= 1.15 * total / world
+
+
 def _worker(rank, world, port, nb, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import oracle

@@ -4,6 +4,7 @@
   python tools/bench_configs.py c3            BPS QR, n=4096, l=m=3, r=p=2, 16,384 systems  (configs[2])
   python tools/bench_configs.py c4            one large system n=2^24, l=u=4, r=2, chunked n-axis path (configs[3])
   python tools/bench_configs.py c5            almost-banded sweep n=256..8192, 1M systems total (configs[4]), this GPU's share
+  torchrun --nproc-per-node N tools/bench_configs.py c5dist   the same sweep on N GPUs, pieces assigned by sharder.plan_groups
   python tools/bench_configs.py c2 [--variant V --stages S]   per-kernel timing of config 2 (tuning aid)
 
 Prints one JSON line per measurement; timing = CUDA events on the library's stream, 3 warm-ups, mean of `--steps`.
@@ -124,9 +125,40 @@ def c4(args, ctx):
                           "relres": rr}))
 
 
+def c5dist(args, ctx):
+    """configs[4] on N GPUs, one process per GPU (torchrun): the sharder's group plan (ssm_b200.sharder.plan_groups) decides which
+    (n, system range) pieces this rank owns; time = max over ranks of the device time for the rank's whole list."""
+    from ssm_b200 import sharder
+    job = sharder.Job(backend="nccl", device=torch.device("cuda", torch.cuda.current_device()))
+    groups = [(256, 524288), (512, 262144), (1024, 131072), (2048, 65536), (4096, 32768), (8192, 32768)]
+    plan = sharder.plan_groups(groups, job.world)
+    mine = plan[job.rank]
+    objs = []
+    for gi, s0, s1 in mine:
+        n, nb = groups[gi][0], s1 - s0
+        A = ssm.AlmostBandedMatrix.generate(n, 2, 2, 2, nb, 20261019 + 4 + 1000 * gi + s0, ctx=ctx)
+        b = ssm.Vec(ctx, n, nb).generate(20261019 + 4 + 1000 * gi + s0)
+        objs.append((A, b, ssm.Vec(ctx, n, nb), ssm.qr(A)))
+
+    def sweep():
+        for A, b, x, F in objs:
+            F.refactor(A); F.solve(b, out=x)
+    job.barrier()
+    t = timeit(sweep, args.steps) if objs else 0.0
+    tmax = job.max_over_ranks(t)
+    rr = max([float(A.residual(x, b).max()) for A, b, x, F in objs] or [0.0])
+    rrmax = job.max_over_ranks(rr)
+    per_rank = job.gather({"rank": job.rank, "ms": t, "pieces": [(groups[gi][0], s1 - s0) for gi, s0, s1 in mine]})
+    if job.rank == 0:
+        tot = sum(nb for _, nb in groups)
+        print(json.dumps({"config": "c5 sharded sweep n=256..8192, 2^20 systems, qr+ldiv!", "n_gpus": job.world, "ms": tmax, "systems_per_s": tot / (tmax * 1e-3),
+                          "relres_max": rrmax, "per_rank": per_rank}))
+    job.close()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("which", choices=["c2", "c3", "c4", "c5", "c5dist"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
@@ -135,9 +167,12 @@ if __name__ == "__main__":
     ap.add_argument("--world", type=int, default=1)
     ap.add_argument("--chunks", type=int, default=0)
     args = ap.parse_args()
-    ctx = ssm.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    import os
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    ctx = ssm.Context(dev, stream=torch.cuda.current_stream().cuda_stream)
     if args.variant:
         ctx.set_option("ab_variant", args.variant)
     if args.stages:
         ctx.set_option("pipeline_stages", args.stages)
-    {"c2": c2, "c3": c3, "c4": c4, "c5": c5}[args.which](args, ctx)
+    {"c2": c2, "c3": c3, "c4": c4, "c5": c5, "c5dist": c5dist}[args.which](args, ctx)
