@@ -103,7 +103,7 @@ def test_errors(bps, ctx):
 
 def test_full_size_config3_properties(bps, ctx):
     """BASELINE.json configs[2]: BPS QR, n=4096, l=m=3, r=p=2, 16,384 systems: residual of every system after
-    Q'b and R\; sampled factors vs the oracle."""
+    Q'b and the R solve; sampled factors vs the oracle."""
     import ssm_b200
     n, l, m, r, p, nb, seed = 4096, 3, 3, 2, 2, 16384, 20261019 + 2
     A = bps.BandedPlusSemiseparableMatrix.generate(n, l, m, r, p, nb, seed, ctx=ctx)
