@@ -96,6 +96,14 @@ int  ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t f_stride, double *
 int  ssm_abqr_ldiv(const ssm_abqr *F, ssm_vec *b);
 /* F \ b = ldiv!(F, copy(b)): x <- R \ (Q'b), b untouched (x may alias b)                                   */
 int  ssm_abqr_solve(const ssm_abqr *F, const ssm_vec *b, ssm_vec *x);
+/* ldiv!(F, B::AbstractMatrix) (:194-199): several right-hand sides per system, one pass over the factors per group of 4 or 8
+ * columns.  A matrix batch holds, per system, the Julia Matrix memory (n x nrhs column-major).                               */
+typedef struct ssm_mat ssm_mat;
+int  ssm_mat_create(ssm_ctx *ctx, int n, int nrhs, int64_t nb, ssm_mat **B);
+int  ssm_mat_destroy(ssm_mat *B);
+int  ssm_mat_set(ssm_mat *B, const double *data, int64_t stride);
+int  ssm_mat_get(const ssm_mat *B, double *data, int64_t stride);
+int  ssm_abqr_ldiv_mat(const ssm_abqr *F, ssm_mat *B);
 /* lmul!(F.Q', b) / lmul!(F.Q, b), Q = QRPackedQ(bandpart(F.factors), F.tau) (:181,201-207)                */
 int  ssm_abqr_lmul_qt(const ssm_abqr *F, ssm_vec *b);
 int  ssm_abqr_lmul_q(const ssm_abqr *F, ssm_vec *b);

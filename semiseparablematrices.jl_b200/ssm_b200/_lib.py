@@ -56,6 +56,11 @@ _SIGS = {
     "ssm_abqr_get": (C.c_int, [c_vp, c_vp, i64, c_vp, i64, c_vp, i64]),
     "ssm_abqr_ldiv": (C.c_int, [c_vp, c_vp]),
     "ssm_abqr_solve": (C.c_int, [c_vp, c_vp, c_vp]),
+    "ssm_mat_create": (C.c_int, [c_vp, C.c_int, C.c_int, i64, C.POINTER(c_vp)]),
+    "ssm_mat_destroy": (C.c_int, [c_vp]),
+    "ssm_mat_set": (C.c_int, [c_vp, c_vp, i64]),
+    "ssm_mat_get": (C.c_int, [c_vp, c_vp, i64]),
+    "ssm_abqr_ldiv_mat": (C.c_int, [c_vp, c_vp]),
     "ssm_abqr_lmul_qt": (C.c_int, [c_vp, c_vp]),
     "ssm_abqr_lmul_q": (C.c_int, [c_vp, c_vp]),
     "ssm_abqr_upper_ldiv": (C.c_int, [c_vp, c_vp]),

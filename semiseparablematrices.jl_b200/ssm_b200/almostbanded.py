@@ -345,6 +345,27 @@ class AlmostBandedQR:
         x = v.get()
         return x[0] if self.single else x
 
+    def ldiv_mat(self, B):
+        """``ldiv!(F, B::AbstractMatrix)`` (:194-199): B has shape (nb, nrhs, n) = per system the memory of a Julia n x nrhs
+        Matrix; every column is solved in one pass over the factors per group of 4 / 8 columns.  Returns an array like B."""
+        arr = np.ascontiguousarray(B, dtype=np.float64)
+        if self.single and arr.ndim == 2:
+            arr = arr[None]
+        if arr.ndim != 3 or arr.shape[0] != self.nb or arr.shape[2] != self.n:
+            raise DimensionMismatch(f"right-hand side has shape {arr.shape}, expected ({self.nb}, nrhs, {self.n})")
+        nrhs = int(arr.shape[1])
+        h = c_vp()
+        L = _lib.lib()
+        check(L.ssm_mat_create(self.ctx._h, self.n, nrhs, self.nb, C.byref(h)), "ssm_mat_create")
+        try:
+            check(L.ssm_mat_set(h, c_vp(arr.ctypes.data), 0), "ssm_mat_set")
+            check(L.ssm_abqr_ldiv_mat(self._h, h), "ssm_abqr_ldiv_mat")
+            out = np.empty_like(arr)
+            check(L.ssm_mat_get(h, c_vp(out.ctypes.data), 0), "ssm_mat_get")
+        finally:
+            L.ssm_mat_destroy(h)
+        return out[0] if (self.single and np.ndim(B) == 2) else out
+
     def solve(self, b, out: "Vec | None" = None):
         """``F \\ b`` = ``ldiv!(F, copy(b))``; with ``out`` (a Vec) nothing is copied back to the host."""
         if out is None:

@@ -125,6 +125,26 @@ def c4(args, ctx):
                           "relres": rr}))
 
 
+def c2m(args, ctx):
+    """multi-RHS ldiv!(F, B::Matrix) on the config-2 shape: nrhs columns per system in one pass over the factors per group."""
+    import ctypes as C
+    from ssm_b200 import _lib
+    n, l, u, r, nb, seed = 1024, 2, 2, 2, args.nb or 65536, 20261019 + 1
+    A = ssm.AlmostBandedMatrix.generate(n, l, u, r, nb, seed, ctx=ctx)
+    F = ssm.qr(A)
+    b = ssm.Vec(ctx, n, nb).generate(seed)
+    t1 = timeit(lambda: F.ldiv(b), args.steps)
+    L = _lib.lib()
+    for nrhs in (4, 8):
+        h = C.c_void_p()
+        _lib.check(L.ssm_mat_create(ctx._h, n, nrhs, nb, C.byref(h)), "ssm_mat_create")
+        t = timeit(lambda: _lib.check(L.ssm_abqr_ldiv_mat(F._h, h), "ldiv_mat"), args.steps)
+        byts = 8 * n * (2 * l + u + 2 * r + 1 + 3 * nrhs) * nb        # factors once + (read b, write x) per column; Q'B round trip not counted
+        print(json.dumps({"config": f"ldiv!(F, B) n={n} (2,2,2) nrhs={nrhs}", "systems": nb, "ms": t, "ms_single_vector_ldiv": t1,
+                          "speedup_vs_columnwise": nrhs * t1 / t, "frac_of_measured_peak": byts / t / 1e6 / PEAK}))
+        L.ssm_mat_destroy(h)
+
+
 def c5dist(args, ctx):
     """configs[4] on N GPUs, one process per GPU (torchrun): the sharder's group plan (ssm_b200.sharder.plan_groups) decides which
     (n, system range) pieces this rank owns; time = max over ranks of the device time for the rank's whole list."""
@@ -158,7 +178,7 @@ def c5dist(args, ctx):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["c2", "c3", "c4", "c5", "c5dist"])
+    ap.add_argument("which", choices=["c2", "c2m", "c3", "c4", "c5", "c5dist"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
@@ -175,4 +195,4 @@ if __name__ == "__main__":
         ctx.set_option("ab_variant", args.variant)
     if args.stages:
         ctx.set_option("pipeline_stages", args.stages)
-    {"c2": c2, "c3": c3, "c4": c4, "c5": c5, "c5dist": c5dist}[args.which](args, ctx)
+    {"c2": c2, "c2m": c2m, "c3": c3, "c4": c4, "c5": c5, "c5dist": c5dist}[args.which](args, ctx)
