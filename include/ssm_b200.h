@@ -83,6 +83,12 @@ int  ssm_ab_set(ssm_ab *A, const double *bands, int64_t bands_stride, const doub
 int  ssm_ab_get(const ssm_ab *A, double *bands, int64_t bands_stride, double *U, int64_t U_stride,
                 double *V, int64_t V_stride);
 int  ssm_ab_generate(ssm_ab *A, uint64_t seed, int dist);       /* device-side synthetic operands        */
+/* Vcat(a, Bd) front end (AlmostBandedMatrix.jl:298-305 bandwidth rule, :316-337 copyto!): the boundary-row form spectral-method
+ * callers produce.  a: r x n dense rows (column-major), Bd: (lb+ub+1) x n band storage of the (n-r) x n banded block.  Builds
+ * U = [I_r; 0], V = a and the bands directly in the device layout.  A must have been created with r rows of fill and bandwidths
+ * >= ssm_ab_vcat_bandwidths(r, lb, ub).                                                                                      */
+int  ssm_ab_vcat_bandwidths(int r, int lb, int ub, int *l, int *u);
+int  ssm_ab_set_vcat(ssm_ab *A, const double *a, int64_t a_stride, const double *Bd, int64_t b_stride, int lb, int ub);
 
 /* qr(A) / factorize(A): _qr -> almostbanded_qr -> widen (:30-38) + _almostbanded_qr! (:125-179).
  * A is not mutated (test_almostbanded.jl:146).  *F must be NULL (a new factor object is returned) or an

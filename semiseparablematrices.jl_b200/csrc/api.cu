@@ -265,6 +265,43 @@ int ssm_ab_set(ssm_ab *A, const double *bands, int64_t sb, const double *U, int6
     return 0;
 }
 
+// almostbandwidths(Vcat(a, Bd)) (AlmostBandedMatrix.jl:298-303): (max(lb + r, r - 1), ub - r); the device batch needs u >= 0, a
+// negative upper bandwidth is widened to 0 (the diagonal then holds the fill values it would otherwise have been read from).
+int ssm_ab_vcat_bandwidths(int r, int lb, int ub, int *l, int *u) {
+    SSM_CHECK_ARG(l && u && r >= 0, "bad arguments");
+    *l = std::max(lb + r, r - 1);
+    *u = std::max(ub - r, 0);
+    return 0;
+}
+
+// AlmostBandedMatrix(Vcat(a, Bd)) = copyto!(AlmostBandedMatrix(undef, ...), Vcat(a, Bd)) (AlmostBandedMatrix.jl:48-49, 316-337):
+// a = r x n dense rows (column-major), Bd = band storage of the (n-r) x n banded block with bandwidths (lb, ub).
+int ssm_ab_set_vcat(ssm_ab *A, const double *a, int64_t a_stride, const double *Bd, int64_t b_stride, int lb, int ub) {
+    SSM_CHECK_ARG(A && a && Bd, "null argument");
+    ssm_ctx *c = A->ctx;
+    DeviceGuard g(c->device);
+    const int r = A->r;
+    if (r < 1 || A->n <= r) { set_error("ssm_ab_set_vcat: need 1 <= r < n"); return SSM_E_SHAPE; }
+    if (lb + ub + 1 < 1 || A->l < std::max(lb + r, r - 1) || A->u < std::max(ub - r, 0)) {
+        set_error("ssm_ab_set_vcat: DimensionMismatch: bandwidths (%d,%d) of the batch cannot hold Vcat(%d rows, banded (%d,%d)); need (%d,%d)", A->l, A->u, r, lb, ub,
+                  std::max(lb + r, r - 1), std::max(ub - r, 0));
+        return SSM_E_SHAPE;
+    }
+    const size_t ea = (size_t)r * A->n, eb = (size_t)(lb + ub + 1) * A->n;
+    if (a_stride == 0) a_stride = (int64_t)ea;
+    if (b_stride == 0) b_stride = (int64_t)eb;
+    if ((size_t)a_stride < ea || (size_t)b_stride < eb) { set_error("ssm_ab_set_vcat: stride smaller than one system"); return SSM_E_SHAPE; }
+    if (is_device_ptr(a) && is_device_ptr(Bd)) return launch_ab_pack_vcat(c, A, a, a_stride, Bd, b_stride, lb, ub);
+    double *stg;
+    SSM_TRY(staging_dev(c, (size_t)A->nb * (ea + eb), &stg));
+    double *sA = stg, *sB = stg + (size_t)A->nb * ea;
+    SSM_TRY(h2d_block(c, sA, a, a_stride, ea, A->nb));
+    SSM_TRY(h2d_block(c, sB, Bd, b_stride, eb, A->nb));
+    SSM_TRY(launch_ab_pack_vcat(c, A, sA, (int64_t)ea, sB, (int64_t)eb, lb, ub));
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // unpack helper shared by ssm_ab_get / ssm_abqr_get: run `launch` into device memory (direct or staged)
 int ssm_ab_get(const ssm_ab *A, double *bands, int64_t sb, double *U, int64_t su, double *V, int64_t sv) {
     SSM_CHECK_ARG(A, "null argument");

@@ -52,6 +52,37 @@ __global__ void ab_unpack_kernel(const double *AU, const double *Vd, double *ban
              for (int q = 0; q < r; ++q) V[s * sv + q + (int64_t)r * i] = vrec[q * 32]; }
 }
 
+// ---- Vcat front end: A = Vcat(a, Bd), a dense r x n boundary rows, Bd an (n-r) x n BandedMatrix (lb, ub) ---------------------------
+// What `_copyto!(::AlmostBandedLayout, ::VcatAlmostBandedLayout, dest, A)` (AlmostBandedMatrix.jl:316-337) builds on the host —
+// U = [I_r; 0], V = a, bands[r+1:end, :] = Bd, in-band entries of the first r rows = a — written straight into the device
+// records, so a spectral-method caller never materialises the (l+u+1) x n band array.  a: r x n column-major (= V's memory);
+// Bd: (lb+ub+1) x n band storage, Bd[k, j] at row ub + k - j of column j.
+__global__ void ab_pack_vcat_kernel(double *AU, double *Vd, const double *a, int64_t sa, const double *Bd, int64_t sbd, int lb, int ub,
+                                    int n, int l, int u, int r, int64_t nb, int64_t np) {
+    const int lane = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    const int64_t tile = blockIdx.y;
+    if (i >= n) return;
+    const int64_t s = tile * TILE + lane;
+    const bool live = s < nb;
+    const int nfa = l + u + 1 + r, ndb = lb + ub + 1;
+    double *rec = AU + ((tile * np + i) * nfa) * 32 + lane;
+    const double *as = a + s * sa, *bs = Bd + s * sbd;
+    for (int d = 0; d <= l + u; ++d) {
+        const int64_t j = i - l + d;
+        double val = 0.0;
+        if (!live) val = (d == l) ? 1.0 : 0.0;                    // padding lanes are identity systems
+        else if (j >= 0 && j < n) {
+            if (i < r) val = as[i + (int64_t)r * j];
+            else { const int64_t k = i - r, off = j - k; if (off >= -lb && off <= ub) val = bs[(int64_t)(ub + k - j) + (int64_t)ndb * j]; }
+        }
+        rec[d * 32] = val;
+    }
+    for (int q = 0; q < r; ++q) rec[(l + u + 1 + q) * 32] = (live && i == q) ? 1.0 : 0.0;
+    double *vrec = Vd + ((tile * np + i) * (r > 0 ? r : 1)) * 32 + lane;
+    for (int q = 0; q < r; ++q) vrec[q * 32] = live ? as[q + (int64_t)r * i] : 0.0;
+}
+
 // zero the out-of-matrix corners of a band-storage batch (entries the loops above never write)
 __global__ void band_corner_zero_kernel(double *bands, int64_t sb, int n, int lo, int up, int64_t nb) {
     const int64_t s = blockIdx.x;
@@ -185,6 +216,12 @@ int launch_ab_pack(ssm_ctx *c, ssm_ab *A, const double *bands, int64_t sb, const
     int64_t tiles = (send + TILE - 1) / TILE - s0 / TILE;
     ab_pack_kernel<<<rec_grid(A->n, tiles), dim3(32, 8), 0, c->stream>>>(A->AU->p, A->V->p, bands, sb, U, su, V, sv, A->n, A->l, A->u,
                                                                           A->r, A->nb, A->np, s0, count);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_ab_pack_vcat(ssm_ctx *c, ssm_ab *A, const double *a, int64_t sa, const double *Bd, int64_t sbd, int lb, int ub) {
+    ab_pack_vcat_kernel<<<rec_grid(A->n, A->ntiles), dim3(32, 8), 0, c->stream>>>(A->AU->p, A->V->p, a, sa, Bd, sbd, lb, ub, A->n, A->l, A->u, A->r, A->nb, A->np);
     c->launches++;
     SSM_CUDA(cudaGetLastError());
     return 0;

@@ -173,11 +173,21 @@ function ldiv!(F::QR{<:Any,<:DenseAB}, b::Vector{Float64})
     fetch_vec!(b, v)
     b
 end
+# matrix right-hand side (:194-199): all columns in one pass over the device-resident factors per group of 4 / 8 columns
 function ldiv!(F::QR{<:Any,<:DenseAB}, B::Matrix{Float64})
-    for j in axes(B, 2)
-        col = B[:, j]
-        ldiv!(F, col)
-        B[:, j] = col
+    _, dF = device_factor(F)
+    n, nrhs = size(B)
+    n == size(F.factors, 1) || throw(DimensionMismatch("right-hand side has $(n) rows, matrix has $(size(F.factors,1))"))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ssm_mat_create, libssm), Cint, (Ctx, Cint, Cint, Int64, Ptr{Ptr{Cvoid}}), context(), n, nrhs, 1, h))
+    try
+        GC.@preserve B begin
+            check(ccall((:ssm_mat_set, libssm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], pointer(B), 0))
+            check(ccall((:ssm_abqr_ldiv_mat, libssm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dF.p, h[]))
+            check(ccall((:ssm_mat_get, libssm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h[], pointer(B), 0))
+        end
+    finally
+        ccall((:ssm_mat_destroy, libssm), Cint, (Ptr{Cvoid},), h[])
     end
     B
 end

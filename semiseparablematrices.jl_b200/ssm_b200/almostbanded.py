@@ -189,6 +189,26 @@ class AlmostBandedMatrix:
         check(_lib.lib().ssm_ab_generate(self._h, seed, dist), "ssm_ab_generate")
         return self
 
+    @classmethod
+    def from_vcat(cls, a, Bd, lbub, ctx: Context | None = None):
+        """``AlmostBandedMatrix(Vcat(a, Bd))`` (AlmostBandedMatrix.jl:48-49, 298-305, 316-337): ``a`` (nb, n, r) = per system the
+        memory of the r x n dense boundary rows, ``Bd`` (nb, n, lb+ub+1) = band storage of the (n-r) x n banded block with
+        bandwidths ``(lb, ub)``.  almostbandwidths = (max(lb+r, r-1), ub-r) (a negative upper bandwidth is stored as 0)."""
+        lb, ub = (int(v) for v in lbub)
+        a = np.ascontiguousarray(a, dtype=np.float64); Bd = np.ascontiguousarray(Bd, dtype=np.float64)
+        single = a.ndim == 2
+        if single:
+            a, Bd = a[None], Bd[None]
+        nb, n, r = a.shape
+        if tuple(Bd.shape) != (nb, n, lb + ub + 1):
+            raise DimensionMismatch(f"banded block storage has shape {Bd.shape}, expected {(nb, n, lb + ub + 1)}")
+        l, u = C.c_int(), C.c_int()
+        check(_lib.lib().ssm_ab_vcat_bandwidths(r, lb, ub, C.byref(l), C.byref(u)), "ssm_ab_vcat_bandwidths")
+        self = cls._empty(ctx or default_context(), n, l.value, u.value, r, nb)
+        self.single = single
+        check(_lib.lib().ssm_ab_set_vcat(self._h, c_vp(a.ctypes.data), 0, c_vp(Bd.ctypes.data), 0, lb, ub), "ssm_ab_set_vcat")
+        return self
+
     # -- reference accessors ----------------------------------------------------------------------
     @property
     def shape(self):

@@ -278,3 +278,43 @@ def test_ldiv_matrix_rhs_matches_columnwise_ldiv(ssm, ctx, l, u, r, nrhs):
         assert max(relerr(X[s, j], ox[s]) for s in range(nb)) <= 1e-12
     with pytest.raises(ssm.DimensionMismatch):
         F.ldiv_mat(B[:, :, :-1])
+
+
+def _block_storage(Bd, lb, ub):
+    """band storage (n, lb+ub+1) of an (n-r) x n banded block: Bd[k, j] at [j, ub + k - j]"""
+    m, n = Bd.shape
+    out = np.zeros((n, lb + ub + 1))
+    for k in range(m):
+        for j in range(n):
+            if -lb <= j - k <= ub:
+                out[j, ub + k - j] = Bd[k, j]
+    return out
+
+
+def test_vcat_front_end_builds_the_reference_representation(ssm, ctx):
+    """AlmostBandedMatrix(Vcat(a, Bd)) (AlmostBandedMatrix.jl:298-305, 316-337; test_almostbanded.jl:27-72, 160-163, 179-185):
+    bandwidth rule, U = [I_r; 0], V = a, bands = what copyto! writes; then qr(A) \\ b ≈ Matrix(A) \\ b."""
+    rng = np.random.default_rng(5)
+    cases = []
+    n = 10                                                       # Vcat(Ones(1,n), BandedMatrix((0 => -Ones(n-1), 1 => 1:(n-1)), (n-1,n)))
+    Bd = np.zeros((n - 1, n))
+    for k in range(n - 1):
+        Bd[k, k] = -1.0; Bd[k, k + 1] = k + 1.0
+    cases.append((np.ones((1, n)), Bd, 0, 1, (1, 0)))
+    (l2, u2, r2), bands2, U2, V2, A2 = vcat_system(rng, 80)       # Vcat(randn(2,n), banded (0,2)): almostbandwidths (2,0)
+    cases.append((V2.T.copy(), A2[2:], 0, 2, (2, 0)))
+    (l3, u3, r3), bands3, U3, V3, A3 = degenerate_system(rng)    # Vcat(randn(2,7), BandedMatrix(2 => 1:5)[1:5,:]): (1,0)
+    cases.append((V3.T.copy(), A3[2:], -2, 2, (1, 0)))
+    for a, Bd, lb, ub, lu in cases:
+        r, n = a.shape
+        A = ssm.AlmostBandedMatrix.from_vcat(np.ascontiguousarray(a.T), _block_storage(Bd, lb, ub), (lb, ub), ctx=ctx)
+        assert A.almostbandwidths() == lu and A.almostbandedrank() == r
+        dense = np.vstack([a, Bd])
+        gb, gU, gV = A._get()
+        assert np.array_equal(gV[0], a.T) and np.array_equal(gU[0], np.eye(r, n))
+        assert np.array_equal(gb[0], oracle.banded_to_storage(dense, *lu))
+        b = rng.standard_normal(n)
+        x = ssm.qr(A).ldiv(b)
+        assert relerr(x, np.linalg.solve(dense, b)) <= 1e-12 * max(1.0, np.linalg.cond(dense) / 10)
+    with pytest.raises(ssm.DimensionMismatch):
+        ssm.AlmostBandedMatrix.from_vcat(np.ones((n, 1)), np.zeros((n, 3)), (0, 1), ctx=ctx)
