@@ -208,6 +208,32 @@ for (UNIT, unitflag) in (('N', 0), ('U', 1))
     end
 end
 
+# A \ b for ONE large system (README.md:96-97, n = 10^6 and beyond): the chunked n-axis path returns the same solution without
+# the strictly sequential sweep (solution parity, not factor parity — DESIGN.md section 6).  Smaller systems keep qr + ldiv!.
+const CHUNKED_MIN_N = Ref(1 << 16)
+function Base.:\(A::DenseAB, b::Vector{Float64})
+    n = size(A, 2)
+    (size(A, 1) == n && n >= CHUNKED_MIN_N[]) || return ldiv!(qr(A), copy(b))
+    length(b) == n || throw(DimensionMismatch("right-hand side has length $(length(b)), matrix has $(n) rows"))
+    l, u = almostbandwidths(A)
+    U, V = arguments(fillpart(A))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:ssm_abc_create, libssm), Cint, (Ctx, Int64, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}), context(), n, l, u, size(U, 2), h)
+    rc == -3 && return ldiv!(qr(A), copy(b))                        # no compiled chunked kernel for this (l+u, r): sequential path
+    check(rc)
+    x = similar(b)
+    try
+        bd = bandpart(A).data
+        GC.@preserve bd U V b x begin
+            check(ccall((:ssm_abc_set, libssm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), h[], pointer(bd), pointer(U), pointer(V)))
+            check(ccall((:ssm_abc_solve, libssm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint), h[], pointer(b), pointer(x), 0))
+        end
+    finally
+        ccall((:ssm_abc_destroy, libssm), Cint, (Ptr{Cvoid},), h[])
+    end
+    x
+end
+
 # ---- batched entry points (no reference equivalent; same-shaped systems stacked along the last axis) -----------------
 """
     solve_batch(bands::Array{Float64,3}, U::Array{Float64,3}, V::Array{Float64,3}, b::Matrix{Float64}, (l,u)) -> x
