@@ -81,6 +81,8 @@ _SIGS = {
     "ssm_bpsqr_upper_ldiv": (C.c_int, [c_vp, c_vp]),
     "ssm_bpsqr_ldiv": (C.c_int, [c_vp, c_vp]),
     "ssm_bpsqr_solve": (C.c_int, [c_vp, c_vp, c_vp]),
+    "ssm_bps_get": (C.c_int, [c_vp, c_vp, i64, c_vp, c_vp, i64, c_vp, c_vp, i64]),
+    "ssm_bpsqr_rq_mul": (C.c_int, [c_vp, C.POINTER(c_vp)]),
     "ssm_bps_mul": (C.c_int, [c_vp, c_vp, c_vp]),
     "ssm_bps_residual": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ssm_bps_upper_ldiv": (C.c_int, [c_vp, c_vp]),

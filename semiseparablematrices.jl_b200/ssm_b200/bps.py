@@ -54,6 +54,21 @@ class BandedPlusSemiseparableMatrix:
         check(_lib.lib().ssm_bps_generate(self._h, seed), "ssm_bps_generate")
         return self
 
+    @classmethod
+    def _wrap(cls, ctx, handle, n, l, m, r, p, nb, single):
+        self = cls.__new__(cls)
+        self.ctx, self._h = ctx, handle
+        self.n, self.l, self.m, self.r, self.p, self.nb, self.single = n, l, m, r, p, nb, single
+        return self
+
+    def get(self):
+        """(B (nb,n,l+m+1), U (nb,r,n), V (nb,r,n), W (nb,p,n), S (nb,p,n)) — the operands in the reference layout"""
+        n, l, m, r, p, nb = self.n, self.l, self.m, self.r, self.p, self.nb
+        B = np.zeros((nb, n, l + m + 1)); U = np.empty((nb, r, n)); V = np.empty((nb, r, n)); W = np.empty((nb, p, n)); S = np.empty((nb, p, n))
+        P = lambda a: c_vp(a.ctypes.data)
+        check(_lib.lib().ssm_bps_get(self._h, P(B), 0, P(U), P(V), 0, P(W), P(S), 0), "ssm_bps_get")
+        return B, U, V, W, S
+
     @property
     def shape(self):
         return (self.n, self.n)
@@ -151,6 +166,13 @@ class BPSQR:
         P = lambda a: c_vp(a.ctypes.data)
         check(_lib.lib().ssm_bpsqr_get(self._h, P(B), 0, P(U), P(V), 0, P(W), P(S), 0, P(tau), 0), "ssm_bpsqr_get")
         return B, U, V, W, S, tau
+
+    def rq_mul(self) -> BandedPlusSemiseparableMatrix:
+        """``rq_mul(F.factors, F.tau)`` (semiseparableqr.jl:282-287): R*Q = Q'AQ of a SYMMETRIC BandedPlusSemiseparableMatrix, again as
+        a symmetric BPS batch ``BPS(B (l,l), (U_new, V_new), (V_new, U_new))`` — one step of the batched QR iteration."""
+        h = c_vp()
+        check(_lib.lib().ssm_bpsqr_rq_mul(self._h, C.byref(h)), "ssm_bpsqr_rq_mul")
+        return BandedPlusSemiseparableMatrix._wrap(self.ctx, h, self.n, self.l, self.l, self.r, self.r, self.nb, self.single)
 
     @property
     def factors(self):

@@ -119,3 +119,38 @@ def test_full_size_config3_properties(bps, ctx):
         fB, fV, fW, fS, ft = oracle.bps_qr(oB_, oU, oV_, oW_, oS_, l, m)
         ox = oracle.bps_upper_ldiv(fB, fW, fS, oracle.bps_lmul_qt(fB, oU, fV, ft, ob, l, l + m), l, l + m)
         assert relerr(xh[s], ox) <= 1e-12
+
+
+@pytest.mark.parametrize("n,l,r", [(20, 3, 2), (33, 2, 2), (17, 1, 1), (64, 4, 3), (25, 2, 1), (12, 3, 2)])
+def test_rq_mul_matches_oracle_and_dense(bps, ctx, n, l, r):
+    """rq_mul(F.factors, F.tau) (semiseparableqr.jl:282-287; test_rq.jl:26-34): R*Q of a symmetric BPS batch == the numpy
+    restatement of the reference step and == dense R0*Q; the result is again a symmetric BPS (tested through its operands)."""
+    from oracle import rq_oracle
+    from test_oracle_rq import rq_true, sym_bps
+    rng = np.random.default_rng(n * 7 + l)
+    nb = 37
+    B, U, V, W, S = sym_bps(rng, n, l, r, nb=nb)
+    A = bps.BandedPlusSemiseparableMatrix(B, (U, V), (W, S), (l, l), ctx=ctx)
+    F = bps.qr(A)
+    RQ = F.rq_mul()
+    assert (RQ.l, RQ.m, RQ.r, RQ.p) == (l, l, r, r)
+    gB, gU, gV, gW, gS = RQ.get()
+    assert np.array_equal(gW, gV) and np.array_equal(gS, gU)
+    for s in range(nb):
+        want, (Bf, Vf, Wf, Sf, tau) = rq_true(B[s], U[s], V[s], W[s], S[s], l)
+        oB, oU, oV = rq_oracle.rq_mul(Bf, U[s], Vf, Wf, Sf, tau, l, 2 * l)
+        scale = np.abs(want).max()
+        assert np.abs(gB[s] - oB).max() <= 1e-13 * scale and np.abs(gU[s] - oU).max() <= 1e-13 * scale and np.abs(gV[s] - oV).max() <= 1e-13 * scale
+        assert np.abs(rq_oracle.rq_dense(gB[s], gU[s], gV[s], l) - want).max() <= 1e-12 * scale
+
+
+def test_rq_mul_errors(bps, ctx):
+    import ssm_b200
+    B, U, V, W, S, _ = oracle.bps_generate(16, 2, 2, 2, 2, 3, seed=5)          # not symmetric: S != U
+    F = bps.qr(bps.BandedPlusSemiseparableMatrix(B, (U, V), (W, S), (2, 2), ctx=ctx))
+    with pytest.raises(ssm_b200.SSMError):
+        F.rq_mul()
+    B, U, V, W, S, _ = oracle.bps_generate(16, 2, 3, 2, 2, 3, seed=5)          # m != l
+    F = bps.qr(bps.BandedPlusSemiseparableMatrix(B, (U, V), (W, S), (2, 3), ctx=ctx))
+    with pytest.raises(ssm_b200.DimensionMismatch):
+        F.rq_mul()

@@ -145,6 +145,36 @@ def c2m(args, ctx):
         L.ssm_mat_destroy(h)
 
 
+def c3rq(args, ctx):
+    """one QR-iteration step of a symmetric BPS batch: qr(A) then rq_mul(F) (R*Q), n=4096, l=m=3, r=p=2 (host-generated symmetric operands)."""
+    n, l, r, nb = args.n or 4096, 3, 2, args.nb or 4096
+    rng = np.random.default_rng(7)
+    B = rng.uniform(-1, 1, (nb, n, 2 * l + 1))
+    for t in range(1, l + 1):                       # symmetric band: A[j+t, j] (slot l+t of column j) = A[j, j+t] (slot l-t of column j+t)
+        B[:, t:, l - t] = B[:, :n - t, l + t]
+        B[:, :t, l - t] = 0.0; B[:, n - t:, l + t] = 0.0
+    B[:, :, l] = 2 * l + 2 + rng.uniform(0, 1, (nb, n))
+    U = rng.uniform(-1, 1, (nb, r, n)) / np.sqrt(r * n); V = rng.uniform(-1, 1, (nb, r, n)) / np.sqrt(r * n)
+    A = bps.BandedPlusSemiseparableMatrix(B, (U, V), (V.copy(), U.copy()), (l, l), ctx=ctx)
+    F = bps.qr(A)
+    t_qr = timeit(lambda: F.refactor(A), args.steps)
+    import ctypes as C
+    from ssm_b200 import _lib
+    def rq():
+        h = C.c_void_p()
+        _lib.check(_lib.lib().ssm_bpsqr_rq_mul(F._h, C.byref(h)), "rq_mul")
+        _lib.lib().ssm_bps_destroy(h)
+    t_rq = timeit(rq, args.steps)
+    RQ = F.rq_mul()
+    gB, gU, gV, _, _ = RQ.get()
+    # similarity transform: trace(R*Q) == trace(A)
+    tr_err = float(np.abs(gB[:, :, l].sum(1) - B[:, :, l].sum(1)).max() / np.abs(B[:, :, l].sum(1)).max())
+    rd = 8 * n * ((2 * l + l + 1) + l + r + 1 + 4 * r + 2 * r) * nb      # factor records read once (R rows, tails, k-bar, tau, [alpha beta], S, A'U, U)
+    wr = 8 * n * ((2 * l + 1) + 2 * r) * nb
+    print(json.dumps({"config": f"symmetric BPS QR-iteration step n={n} l={l} r={r}", "systems": nb, "qr_ms": t_qr, "rq_mul_ms": t_rq,
+                      "rq_systems_per_s": nb / (t_rq * 1e-3), "rq_GBps_algorithmic": (rd + wr) / t_rq / 1e6, "trace_relerr": tr_err}))
+
+
 def c5dist(args, ctx):
     """configs[4] on N GPUs, one process per GPU (torchrun): the sharder's group plan (ssm_b200.sharder.plan_groups) decides which
     (n, system range) pieces this rank owns; time = max over ranks of the device time for the rank's whole list."""
@@ -178,7 +208,7 @@ def c5dist(args, ctx):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["c2", "c2m", "c3", "c4", "c5", "c5dist"])
+    ap.add_argument("which", choices=["c2", "c2m", "c3", "c3rq", "c4", "c5", "c5dist"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
@@ -195,4 +225,4 @@ if __name__ == "__main__":
         ctx.set_option("ab_variant", args.variant)
     if args.stages:
         ctx.set_option("pipeline_stages", args.stages)
-    {"c2": c2, "c2m": c2m, "c3": c3, "c4": c4, "c5": c5, "c5dist": c5dist}[args.which](args, ctx)
+    {"c2": c2, "c2m": c2m, "c3": c3, "c3rq": c3rq, "c4": c4, "c5": c5, "c5dist": c5dist}[args.which](args, ctx)
