@@ -315,4 +315,20 @@ function ldiv!(R::UpperTriangular{<:Any,<:BandedPlusSemiseparableMatrix{Float64}
     b
 end
 
+# rq_mul(F.factors, τ) (semiseparableqr.jl:282-287): R*Q of a symmetric BPS factorisation produced by the B200 path
+function SemiseparableMatrices.rq_mul(R::BandedPlusSemiseparableMatrix{Float64}, τ::Vector{Float64})
+    haskey(BPSFACTORS, R) || return invoke(SemiseparableMatrices.rq_mul, Tuple{BandedPlusSemiseparableMatrix,Vector}, R, τ)
+    _, dF = BPSFACTORS[R]
+    n = size(R, 1); l = bandwidth(R.B, 1); r = size(R.U, 2)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ssm_bpsqr_rq_mul, libssm), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), dF.p, h))
+    dQ = Handle(h[], :bps)
+    B = BandedMatrix{Float64}(undef, (n, n), (l, l))
+    U = Matrix{Float64}(undef, n, r); V = similar(U); W = similar(U); S = similar(U)
+    GC.@preserve B U V W S check(ccall((:ssm_bps_get, libssm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64),
+        dQ.p, pointer(B.data), 0, pointer(U), pointer(V), 0, pointer(W), pointer(S), 0))
+    BandedPlusSemiseparableMatrix(B, (U, V), (W, S))
+end
+
 end # module
