@@ -154,7 +154,8 @@ int  ssm_bpsqr_ldiv(const ssm_bpsqr *F, ssm_vec *b);
 int  ssm_bpsqr_solve(const ssm_bpsqr *F, const ssm_vec *b, ssm_vec *x);   /* x <- F \ b, b untouched (x may alias b) */
 /* rq_mul(F.factors, F.tau) (semiseparableqr.jl:170-311, 642-845): R*Q = Q'AQ of a SYMMETRIC BandedPlusSemiseparableMatrix (W = V,
  * S = U, m = l), returned as a new symmetric batch BPS(B (l, l), (U_new, V_new), (V_new, U_new)) — one step of the batched QR
- * iteration.  SSM_E_SHAPE when the factors are not those of a symmetric shape, SSM_E_STATE when S[:, 1:r] != U (:195-205).        */
+ * iteration.  *RQ must be NULL (a new batch is returned) or a previous result of the same shape, which is overwritten.
+ * SSM_E_SHAPE when the factors are not those of a symmetric shape, SSM_E_STATE when S[:, 1:r] != U (:195-205).                     */
 int  ssm_bpsqr_rq_mul(const ssm_bpsqr *F, ssm_bps **RQ);
 /* the operands of a batch back in the reference layout (any pointer may be NULL)                                                 */
 int  ssm_bps_get(const ssm_bps *A, double *B, int64_t B_stride, double *U, double *V, int64_t UV_stride, double *W, double *S,

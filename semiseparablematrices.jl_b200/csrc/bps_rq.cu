@@ -18,13 +18,17 @@ namespace ssm {
 
 struct RqOut { double *NEW; int64_t np2; int nfa2, tl2, tm2, tr2, tp2; };
 
+// split = 1: one warp per tile.  split = 2 / 4: the tile's 32 systems are spread over 2 / 4 warps (the other lanes shadow and do not
+// store) — the step is a long dependent chain, so small batches are latency bound and more warps in flight is what helps.
 template <int L, int M, int R, int P>
-__global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const double *OUT, RqOut o, int *flag, int n, int64_t np, int64_t npo) {
+__global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const double *OUT, RqOut o, int *flag, int n, int64_t np, int64_t npo, int split) {
     using D = BpsDims<L, M, R, P>;
     static_assert(P == R, "symmetric BPS: p == r");
     constexpr int PW = P + R, MW = L + M;
-    const int lane = threadIdx.x;
-    const int64_t tile = blockIdx.x;
+    const int lw = 32 / split;
+    const int lane = ((int)threadIdx.x & (lw - 1)) + lw * (int)(blockIdx.x % split);
+    const bool writer = (int)threadIdx.x < lw;
+    const int64_t tile = blockIdx.x / split;
     const double *rec0 = REC + (tile * np + BPS_FRONT) * D::NFA * 32 + lane;
     const double *out0 = OUT + tile * npo * D::NFO * 32 + lane;
     auto recf = [&](int i, int f) -> double { return i < n ? rec0[((int64_t)i * D::NFA + f) * 32] : 0.0; };
@@ -36,7 +40,7 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
     // new operand records
     const int nfb2 = o.tl2 + o.tm2 + 1, FU2 = nfb2, FV2 = nfb2 + o.tr2, FW2 = nfb2 + 2 * o.tr2, FS2 = nfb2 + 2 * o.tr2 + o.tp2;
     double *new0 = o.NEW + (tile * o.np2 + BPS_FRONT) * o.nfa2 * 32 + lane;
-    auto put = [&](int i, int f, double v) { new0[((int64_t)i * o.nfa2 + f) * 32] = v; };
+    auto put = [&](int i, int f, double v) { if (writer) new0[((int64_t)i * o.nfa2 + f) * 32] = v; };
 
     // ---- prologue: totals for the suffix sums; S[:, 1:r] must equal U (semiseparableqr.jl:199-201) ----
     double T1[R][R], T2[PW][R];
@@ -338,17 +342,22 @@ int ssm_bpsqr_rq_mul(const ssm_bpsqr *F, ssm_bps **out) {
     if (F->p != F->r || F->m != F->l) { set_error("ssm_bpsqr_rq_mul: DimensionMismatch: R*Q needs the factors of a symmetric BandedPlusSemiseparableMatrix (p == r, m == l); got (l,m,r,p)=(%d,%d,%d,%d)", F->l, F->m, F->r, F->p); return SSM_E_SHAPE; }
     if (F->n <= F->tl) { set_error("ssm_bpsqr_rq_mul: n must exceed the lower bandwidth"); return SSM_E_UNSUPPORTED; }
     ssm_ctx *c = F->ctx;
-    ssm_bps *Q = nullptr;
-    SSM_TRY(ssm_bps_create(c, F->n, F->l, F->l, F->r, F->r, F->nb, &Q));
+    ssm_bps *Q = *out;                                     // reuse an existing result batch of the same shape (steady-state iteration)
+    const bool fresh = Q == nullptr;
+    if (Q && (Q->n != F->n || Q->l != F->l || Q->m != F->l || Q->r != F->r || Q->p != F->r || Q->nb != F->nb)) { set_error("ssm_bpsqr_rq_mul: result batch has a different shape"); return SSM_E_SHAPE; }
+    if (!Q) SSM_TRY(ssm_bps_create(c, F->n, F->l, F->l, F->r, F->r, F->nb, &Q));
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     DevBufPtr flag;
     int rc = dev_alloc(c->device, 1, true, c->stream, flag);
     if (!rc) {
         RqOut o{Q->REC->p, Q->np, bps_nfa(Q->tl, Q->tm, Q->tr, Q->tp), Q->tl, Q->tm, Q->tr, Q->tp};
+        // spreading a tile over 2 / 4 warps was measured and does not pay here (the window rows are re-read from L1 / L2 by every
+        // warp of the tile: 16,384 systems 26 -> 42 ms); the knob stays for experiments (ab_variant 2 -> 2 warps per tile)
+        const int split = c->ab_variant == 2 ? 2 : 1;
         rc = SSM_E_UNSUPPORTED;
 #define X(L_, M_, R_, P_)                                                                                                   \
     if (F->tl == L_ && F->tm == M_ && F->tr == R_ && F->tp == P_) {                                                        \
-        bps_rq_kernel<L_, M_, R_, P_><<<(unsigned)F->ntiles, 32, 0, c->stream>>>(F->REC->p, F->OUT->p, o, reinterpret_cast<int *>(flag->p), F->n, F->np, F->npo); \
+        bps_rq_kernel<L_, M_, R_, P_><<<(unsigned)(F->ntiles * split), 32, 0, c->stream>>>(F->REC->p, F->OUT->p, o, reinterpret_cast<int *>(flag->p), F->n, F->np, F->npo, split); \
         rc = 0;                                                                                                            \
     }
         SSM_RQ_SHAPES(X)
@@ -363,7 +372,7 @@ int ssm_bpsqr_rq_mul(const ssm_bpsqr *F, ssm_bps **out) {
         }
     }
     cudaSetDevice(prev);
-    if (rc) { ssm_bps_destroy(Q); return rc; }
+    if (rc) { if (fresh) ssm_bps_destroy(Q); return rc; }
     *out = Q;
     return 0;
 }

@@ -160,12 +160,8 @@ def c3rq(args, ctx):
     t_qr = timeit(lambda: F.refactor(A), args.steps)
     import ctypes as C
     from ssm_b200 import _lib
-    def rq():
-        h = C.c_void_p()
-        _lib.check(_lib.lib().ssm_bpsqr_rq_mul(F._h, C.byref(h)), "rq_mul")
-        _lib.lib().ssm_bps_destroy(h)
-    t_rq = timeit(rq, args.steps)
     RQ = F.rq_mul()
+    t_rq = timeit(lambda: _lib.check(_lib.lib().ssm_bpsqr_rq_mul(F._h, C.byref(RQ._h)), "rq_mul"), args.steps)     # into the existing batch
     gB, gU, gV, _, _ = RQ.get()
     # similarity transform: trace(R*Q) == trace(A)
     tr_err = float(np.abs(gB[:, :, l].sum(1) - B[:, :, l].sum(1)).max() / np.abs(B[:, :, l].sum(1)).max())
