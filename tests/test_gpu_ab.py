@@ -318,3 +318,26 @@ def test_vcat_front_end_builds_the_reference_representation(ssm, ctx):
         assert relerr(x, np.linalg.solve(dense, b)) <= 1e-12 * max(1.0, np.linalg.cond(dense) / 10)
     with pytest.raises(ssm.DimensionMismatch):
         ssm.AlmostBandedMatrix.from_vcat(np.ones((n, 1)), np.zeros((n, 3)), (0, 1), ctx=ctx)
+
+
+def test_full_size_config5_sweep_properties(ssm, ctx):
+    """BASELINE.json configs[4]: the n = 256 .. 8192 sweep, 2^20 systems in total (this GPU takes every group whole).  Every system:
+    structured residual <= 1e-13; per group a few systems against the oracle (rel. error <= 1e-12)."""
+    groups = [(256, 524288), (512, 262144), (1024, 131072), (2048, 65536), (4096, 32768), (8192, 32768)]
+    l, u, r, seed = 2, 2, 2, 20261019 + 4
+    total = 0
+    for n, nb in groups:
+        A = ssm.AlmostBandedMatrix.generate(n, l, u, r, nb, seed, ctx=ctx)
+        b = ssm.Vec(ctx, n, nb).generate(seed)
+        x = ssm.Vec(ctx, n, nb)
+        F = ssm.qr(A)
+        F.solve(b, out=x)
+        rr = A.residual(x, b)
+        assert np.isfinite(rr).all() and rr.max() <= 1e-13, (n, rr.max())
+        xh = x.get()
+        for s in (0, nb // 2 + 17, nb - 1):
+            ob, oU, oV, obv = (a[0] for a in oracle.ab_generate(n, l, u, r, 1, seed, s0=int(s)))
+            assert relerr(xh[s], oracle.ab_solve(ob, oU, oV, obv, l, u)) <= 1e-12
+        total += nb
+        del A, b, x, F, xh
+    assert total == 1 << 20
