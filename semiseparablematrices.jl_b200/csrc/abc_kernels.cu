@@ -703,7 +703,7 @@ struct ssm_abc {
 
 #define SSM_CHECK_ARG(cond, msg) do { if (!(cond)) { set_error("%s: %s", __func__, msg); return SSM_E_ARG; } } while (0)
 
-#define SSM_ABC_SHAPES(X) X(1, 1) X(1, 2) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(4, 2) X(6, 2) X(8, 2)
+#define SSM_ABC_SHAPES(X) X(1, 0) X(2, 0) X(4, 0) X(1, 1) X(1, 2) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(4, 2) X(6, 2) X(8, 2)
 
 static bool abc_supported(int lp, int r) {
 #define X(LP_, R_) if (lp == LP_ && r == R_) return true;

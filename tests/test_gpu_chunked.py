@@ -35,7 +35,8 @@ def _rand(rng, n, l, u, r):
 
 
 @pytest.mark.parametrize("n,l,u,r,P", [(64, 2, 2, 2, 4), (50, 1, 0, 1, 3), (97, 4, 4, 2, 4), (40, 2, 0, 2, 2), (33, 1, 1, 1, 1),
-                                       (200, 3, 1, 2, 8), (500, 2, 2, 2, 16), (777, 4, 4, 2, 7), (130, 1, 1, 2, 5), (64, 2, 1, 1, 3)])
+                                       (200, 3, 1, 2, 8), (500, 2, 2, 2, 16), (777, 4, 4, 2, 7), (130, 1, 1, 2, 5), (64, 2, 1, 1, 3),
+                                       (300, 2, 2, 0, 6), (90, 1, 0, 0, 3), (128, 1, 1, 0, 4)])
 def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P):
     rng = np.random.default_rng(n * 13 + P)
     bands, U, V, b = _rand(rng, n, l, u, r)
