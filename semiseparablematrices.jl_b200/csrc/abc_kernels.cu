@@ -272,11 +272,7 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
 //   TOP  : [W][3W+1] = [Rhat | Fhat | Ghat | hhat]  (z_M = Rhat^-1 (hhat - Fhat z_L - Ghat z_R))
 // ---------------------------------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(128) abc_merge_kernel(const double *Ein, double *Eout, double *TOP, int nin) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int nout = (nin + 1) / 2;
-    if (i >= nout) return;
+__device__ __forceinline__ void abc_merge_one(const double *Ein, double *Eout, double *TOP, const int nin, const int i, const int lane) {
     constexpr int EW = 2 * W + 1, TW = 3 * W + 1;
     const double *Ea = Ein + (int64_t)(2 * i) * W * EW;
     if (2 * i + 1 >= nin) {                      // odd block passes through
@@ -331,12 +327,17 @@ __global__ void __launch_bounds__(128) abc_merge_kernel(const double *Ein, doubl
     }
 }
 
+template <int W>
+__global__ void __launch_bounds__(128) abc_merge_kernel(const double *Ein, double *Eout, double *TOP, int nin) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= (nin + 1) / 2) return;
+    abc_merge_one<W>(Ein, Eout, TOP, nin, i, threadIdx.x & 31);
+}
+
 // root: one block [F | G | h] over (z_0, z_P).  Real unknowns: z_0 entries l..W-1 (separator columns >= 0 and the
 // free tail T_{-1}) and z_P entries 0..l-1 (separator columns < n); everything else is a phantom and stays 0.
 template <int W>
-__global__ void __launch_bounds__(32) abc_root_kernel(const double *E, double *Z, int P, int l) {
-    __shared__ double Rm[W][W + 1];
-    const int lane = threadIdx.x;
+__device__ __forceinline__ void abc_root_one(const double *E, double *Z, const int P, const int l, const int lane, double (*Rm)[W + 1]) {
     constexpr int EW = 2 * W + 1;
     const int n0 = W - l;                         // unknowns taken from z_0
     double M[W];
@@ -391,32 +392,61 @@ __global__ void __launch_bounds__(32) abc_root_kernel(const double *E, double *Z
     }
 }
 
-// expansion of one level: merge i of a level whose blocks span `span` chunks recovers z at chunk index (2i+1)*span
 template <int W>
-__global__ void __launch_bounds__(128) abc_expand_kernel(const double *TOP, double *Z, int nmerge, int span, int P) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nmerge) return;
+__global__ void __launch_bounds__(32) abc_root_kernel(const double *E, double *Z, int P, int l) {
+    __shared__ double Rm[W][W + 1];
+    abc_root_one<W>(E, Z, P, l, threadIdx.x, Rm);
+}
+
+// expansion of one level: merge i of a level whose blocks span `span` chunks recovers z at chunk index (2i+1)*span.
+// One warp per merge: lanes hold the multipliers [z_M (filled in as it is solved) | z_L | z_R | -1] of the stored top rows
+// [Rhat | Fhat | Ghat | hhat]; each row is one coalesced load and one butterfly sum.
+template <int W>
+__device__ __forceinline__ void abc_expand_one(const double *TOP, double *Z, const int i, const int span, const int P, const int lane) {
     constexpr int TW = 3 * W + 1;
     const double *T = TOP + (int64_t)i * W * TW;
     const int64_t iL = (int64_t)2 * i * span, iM = iL + span;
     int64_t iR = iM + span; if (iR > P) iR = P;
-    const double *zL = Z + iL * W, *zR = Z + iR * W;
-    double zl[W], zr[W], sol[W];
-#pragma unroll
-    for (int t = 0; t < W; ++t) { zl[t] = zL[t]; zr[t] = zR[t]; }
+    double mult = 0.0;
+    if (lane >= W && lane < 2 * W) mult = Z[iL * W + (lane - W)];
+    else if (lane >= 2 * W && lane < 3 * W) mult = Z[iR * W + (lane - 2 * W)];
+    else if (lane == 3 * W) mult = -1.0;
 #pragma unroll
     for (int j = W - 1; j >= 0; --j) {
-        double acc = T[j * TW + 3 * W];
+        const double v = lane < TW ? T[j * TW + lane] : 0.0;
+        double p = v * mult;                                  // lanes <= j of the z_M part still hold 0
 #pragma unroll
-        for (int t = 0; t < W; ++t) acc = fma(-T[j * TW + W + t], zl[t], acc);
-#pragma unroll
-        for (int t = 0; t < W; ++t) acc = fma(-T[j * TW + 2 * W + t], zr[t], acc);
-#pragma unroll
-        for (int t = j + 1; t < W; ++t) acc = fma(-T[j * TW + t], sol[t], acc);
-        sol[j] = acc / T[j * TW + j];
+        for (int o = 16; o >= 1; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+        const double rjj = __shfl_sync(FULL, v, j);
+        if (lane == j) mult = -p / rjj;
     }
-#pragma unroll
-    for (int t = 0; t < W; ++t) Z[iM * W + t] = sol[t];
+    if (lane < W) Z[iM * W + lane] = mult;
+}
+template <int W>
+__global__ void __launch_bounds__(128) abc_expand_kernel(const double *TOP, double *Z, int nmerge, int span, int P) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= nmerge) return;
+    abc_expand_one<W>(TOP, Z, i, span, P, threadIdx.x & 31);
+}
+
+// The top of the tree in ONE launch: every level with at most 32 blocks (<= 16 merges; 512 threads keep the merge in registers),
+// the root solve and the matching
+// expansions, one warp per merge and a CTA barrier between levels (each of those levels would otherwise be a launch of a few warps).
+struct AbcTop { int nlev; int cnt[8]; int64_t eoff[9]; int64_t toff[8]; int span0; };
+template <int W>
+__global__ void __launch_bounds__(512) abc_tree_top_kernel(double *E, double *TOP, double *Z, const AbcTop t, const int P, const int l) {
+    __shared__ double Rm[W][W + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int lv = 0; lv < t.nlev; ++lv) {
+        if (w < (t.cnt[lv] + 1) / 2) abc_merge_one<W>(E + t.eoff[lv], E + t.eoff[lv + 1], TOP + t.toff[lv], t.cnt[lv], w, lane);
+        __syncthreads();
+    }
+    if (w == 0) abc_root_one<W>(E + t.eoff[t.nlev], Z, P, l, lane, Rm);
+    __syncthreads();
+    for (int lv = t.nlev - 1; lv >= 0; --lv) {
+        if (w < t.cnt[lv] / 2) abc_expand_one<W>(TOP + t.toff[lv], Z, w, t.span0 << lv, P, lane);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -757,26 +787,38 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     static_assert(ABC_CPW == 32 / GS, "abc_layout must round jx to the chunks-per-warp of stage 1");
     abc_qr_kernel<LP, R, GS><<<(unsigned)((P + 4 * ABC_CPW - 1) / (4 * ABC_CPW)), 128, 0, c->stream>>>(a);
     c->launches++;
-    // levels: level t has nlev[t] blocks stored at E + off[t]
+    // levels: level t has cnt[t] blocks stored at E + eoff[t]; levels with more than 32 blocks are one launch each, the rest of the
+    // tree (merges, root, expansions) is a single launch
     std::vector<int> cnt; std::vector<int64_t> eoff, toff;
     int cur = P; int64_t eo = 0, to = 0;
     cnt.push_back(cur); eoff.push_back(0);
     while (cur > 1) {
         const int nout = (cur + 1) / 2;
         const int64_t nexto = eo + (int64_t)cur * W * EW;
-        abc_merge_kernel<W><<<(unsigned)((nout + 3) / 4), 128, 0, c->stream>>>(A->E->p + eo, A->E->p + nexto, A->TOP->p + to, cur);
-        c->launches++;
         toff.push_back(to);
         to += (int64_t)(cur / 2) * W * TW;
         eo = nexto; cur = nout;
         cnt.push_back(cur); eoff.push_back(eo);
     }
-    abc_root_kernel<W><<<1, 32, 0, c->stream>>>(A->E->p + eo, A->Z->p, P, A->l);
-    c->launches++;
-    for (int t = (int)toff.size() - 1; t >= 0; --t) {
+    const int nlevels = (int)toff.size();
+    int t0 = 0;
+    while (t0 < nlevels && cnt[t0] > 32) ++t0;                 // first level handled by the fused top kernel
+    for (int t = 0; t < t0; ++t) {
+        abc_merge_kernel<W><<<(unsigned)(((cnt[t] + 1) / 2 + 3) / 4), 128, 0, c->stream>>>(A->E->p + eoff[t], A->E->p + eoff[t + 1], A->TOP->p + toff[t], cnt[t]);
+        c->launches++;
+    }
+    {
+        AbcTop top{};
+        top.nlev = nlevels - t0; top.span0 = 1 << t0;
+        for (int k = 0; k < top.nlev; ++k) { top.cnt[k] = cnt[t0 + k]; top.eoff[k] = eoff[t0 + k]; top.toff[k] = toff[t0 + k]; }
+        top.eoff[top.nlev] = eoff[nlevels];
+        abc_tree_top_kernel<W><<<1, 512, 0, c->stream>>>(A->E->p, A->TOP->p, A->Z->p, top, P, A->l);
+        c->launches++;
+    }
+    for (int t = t0 - 1; t >= 0; --t) {
         const int nmerge = cnt[t] / 2;
         if (nmerge == 0) continue;
-        abc_expand_kernel<W><<<(unsigned)((nmerge + 127) / 128), 128, 0, c->stream>>>(A->TOP->p + toff[t], A->Z->p, nmerge, 1 << t, P);
+        abc_expand_kernel<W><<<(unsigned)((nmerge + 3) / 4), 128, 0, c->stream>>>(A->TOP->p + toff[t], A->Z->p, nmerge, 1 << t, P);
         c->launches++;
     }
     abc_bs_kernel<LP, R><<<gchunks, 128, 0, c->stream>>>(a);
