@@ -16,6 +16,7 @@
 // The numpy restatement tests/emul/sof_reference.py documents the algebra and is the CPU check of this file.
 // Layout (row-major, one system): REC[n+pad][lp+1+r] = A[i, i-l .. i+u] | U[i, :];  V[n+pad][r];  lp = l + u.
 #include "../../include/ssm_rng.h"
+#include "fastmath.cuh"
 #include "ssm_internal.cuh"
 
 namespace ssm {
@@ -38,25 +39,6 @@ struct AbcArgs {
 // multiple of pw = lp+1 columns (the sweep is unrolled by pw; no remainder code, no divergence around the shuffles).
 __host__ __device__ __forceinline__ int64_t chunk_start(const AbcArgs &a, int c) { return (int64_t)c * a.m0 + (int64_t)a.pw * (c < a.jx ? c : a.jx); }
 
-// fp64 reciprocal / reciprocal square root without the IEEE slow paths: hardware seed (MUFU, ~2^-22) + two Newton steps
-// (relative error ~1 ulp).  The chunked path returns a solution, not reference-identical factors, so 1-2 ulp is immaterial.
-__device__ __forceinline__ double fast_rcp(double a) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double e = fma(-a, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-a, y, 1.0);
-    return fma(y, e, y);
-}
-__device__ __forceinline__ double fast_rsqrt(double a) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    const double h = 0.5 * a;
-    double e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
-    return fma(y, e, y);
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // stage 1
