@@ -76,10 +76,36 @@ SSM_HD void bps_init(BpsState<L, M, R, P> &st, const double *gtot /* R*R row-maj
 
 // One column q of the sweep.  last = (q == n-1): no reflector, only the final diagonal entry (:123).
 // out[] is the output row record (BpsDims::NFO doubles).
-template <int L, int M, int R, int P, class RowFn>
-SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, double *out) {
+//
+// PAR = 2: the whole step.  PAR = 0 / 1: this caller owns only the band-wide columns t with (t & 1) == PAR of E, Z, dbar, c6, c3E
+// and of the emitted row (out[OD + t], t >= 1) — two warps working on the same systems split the band-wide half of the arithmetic,
+// and because a step shifts every column one place left, a warp that owns the odd columns now owns the even ones at the next
+// step without moving a register.  Column 0 (needed by the scalar prelude of both) is handed over through `xch`: the caller that
+// produces the new column 0 puts it (xch.put(i, v), i < R + L) at the end of its step, the other gets it (xch.get(i)) at the start of
+// its next one; the caller must place a barrier between two steps.  Everything that is not band-wide is computed by both callers.
+struct BpsNoExchange {
+    SSM_HD void put(int, double) const {}
+    SSM_HD void sync() const {}
+    SSM_HD double get(int) const { return 0.0; }
+};
+template <int L, int M, int R, int P, int PAR = 2, class RowFn, class XFn = BpsNoExchange>
+SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, double *out, XFn xch = XFn()) {
     using D = BpsDims<L, M, R, P>;
     constexpr int LM = D::LM;
+#define SSM_OWN(t) (PAR == 2 || (((t) & 1) == PAR))
+    // column 0 of E and Z: mine, or handed over by the caller that owns the even columns
+    double e0[R], z0[L];
+    if (PAR != 1) {
+#pragma unroll
+        for (int a = 0; a < R; ++a) e0[a] = st.E[a][0];
+#pragma unroll
+        for (int s = 0; s < L; ++s) z0[s] = st.Z[s][0];
+    } else {                       // put by the other caller at the end of its previous step; the caller's barrier lies in between
+#pragma unroll
+        for (int a = 0; a < R; ++a) e0[a] = xch.get(a);
+#pragma unroll
+        for (int s = 0; s < L; ++s) z0[s] = xch.get(R + s);
+    }
     double u1[R], V1[R], w1[P], S1[P];
 #pragma unroll
     for (int a = 0; a < R; ++a) { u1[a] = row(0, D::FU + a); V1[a] = row(0, D::FV + a); }
@@ -124,7 +150,7 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
     double core[R], kb[R], b[L];
 #pragma unroll
     for (int a = 0; a < R; ++a) {
-        double s = st.E[a][0];
+        double s = e0[a];
 #pragma unroll
         for (int c = 0; c < P; ++c) s = fma(st.Q[a][c], S1[c], s);
 #pragma unroll
@@ -132,7 +158,7 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
         core[a] = s;
         kb[a] = V1[a] + s;
     }
-    double pivot = row(0, L) + st.Z[0][0];
+    double pivot = row(0, L) + z0[0];
 #pragma unroll
     for (int a = 0; a < R; ++a) { pivot = fma(u1[a], core[a], pivot); pivot = fma(st.Y[0][a], g1[a], pivot); }
 #pragma unroll
@@ -141,7 +167,7 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
     for (int s = 1; s <= L; ++s) {
         double v = xb[s - 1];
         if (s <= L - 1) {
-            v += st.Z[s][0];
+            v += z0[s];
 #pragma unroll
             for (int c = 0; c < P; ++c) v = fma(st.X[s][c], S1[c], v);
 #pragma unroll
@@ -209,6 +235,7 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
     double dbar[LM + 1];
 #pragma unroll
     for (int t = 0; t <= LM; ++t) {
+        if (!SSM_OWN(t)) { dbar[t] = 0.0; continue; }
         double s = 0.0;
 #pragma unroll
         for (int i = 1; i <= L; ++i) {
@@ -255,7 +282,9 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
         for (int t = 1; t <= L - 1; ++t) s = fma(st.Y[t][a], yh[t], s);
         c5[a] = s; }
 #pragma unroll
-    for (int t = 0; t < LM; ++t) { double s = st.Z[0][t];
+    for (int t = 0; t < LM; ++t) {
+        if (t == 0 || !SSM_OWN(t)) { c6[t] = 0.0; continue; }       // c6[0] is never used
+        double s = st.Z[0][t];
 #pragma unroll
         for (int i = 1; i <= L - 1; ++i) s = fma(st.Z[i][t], yh[i], s);
         c6[t] = s; }
@@ -278,8 +307,10 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
     for (int c = 0; c < P; ++c) phi[c] = fma(sig1, w1[c], f[c] + c1[c] + c4[c]);
 #pragma unroll
     for (int t = 0; t < LM; ++t) { double s = 0.0;
+        if (t >= 1 && SSM_OWN(t)) {                                   // c3E[0] is never used
 #pragma unroll
-        for (int a = 0; a < R; ++a) s = fma(c3[a], st.E[a][t], s);
+            for (int a = 0; a < R; ++a) s = fma(c3[a], st.E[a][t], s);
+        }
         c3E[t] = s; }
     // row q of R (:518-561) from the pre-update state
     double beta[R];
@@ -302,6 +333,7 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
     out[D::OD] = -nu;
 #pragma unroll
     for (int t = 1; t <= LM; ++t) {
+        if (!SSM_OWN(t)) continue;
         double s = -tau * dbar[t];
         if (t <= M) s = fma(wcoef, d1[t], s);
         if (t <= LM - 1) {
@@ -339,6 +371,7 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
         for (int c = 0; c < R; ++c) st.K[a][c] = fma(-tk, psi[c], st.K[a][c]);
 #pragma unroll
         for (int t = 0; t < LM; ++t) {
+            if (!SSM_OWN(t + 1)) continue;
             double v = (t + 1 <= LM - 1) ? st.E[a][t + 1] : 0.0;
             double w = dbar[t + 1];
             if (t + 1 <= LM - 1) w += c3E[t + 1] + c6[t + 1];
@@ -355,6 +388,7 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
         for (int c = 0; c < P; ++c) st.X[s - 1][c] = fma(-tb, phi[c], sh ? fma(Yu[s], w1[c], st.X[s][c]) : 0.0);
 #pragma unroll
         for (int t = 0; t < LM; ++t) {
+            if (!SSM_OWN(t + 1)) continue;
             double v = (sh && t + 1 <= LM - 1) ? st.Z[s][t + 1] : 0.0;
             if (sh && t + 1 <= M) v = fma(Yu[s], d1[t + 1], v);
             double w = dbar[t + 1];
@@ -369,6 +403,13 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
     for (int a = 0; a < R; ++a)
 #pragma unroll
         for (int c = 0; c < P; ++c) st.uw[a][c] = fma(u1[a], w1[c], st.uw[a][c]);
+    if (PAR == 1) {                // the new column 0 came from old column 1: publish it for the other caller's next step
+#pragma unroll
+        for (int a = 0; a < R; ++a) xch.put(a, st.E[a][0]);
+#pragma unroll
+        for (int s = 0; s < L; ++s) xch.put(R + s, st.Z[s][0]);
+    }
+#undef SSM_OWN
 }
 
 // ---- lmul!(Q', b) (semiseparableqr.jl:863-919) as a forward streaming pass ---------------------

@@ -7,6 +7,7 @@
 // plus the boundary kernels (pack / unpack / generate) and the O(n) matvec / residual (K9).
 // One lane per system, one warp per tile of 32 systems, as in the AlmostBanded path.
 #include "../../include/ssm_rng.h"
+#include <type_traits>
 #include "bps_core.cuh"
 #include "ssm_internal.cuh"
 #include "stream_loader.cuh"
@@ -347,14 +348,74 @@ int launch_bpsqr_unpack(ssm_ctx *c, const ssm_bpsqr *F, double *B, int64_t sb, d
     return 0;
 }
 
+// Pair mode: a CTA of two warps sweeps ONE tile together — both warps hold all 32 systems, share the window ring, compute the scalar
+// part of every step redundantly and split the band-wide half of the arithmetic (the E / Z state, dbar, c6, the emitted R row) by
+// column parity (bps_core.cuh, PAR).  Twice the warps in flight like the 16+16 split above, but no idle lanes in the band-wide part.
+// The only traffic between the two warps is column 0 of E and Z (R + L doubles per system and step) through shared memory.
+struct BpsPairExchange {
+    double *buf; int lane;
+    __device__ __forceinline__ void put(int i, double v) const { buf[i * 32 + lane] = v; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ double get(int i) const { return buf[i * 32 + lane]; }
+};
+template <int L, int M, int R, int P>
+__global__ void __launch_bounds__(64) bps_qr_pair_kernel(const double *REC, const double *GT, double *OUT, int n, int64_t np, int64_t npo) {
+    using D = BpsDims<L, M, R, P>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ double xbuf[(R + L) * 32];
+    const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    WindowRing<D::NFA, BPS_NST_SPLIT, 2> win;
+    win.init(REC + (tile * np + BPS_FRONT - M) * D::NFA * 32, smem, (int64_t)n + L + M);
+    double gt[R * R];
+#pragma unroll
+    for (int e = 0; e < R * R; ++e) gt[e] = __ldg(GT + (tile * (R * R) + e) * 32 + lane);
+    BpsState<L, M, R, P> st;
+    bps_init<L, M, R, P>(st, gt);
+    double *out = OUT + tile * npo * D::NFO * 32 + lane;
+    const BpsPairExchange xch{xbuf, lane};
+    for (int i = threadIdx.x; i < (R + L) * 32; i += 64) xbuf[i] = 0.0;       // column 0 of the zero initial state
+    __syncthreads();
+    for (int k = 0; k < L + M; ++k) win.wait(k);          // rows -M .. L-1
+    // one column; PARC::value = parity of the band-wide columns this warp owns at this step = (h + q) & 1
+    auto step = [&](auto parc, const int q) {
+        constexpr int PAR = decltype(parc)::value;
+        win.wait((int64_t)q + L + M);                      // row q+L
+        double o[D::NFO];
+        bps_step<L, M, R, P, PAR>(st, [&](int rel, int f) { return win.rec((int64_t)q + rel + M)[f * 32]; }, q == n - 1, o, xch);
+#pragma unroll
+        for (int f = 0; f < D::NFO; ++f) {
+            const bool band = f > D::OD && f <= D::OD + L + M;                       // R[q, q+t], t >= 1: written by the column's owner
+            const bool mine = band ? (((f - D::OD) & 1) == PAR) : (h == 0);
+            if (mine) out[((int64_t)q * D::NFO + f) * 32] = o[f];
+        }
+        win.release(q);                                    // row q-M leaves the window
+    };
+    int q = 0;
+    if (h == 1) { step(std::integral_constant<int, 1>{}, 0); q = 1; }
+    while (q < n) {
+        step(std::integral_constant<int, 0>{}, q++);
+        if (q >= n) break;
+        step(std::integral_constant<int, 1>{}, q++);
+    }
+}
+
 template <int L, int M, int R, int P>
 static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
     using D = BpsDims<L, M, R, P>;
     bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)A->ntiles, 128, 0, c->stream>>>(A->REC->p, nullptr, F->GT->p, nullptr, A->n, A->np, 0);
     c->launches++;
     // split tiles over two warps while the batch cannot give every warp scheduler ~2 warps (ab_variant 1 / 2 force off / on)
-    const bool split = c->ab_variant == 2 || (c->ab_variant == 0 && A->ntiles < (int64_t)c->sm_count * 8);
-    if (split) {
+    // ab_variant: 0 auto, 1 one warp per tile, 2 two warps of 16 systems, 3 pair mode.  Measured at config 3 (512 tiles): 8.07 / 5.81 /
+    // 5.14 ms; at 2,048 tiles one warp per tile and pair mode tie (20.9 / 20.6 ms), so pair mode is the default below 16 tiles per SM.
+    const bool split = c->ab_variant == 2;
+    const bool pair = c->ab_variant == 3 || (c->ab_variant == 0 && A->ntiles < (int64_t)c->sm_count * 16);
+    if (pair) {
+        const size_t smem = WindowRing<D::NFA, BPS_NST_SPLIT, 2>::smem_bytes();
+        auto kern = bps_qr_pair_kernel<L, M, R, P>;
+        SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)A->ntiles, 64, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+    } else if (split) {
         const size_t smem = WindowRing<D::NFA, BPS_NST_SPLIT, 2>::smem_bytes();
         auto kern = bps_qr_kernel<L, M, R, P, 2>;
         SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

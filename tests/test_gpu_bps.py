@@ -38,7 +38,7 @@ def test_generate_matches_oracle_bitwise(bps, ctx):
     assert np.array_equal(y1, y2)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("l,m,r,p", SHAPES)
 def test_qr_and_solves_match_oracle(bps, ctx, variant, l, m, r, p):
     ctx.set_option("ab_variant", variant)
