@@ -191,6 +191,9 @@ template <int UB, int R>
 SSM_HD double bs_step(BsState<UB, R> &st, const int PH, const double *in_r, const double *in_v, const double in_c,
                       const bool unit = false) {
     constexpr int PX = UB + 1;
+    // the reciprocal of the diagonal does not depend on the recurrence: formed first, it overlaps the FMA chain below instead of
+    // sitting at its end (the back-substitution is a serial chain per system; this matters whenever there are few warps per SM)
+    const double rinv = unit ? 1.0 : 1.0 / in_r[0];
     // s += V[:, i+UB+1] * x[i+UB+1]; x[i+UB+1] sits in slot (i+UB+1) mod PX = PH  (:229-230)
     const double xfar = st.XW[PH % PX];
 #pragma unroll
@@ -200,7 +203,7 @@ SSM_HD double bs_step(BsState<UB, R> &st, const int PH, const double *in_r, cons
     for (int q = 0; q < R; ++q) acc = fma(-in_r[UB + 1 + q], st.S[q], acc);   // b[kr] -= U[kr,:]*buffer  (:231)
 #pragma unroll
     for (int t = UB; t >= 1; --t) acc = fma(-in_r[t], st.XW[(PH + t) % PX], acc);  // band part (:233-236)
-    const double x = unit ? acc : acc / in_r[0];
+    const double x = acc * rinv;
     st.XW[PH % PX] = x;                                                    // slot of x[i+UB+1] is now x[i]
     return x;
 }

@@ -126,7 +126,7 @@ __device__ inline void generic_ab_backsolve(const AbSolveArgs &a, int l, int u, 
         double acc = rin[(int64_t)i * 32];
         for (int q = 0; q < r; ++q) acc = fma(-ru[((int64_t)i * nfr + ub + 1 + q) * 32], S[q], acc);  // :231
         for (int t = ub; t >= 1; --t) acc = fma(-ru[((int64_t)i * nfr + t) * 32], XW[t - 1], acc);    // :233-236
-        const double x = a.unit ? acc : acc / ru[((int64_t)i * nfr) * 32];
+        const double x = a.unit ? acc : acc * (1.0 / ru[((int64_t)i * nfr) * 32]);   // same rounding as bs_step (ab_core.cuh)
         rhs[(int64_t)i * 32] = x;
         for (int t = ub; t >= 1; --t) XW[t] = XW[t - 1];
         XW[0] = x;
@@ -152,7 +152,7 @@ __device__ inline void generic_ab_tri(const double *AU, const double *V, double 
             double acc = rhs[(int64_t)i * 32];
             for (int q = 0; q < r; ++q) acc = fma(-au[((int64_t)i * nfa + l + u + 1 + q) * 32], S[q], acc);
             for (int t = u; t >= 1; --t) acc = fma(-au[((int64_t)i * nfa + l + t) * 32], XW[t - 1], acc);
-            const double x = unit ? acc : acc / au[((int64_t)i * nfa + l) * 32];
+            const double x = unit ? acc : acc * (1.0 / au[((int64_t)i * nfa + l) * 32]);
             rhs[(int64_t)i * 32] = x;
             for (int t = u; t >= 1; --t) XW[t] = XW[t - 1];
             XW[0] = x;
@@ -161,7 +161,7 @@ __device__ inline void generic_ab_tri(const double *AU, const double *V, double 
         for (int i = 0; i < n; ++i) {
             double acc = rhs[(int64_t)i * 32];
             for (int t = l; t >= 1; --t) acc = fma(-au[((int64_t)i * nfa + l - t) * 32], XW[t - 1], acc);
-            const double x = unit ? acc : acc / au[((int64_t)i * nfa + l) * 32];
+            const double x = unit ? acc : acc * (1.0 / au[((int64_t)i * nfa + l) * 32]);
             rhs[(int64_t)i * 32] = x;
             for (int t = l; t >= 1; --t) XW[t] = XW[t - 1];
             XW[0] = x;
