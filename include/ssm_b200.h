@@ -60,7 +60,9 @@ int  ssm_ctx_create(int device, ssm_ctx **ctx);                 /* own non-block
 int  ssm_ctx_create_on_stream(int device, void *cuda_stream, ssm_ctx **ctx); /* caller's cudaStream_t   */
 int  ssm_ctx_destroy(ssm_ctx *ctx);
 int  ssm_ctx_sync(ssm_ctx *ctx);
-/* tuning knobs (kernel variant selection for A/B measurements): key in {"ab_variant","pipeline_stages"} */
+/* tuning knobs (kernel variant selection for A/B measurements): key in {"ab_variant" (0 auto, 1 direct loads, 2 per-step
+   bulk-async ring, 4 grouped ring with a producer warp, 9 generic shapes), "pipeline_stages", "group_bytes",
+   "group_max_per_sm" (auto: batches of at most this many 32-system tiles per SM use variant 4)} */
 int  ssm_ctx_set_option(ssm_ctx *ctx, const char *key, int value);
 int  ssm_ctx_get_option(ssm_ctx *ctx, const char *key, int *value);
 /* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */

@@ -15,6 +15,7 @@
 //   fill extension   :  dd = l+u+1 .. 2l+u    <- Ucur[rho,:] . V[:, c]   (c = k+1+ub at the end of step k)
 #pragma once
 #include <cmath>
+#include "fastmath.cuh"
 
 #if defined(__CUDACC__)
 #define SSM_HD __host__ __device__ __forceinline__
@@ -89,12 +90,16 @@ SSM_HD void ab_step(AbState<L, U, R> &st, const int PH, const double *in_rec, co
     double ssq = x0 * x0;
 #pragma unroll
     for (int i = 1; i <= L; ++i) { const double xi = st.A[(PH + i) % P][L - i]; ssq = fma(xi, xi, ssq); }
-    const double nrm = sqrt(ssq);
+    const bool nz = act && (ssq != 0.0);
+    // nu = copysign(|x|, x0), xi = x0 + nu, tau = xi / nu, 1 / xi: branch-free (fastmath.cuh), each within ~1 ulp of the IEEE
+    // sqrt / divide sequence.  Measured on B200 (profiles/r1_measurements.md): 15 % faster sweeps when a warp runs alone on its
+    // scheduler (<= 2 tiles per SM), no change at the headline size (memory bound)
+    const double rs = fast_rsqrt(ssq);
+    const double nrm = fast_sqrt_from_rsqrt(ssq, rs);
     const double nu = copysign(nrm, x0);
     const double xi1 = x0 + nu;
-    const bool nz = act && (ssq != 0.0);
-    const double inv_xi = nz ? 1.0 / xi1 : 0.0;
-    const double tau = nz ? xi1 / nu : 0.0;
+    const double inv_xi = nz ? fast_rcp(xi1) : 0.0;
+    const double tau = nz ? xi1 * copysign(rs, x0) : 0.0;
     double v[L > 0 ? L : 1];
 #pragma unroll
     for (int i = 1; i <= L; ++i) v[i - 1] = st.A[(PH + i) % P][L - i] * inv_xi;
@@ -193,7 +198,7 @@ SSM_HD double bs_step(BsState<UB, R> &st, const int PH, const double *in_r, cons
     constexpr int PX = UB + 1;
     // the reciprocal of the diagonal does not depend on the recurrence: formed first, it overlaps the FMA chain below instead of
     // sitting at its end (the back-substitution is a serial chain per system; this matters whenever there are few warps per SM)
-    const double rinv = unit ? 1.0 : 1.0 / in_r[0];
+    const double rinv = unit ? 1.0 : fast_rcp(in_r[0]);
     // s += V[:, i+UB+1] * x[i+UB+1]; x[i+UB+1] sits in slot (i+UB+1) mod PX = PH  (:229-230)
     const double xfar = st.XW[PH % PX];
 #pragma unroll

@@ -129,6 +129,146 @@ __global__ void __launch_bounds__(32) ab_backsolve_kernel(const AbSolveArgs a, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Small-batch variants of K1/K2/K3 (GroupRing, stream_loader.cuh): one consumer warp per tile plus one producer warp that
+// feeds the ring.  Same arithmetic (ab_core.cuh), same records, same results bit for bit; only the loader cost per step
+// changes.  (Splitting a tile's 32 systems over 2 or 4 consumer warps was built and measured: no gain — a sweep is bound by
+// its serial chain of n steps, which has the same length however few systems a warp carries.)
+// ---------------------------------------------------------------------------------------------------------
+template <int L, int U, int R, bool RHS, bool STOREQ>
+__global__ void __launch_bounds__(64) ab_qr_group_kernel(const AbArgs a, const int nstage, const int gm) {
+    using D = AbDims<L, U, R>;
+    constexpr int P = D::P, UB = D::UB, NFA = D::NFA, NFR = D::NFR, NFQ = D::NFQ;
+    using Ring = GroupRing<NFA, R, RHS ? 1 : 0, +1, P>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int64_t tile = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.n;
+    const int64_t nblocks = (n + P - 1) / P;
+    const double *au_t = a.AU + tile * a.np * NFA * 32;
+    const double *vv_t = a.V + tile * a.np * (R > 0 ? R : 1) * 32;
+    const double *rin_t = RHS ? a.rhs_in + tile * a.np * 32 : nullptr;
+    Ring::init_barriers(smem, nstage, gm, 1);
+    if (warp == 1) {
+        if (lane == 0)
+            Ring::produce(au_t + (int64_t)L * NFA * 32, vv_t + (int64_t)(UB + 1) * R * 32, RHS ? rin_t + L * 32 : nullptr, smem, nstage, gm, nblocks);
+        return;
+    }
+    const int col = lane;
+    const double *au = au_t + col, *vv = vv_t + col, *rin = RHS ? rin_t + col : nullptr;
+    double *rhs = RHS ? a.rhs + tile * a.np * 32 + col : nullptr;
+    double *ru = a.RU + tile * a.np * NFR * 32 + col;
+    double *qt = STOREQ ? a.QT + tile * a.np * NFQ * 32 + col : nullptr;
+
+    AbState<L, U, R> st;
+    ab_prologue<L, U, R, RHS>(
+        st, [&](int rho, int f) { return __ldg(au + (rho * NFA + f) * 32); },
+        [&](int c, int q) { return __ldg(vv + (c * R + q) * 32); }, [&](int rho) { return rin[rho * 32]; });
+    Ring ld;
+    ld.attach(smem, nstage, gm, nblocks, col);
+    for (int kb = 0; kb < n; kb += P) {
+        ld.block_begin();
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) {
+            const int k = kb + ph;
+            double rec[NFA], vc[R > 0 ? R : 1], bb[1];
+            ld.read(ph, rec, vc, bb);
+            double out_r[NFR], out_q[NFQ], out_c;
+            ab_step<L, U, R, RHS>(st, ph, rec, vc, bb[0], k < n - 1, out_r, out_q, out_c);
+            if (k < n) {
+#pragma unroll
+                for (int f = 0; f < NFR; ++f) ru[((int64_t)k * NFR + f) * 32] = out_r[f];
+                if (STOREQ) {
+#pragma unroll
+                    for (int f = 0; f < NFQ; ++f) qt[((int64_t)k * NFQ + f) * 32] = out_q[f];
+                }
+                if (RHS) rhs[(int64_t)k * 32] = out_c;
+            }
+        }
+        ld.block_end();
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(64) ab_qt_group_kernel(const AbSolveArgs a, const int nstage, const int gm) {
+    constexpr int P = L + 1, NFQ = L + 1;
+    using Ring = GroupRing<NFQ, 1, 0, +1, P>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int64_t tile = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.n;
+    const int64_t nblocks = (n + P - 1) / P;
+    const double *qt_t = a.QT + tile * a.np * NFQ * 32;
+    const double *rin_t = a.rhs_in + tile * a.np * 32;
+    Ring::init_barriers(smem, nstage, gm, 1);
+    if (warp == 1) {
+        if (lane == 0) Ring::produce(qt_t, rin_t + L * 32, nullptr, smem, nstage, gm, nblocks);
+        return;
+    }
+    const int col = lane;
+    double *rhs = a.rhs + tile * a.np * 32 + col;
+    const double *rin = rin_t + col;
+    QtState<L> st;
+    qt_prologue<L>(st, [&](int rho) { return rin[rho * 32]; });
+    Ring ld;
+    ld.attach(smem, nstage, gm, nblocks, col);
+    for (int kb = 0; kb < n; kb += P) {
+        ld.block_begin();
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) {
+            const int k = kb + ph;
+            double q[NFQ], bb[1], dummy[1];
+            ld.read(ph, q, bb, dummy);
+            const double c = qt_step<L>(st, ph, q, bb[0]);
+            if (k < n) rhs[(int64_t)k * 32] = c;
+        }
+        ld.block_end();
+    }
+}
+
+template <int L, int U, int R>
+__global__ void __launch_bounds__(64) ab_backsolve_group_kernel(const AbSolveArgs a, const int nstage, const int gm) {
+    using D = AbDims<L, U, R>;
+    constexpr int UB = D::UB, PX = UB + 1, NFR = D::NFR;
+    using Ring = GroupRing<NFR, R, 1, -1, PX>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int64_t tile = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.n;
+    const int nblk = (n + PX - 1) / PX;
+    const int itop = nblk * PX - 1;
+    const double *ru_t = a.RU + tile * a.np * NFR * 32;
+    const double *vv_t = a.V + tile * a.np * (R > 0 ? R : 1) * 32;
+    const double *rin_t = a.rhs_in + tile * a.np * 32;
+    Ring::init_barriers(smem, nstage, gm, 1);
+    if (warp == 1) {
+        if (lane == 0)
+            Ring::produce(ru_t + (int64_t)itop * NFR * 32, vv_t + (int64_t)(itop + UB + 1) * R * 32, rin_t + (int64_t)itop * 32, smem, nstage, gm, nblk);
+        return;
+    }
+    const int col = lane;
+    double *rhs = a.rhs + tile * a.np * 32 + col;
+    BsState<UB, R> st;
+    bs_init<UB, R>(st);
+    Ring ld;
+    ld.attach(smem, nstage, gm, nblk, col);
+    const bool unit = a.unit != 0;
+    for (int ib = (nblk - 1) * PX; ib >= 0; ib -= PX) {
+        ld.block_begin();
+#pragma unroll
+        for (int ph = PX - 1; ph >= 0; --ph) {
+            const int i = ib + ph;
+            double r[NFR], vc[R > 0 ? R : 1], cc[1];
+            ld.read(PX - 1 - ph, r, vc, cc);
+            if (i < n) {
+                const double x = bs_step<UB, R>(st, ph, r, vc, cc[0], unit);
+                rhs[(int64_t)i * 32] = x;
+            }
+        }
+        ld.block_end();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // generic (runtime l,u,r) kernels — any shape within SSM_MAX_*; also Q*b and the operand-level triangular solves
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) ab_qr_generic_kernel(const AbArgs a, int l, int u, int r, int with_rhs, int store_q) {
@@ -148,12 +288,18 @@ __global__ void __launch_bounds__(32) ab_tri_generic_kernel(const double *AU, co
 // ---------------------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------------------
-static int pick_stages(const ssm_ctx *c, size_t stage_bytes) {
+static int pick_stages(const ssm_ctx *c, size_t stage_bytes, int64_t ntiles) {
     if (c->pipeline_stages > 0) return c->pipeline_stages;
-    // fill ~15 KB per warp so that 14 single-warp CTAs (all 2048 tiles of the headline config) stay co-resident
-    int s = (int)(15000 / (stage_bytes + 8));
+    // The ring is the only thing that hides HBM latency for a single-warp CTA, so it takes the shared memory the grid leaves
+    // free: ~15 KB per warp when 14 CTAs per SM are co-resident (all 2048 tiles of the headline config), proportionally
+    // deeper when the batch is small (Little: ~6.5 MB must be in flight device-wide to reach the HBM rate).
+    int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 14) per_sm = 14;
+    const size_t budget = (size_t)(210 * 1024) / (size_t)per_sm;
+    int s = (int)(budget / (stage_bytes + 8));
     if (s < 2) s = 2;
-    if (s > 8) s = 8;
+    if (s > 48) s = 48;
     return s;
 }
 
@@ -165,15 +311,72 @@ static int launch1(ssm_ctx *c, K kern, int64_t ntiles, size_t smem, const char *
     return 0;
 }
 
+// GroupRing geometry for a grid of ntiles CTAs: as many stages of gm blocks as the shared memory left per CTA holds; returns
+// false when not even two single-block stages fit (the caller then keeps the per-step ring).
+static bool pick_group(const ssm_ctx *c, size_t block_bytes, int64_t ntiles, int *nstage, int *gm) {
+    int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
+    if (per_sm < 1) per_sm = 1;
+    const size_t budget = (size_t)(200 * 1024) / (size_t)per_sm;
+    int g = (int)((size_t)c->group_bytes / block_bytes);   // aim at group_bytes per bulk copy group ...
+    if (g < 1) g = 1;
+    int s = (int)(budget / (g * block_bytes + 16));
+    while (s < 6 && g > 1) { --g; s = (int)(budget / (g * block_bytes + 16)); }   // ... but keep at least 6 stages in flight
+    if (s < 2) return false;
+    if (s > 12) s = 12;
+    if (c->pipeline_stages > 0) s = c->pipeline_stages;
+    if ((size_t)s * (g * block_bytes + 16) > (size_t)220 * 1024) return false;
+    *nstage = s; *gm = g;
+    return true;
+}
+
+template <class K>
+static int launch_group(ssm_ctx *c, K kern, size_t smem) {
+    if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    (void)c;
+    return 0;
+}
+
+static inline bool is_group_variant(int v) { return v == 4; }
+
+#define SSM_GROUP_GO(KERN_, ARGS_)                                                                 \
+    {                                                                                              \
+        auto kern = KERN_;                                                                         \
+        SSM_TRY(launch_group(c, kern, smem));                                                      \
+        kern<<<(unsigned)ntiles, 64, smem, c->stream>>>(ARGS_, ns, gm);                            \
+    }
+
+template <int L, int U, int R, bool RHS, bool SQ>
+static int qr_group(ssm_ctx *c, int64_t ntiles, const AbArgs &a, bool *done) {
+    using D = AbDims<L, U, R>;
+    using RG = GroupRing<D::NFA, R, RHS ? 1 : 0, +1, D::P>;
+    int ns, gm;
+    *done = false;
+    if (!pick_group(c, RG::BLOCK_BYTES, ntiles, &ns, &gm)) return 0;
+    const size_t smem = RG::smem_bytes(ns, gm);
+    SSM_GROUP_GO((ab_qr_group_kernel<L, U, R, RHS, SQ>), a)
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    *done = true;
+    return 0;
+}
+
 template <int L, int U, int R>
 static int qr_inst(ssm_ctx *c, int64_t ntiles, const AbArgs &a, bool with_rhs, bool store_q, int variant) {
     using D = AbDims<L, U, R>;
     dim3 grid((unsigned)ntiles), block(32);
+    if (is_group_variant(variant)) {       // instantiated for qr (keep reflectors) and for the fused A\\b sweep
+        bool done = false;
+        if (!with_rhs && store_q) SSM_TRY((qr_group<L, U, R, false, true>(c, ntiles, a, &done)));
+        if (with_rhs && !store_q) SSM_TRY((qr_group<L, U, R, true, false>(c, ntiles, a, &done)));
+        if (done) return 0;
+        variant = 2;
+    }
 #define SSM_QR_CASE(RHS_, SQ_)                                                                                   \
     if (with_rhs == RHS_ && store_q == SQ_) {                                                                    \
         if (variant == 2) {                                                                                      \
             using LD = RingLoader<D::NFA, R, RHS_ ? 1 : 0, +1>;                                                  \
-            const int ns = pick_stages(c, LD::STAGE_BYTES);                                                      \
+            const int ns = pick_stages(c, LD::STAGE_BYTES, ntiles);                                                      \
             const size_t smem = LD::smem_bytes(ns);                                                              \
             auto kern = ab_qr_kernel<L, U, R, RHS_, SQ_, RingLoaderD>;                                            \
             SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qr_ring"));                                               \
@@ -195,9 +398,21 @@ static int qr_inst(ssm_ctx *c, int64_t ntiles, const AbArgs &a, bool with_rhs, b
 template <int L>
 static int qt_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant) {
     dim3 grid((unsigned)ntiles), block(32);
+    if (is_group_variant(variant)) {
+        using RG = GroupRing<L + 1, 1, 0, +1, L + 1>;
+        int ns, gm;
+        if (pick_group(c, RG::BLOCK_BYTES, ntiles, &ns, &gm)) {
+            const size_t smem = RG::smem_bytes(ns, gm);
+            SSM_GROUP_GO((ab_qt_group_kernel<L>), a)
+            c->launches++;
+            SSM_CUDA(cudaGetLastError());
+            return 0;
+        }
+        variant = 2;
+    }
     if (variant == 2) {
         using LD = RingLoader<L + 1, 1, 0, +1>;
-        const int ns = pick_stages(c, LD::STAGE_BYTES);
+        const int ns = pick_stages(c, LD::STAGE_BYTES, ntiles);
         const size_t smem = LD::smem_bytes(ns);
         auto kern = ab_qt_kernel<L, RingLoaderD>;
         SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qt_ring"));
@@ -214,9 +429,21 @@ template <int L, int U, int R>
 static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant) {
     using D = AbDims<L, U, R>;
     dim3 grid((unsigned)ntiles), block(32);
+    if (is_group_variant(variant)) {
+        using RG = GroupRing<D::NFR, R, 1, -1, D::UB + 1>;
+        int ns, gm;
+        if (pick_group(c, RG::BLOCK_BYTES, ntiles, &ns, &gm)) {
+            const size_t smem = RG::smem_bytes(ns, gm);
+            SSM_GROUP_GO((ab_backsolve_group_kernel<L, U, R>), a)
+            c->launches++;
+            SSM_CUDA(cudaGetLastError());
+            return 0;
+        }
+        variant = 2;
+    }
     if (variant == 2) {
         using LD = RingLoader<D::NFR, R, 1, -1>;
-        const int ns = pick_stages(c, LD::STAGE_BYTES);
+        const int ns = pick_stages(c, LD::STAGE_BYTES, ntiles);
         const size_t smem = LD::smem_bytes(ns);
         auto kern = ab_backsolve_kernel<L, U, R, RingLoaderD>;
         SSM_TRY(launch1(c, kern, ntiles, smem, "ab_bs_ring"));
@@ -236,9 +463,9 @@ static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
 // store-heavy), the two light solve kernels with the bulk-async ring (profiles/README.md)
 // Below ~7 single-warp CTAs per SM there are too few warps to hide HBM latency behind one-step-ahead register loads, and the ring's
 // deep bulk-async prefetch wins for the QR sweep as well (measured: n=1024 x 16,384 systems 0.81 -> 0.47 ms, n=8192 x 4,096 5.1 -> 3.6 ms).
-static int effective_variant(const ssm_ctx *c, int kernel_default, int64_t ntiles = 1 << 30) {
+static int effective_variant(const ssm_ctx *c, int kernel_default, int64_t ntiles) {
     if (c->ab_variant != 0) return c->ab_variant;
-    if (kernel_default == 1 && ntiles <= (int64_t)c->sm_count * 7) return 2;
+    if (ntiles <= (int64_t)c->sm_count * c->group_max_per_sm) return 4;   // small batch: GroupRing kernels
     return kernel_default;
 }
 
@@ -261,7 +488,7 @@ int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &
 int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a, bool transpose) {
     (void)u; (void)r;
     if (ntiles <= 0) return 0;
-    const int variant = effective_variant(c, 2);
+    const int variant = effective_variant(c, 2, ntiles);
     if (variant != 9 && transpose) {
         switch (l) {
             case 1: return qt_inst<1>(c, ntiles, a, variant);
@@ -280,7 +507,7 @@ int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveA
 
 int launch_ab_backsolve(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a) {
     if (ntiles <= 0) return 0;
-    const int variant = effective_variant(c, 2);
+    const int variant = effective_variant(c, 2, ntiles);
     if (variant != 9) {
 #define X(L_, U_, R_) \
     if (l == L_ && u == U_ && r == R_) return bs_inst<L_, U_, R_>(c, ntiles, a, variant);

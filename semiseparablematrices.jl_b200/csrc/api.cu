@@ -147,6 +147,8 @@ int ssm_ctx_set_option(ssm_ctx *c, const char *key, int value) {
     SSM_CHECK_ARG(c && key, "null argument");
     if (!strcmp(key, "ab_variant")) c->ab_variant = value;
     else if (!strcmp(key, "pipeline_stages")) c->pipeline_stages = value;
+    else if (!strcmp(key, "group_max_per_sm")) c->group_max_per_sm = value;
+    else if (!strcmp(key, "group_bytes")) c->group_bytes = value;
     else { set_error("unknown option '%s'", key); return SSM_E_ARG; }
     return 0;
 }
@@ -154,6 +156,8 @@ int ssm_ctx_get_option(ssm_ctx *c, const char *key, int *value) {
     SSM_CHECK_ARG(c && key && value, "null argument");
     if (!strcmp(key, "ab_variant")) *value = c->ab_variant;
     else if (!strcmp(key, "pipeline_stages")) *value = c->pipeline_stages;
+    else if (!strcmp(key, "group_max_per_sm")) *value = c->group_max_per_sm;
+    else if (!strcmp(key, "group_bytes")) *value = c->group_bytes;
     else if (!strcmp(key, "sm_count")) *value = c->sm_count;
     else { set_error("unknown option '%s'", key); return SSM_E_ARG; }
     return 0;

@@ -1,19 +1,33 @@
-// fastmath.cuh — fp64 reciprocal / reciprocal square root without the IEEE slow paths (device only).
+// fastmath.cuh — fp64 reciprocal / reciprocal square root without the IEEE slow paths.
+// Device: hardware seed (MUFU, ~2^-22) + two Newton steps, branch-free — besides being shorter than the IEEE sequences
+// (measured on B200, dependent chain: sqrt 92 cycles, 1/x 71, y/x 123; fast_rsqrt 63, fast_rcp 47), the absence of a slow-path
+// branch lets the compiler schedule independent arithmetic across them, which is what a lone warp per scheduler needs.
+// Host (tests/emul): plain IEEE expressions; the two agree to ~1 ulp.
 #pragma once
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define SSM_FM_HD __host__ __device__ __forceinline__
+#else
+#define SSM_FM_HD inline
+#endif
 
 namespace ssm {
 
-// fp64 reciprocal / reciprocal square root without the IEEE slow paths: hardware seed (MUFU, ~2^-22) + two Newton steps
-// (relative error ~1 ulp).  The chunked path returns a solution, not reference-identical factors, so 1-2 ulp is immaterial.
-__device__ __forceinline__ double fast_rcp(double a) {
+SSM_FM_HD double fast_rcp(double a) {
+#if defined(__CUDA_ARCH__)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     double e = fma(-a, y, 1.0);
     y = fma(y, e, y);
     e = fma(-a, y, 1.0);
     return fma(y, e, y);
+#else
+    return 1.0 / a;
+#endif
 }
-__device__ __forceinline__ double fast_rsqrt(double a) {
+SSM_FM_HD double fast_rsqrt(double a) {
+#if defined(__CUDA_ARCH__)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     const double h = 0.5 * a;
@@ -21,10 +35,13 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
     y = fma(y, e, y);
     e = fma(-h * y, y, 0.5);
     return fma(y, e, y);
+#else
+    return 1.0 / std::sqrt(a);
+#endif
 }
 
 // sqrt(a) to ~1 ulp from the refined reciprocal square root (a > 0 and finite; a == 0 gives NaN, callers mask it)
-__device__ __forceinline__ double fast_sqrt_from_rsqrt(double a, double rs) {
+SSM_FM_HD double fast_sqrt_from_rsqrt(double a, double rs) {
     const double nrm = a * rs;
     return fma(fma(-nrm, nrm, a), 0.5 * rs, nrm);
 }

@@ -61,7 +61,9 @@ struct ssm_ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
     bool         own_stream = false;
-    int          ab_variant = 0;       // 0 auto, 1 direct-load kernels, 2 bulk-async (TMA) ring kernels, 9 generic
+    int          ab_variant = 0;       // 0 auto, 1 direct-load kernels, 2 bulk-async (TMA) ring kernels, 4 GroupRing kernels (producer warp + grouped bulk copies), 9 generic
+    int          group_bytes = 32768;  // GroupRing: target size of one bulk-copy group
+    int          group_max_per_sm = 9; // auto: batches of at most this many tiles per SM run the GroupRing kernels
     int          pipeline_stages = 0;  // 0 = kernel default
     int          sm_count = 148;
     int64_t      launches = 0;

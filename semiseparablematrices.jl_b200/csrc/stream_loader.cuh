@@ -149,6 +149,96 @@ struct RingLoader {
 template <int NF0, int NF1, int NF2, int DIR> using DirectLoaderD = DirectLoader<NF0, NF1, NF2, DIR>;
 template <int NF0, int NF1, int NF2, int DIR> using RingLoaderD = RingLoader<NF0, NF1, NF2, DIR>;
 
+// ---- GroupRing ----------------------------------------------------------------------------------------
+// The loader for SMALL batches, where one warp per scheduler (or fewer) runs alone and every cycle spent on the loader sits
+// on the sweep's serial chain.  Differences from RingLoader:
+//   * a stage holds a GROUP of gm blocks of P consecutive steps (P = the sweep's unroll period); the rows of a group are
+//     contiguous in the tile's record stream, so a group is ONE bulk copy per stream and ONE mbarrier wait per gm*P steps;
+//   * the copies are issued by a dedicated producer warp (one thread), which waits on per-stage "empty" mbarriers — the
+//     consumers never execute a copy instruction;
+// Inside a block the reads are plain LDS at compile-time offsets from three pointers, so the compiler hoists them freely.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int NF0, int NF1, int NF2, int DIR, int P>
+struct GroupRing {
+    static constexpr int RECD = (NF0 + NF1 + NF2) * 32;                 // doubles per step
+    static constexpr size_t BLOCK_BYTES = (size_t)P * RECD * 8;
+    static __host__ __device__ size_t smem_bytes(int nstage, int gm) { return (size_t)nstage * gm * BLOCK_BYTES + (size_t)nstage * 16; }
+
+    // every thread of the CTA calls this once (contains a CTA barrier)
+    static __device__ __forceinline__ void init_barriers(void *smem, int nstage, int gm, int nconsumer_warps) {
+        const uint32_t bars = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)nstage * gm * BLOCK_BYTES);
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < nstage; ++s) { mbar_init(bars + 16u * s, 1); mbar_init(bars + 16u * s + 8u, nconsumer_warps); }
+            fence_barrier_init();
+        }
+        __syncthreads();
+    }
+    // producer thread: g0..g2 = tile base (not lane adjusted) of the record step 0 reads from each stream
+    static __device__ __forceinline__ void produce(const double *g0, const double *g1, const double *g2, void *smem, int nstage,
+                                                   int gm, int64_t nblocks) {
+        double *ring = reinterpret_cast<double *>(smem);
+        const int G = gm * P;
+        const uint32_t bars = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)nstage * gm * BLOCK_BYTES);
+        int s = 0; uint32_t use = 0;
+        for (int64_t b0 = 0; b0 < nblocks; b0 += gm) {
+            if (use > 0) mbar_wait(bars + 16u * s + 8u, (use - 1) & 1u);
+            const int rows = (int)((nblocks - b0 < gm ? nblocks - b0 : gm)) * P;
+            const int64_t r0 = b0 * P;                                   // first step of the group
+            const int64_t lo = DIR > 0 ? r0 : -(r0 + rows - 1);          // lowest record of the group, relative to step 0's
+            const uint32_t bar = bars + 16u * s;
+            double *dst = ring + (size_t)s * G * RECD;
+            mbar_expect_tx(bar, (uint32_t)rows * RECD * 8u);
+            if (NF0 > 0) bulk_g2s(smem_u32(dst), g0 + lo * NF0 * 32, (uint32_t)rows * NF0 * 256u, bar);
+            if (NF1 > 0) bulk_g2s(smem_u32(dst + (size_t)G * NF0 * 32), g1 + lo * NF1 * 32, (uint32_t)rows * NF1 * 256u, bar);
+            if (NF2 > 0) bulk_g2s(smem_u32(dst + (size_t)G * (NF0 + NF1) * 32), g2 + lo * NF2 * 32, (uint32_t)rows * NF2 * 256u, bar);
+            if (++s == nstage) { s = 0; ++use; }
+        }
+    }
+
+    // ---- consumer side ----
+    double *ring; uint32_t bars; int nstage, gm, lane, col;
+    int64_t blocks_left;
+    int cur = 0, blk = 0, cb = 0; uint32_t parity = 0;
+    const double *s0, *s1, *s2;
+    __device__ __forceinline__ void attach(void *smem, int nst, int gm_, int64_t nblocks, int col_) {
+        ring = reinterpret_cast<double *>(smem); nstage = nst; gm = gm_; blocks_left = nblocks; col = col_;
+        lane = threadIdx.x & 31;
+        bars = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)nst * gm_ * BLOCK_BYTES);
+    }
+    __device__ __forceinline__ void block_begin() {
+        if (blk == 0) {
+            mbar_wait(bars + 16u * cur, parity);
+            cb = (int)(blocks_left < gm ? blocks_left : gm);
+        }
+        const int G = gm * P;
+        const int row = DIR > 0 ? blk * P : cb * P - 1 - blk * P;
+        const double *base = ring + (size_t)cur * G * RECD + col;
+        s0 = base + row * NF0 * 32;
+        s1 = base + G * NF0 * 32 + row * NF1 * 32;
+        s2 = base + G * (NF0 + NF1) * 32 + row * NF2 * 32;
+    }
+    // t = step within the block, in consumption order (compile-time at the call site)
+    __device__ __forceinline__ void read(const int t, double *r0, double *r1, double *r2) const {
+#pragma unroll
+        for (int f = 0; f < NF0; ++f) r0[f] = s0[(DIR * t * NF0 + f) * 32];
+#pragma unroll
+        for (int f = 0; f < NF1; ++f) r1[f] = s1[(DIR * t * NF1 + f) * 32];
+#pragma unroll
+        for (int f = 0; f < NF2; ++f) r2[f] = s2[(DIR * t * NF2 + f) * 32];
+    }
+    __device__ __forceinline__ void block_end() {
+        if (++blk == cb) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 16u * cur + 8u);
+            blk = 0; blocks_left -= cb;
+            if (++cur == nstage) { cur = 0; parity ^= 1u; }
+        }
+    }
+};
+
 // ---- WindowRing ---------------------------------------------------------------------------------------
 // A sliding window of whole records that stay in shared memory while the sweep needs them (the BPS sweep looks
 // M rows back and L rows ahead).  Record k of the sequence lives in slot k mod NST (NST a power of two) from

@@ -20,7 +20,7 @@ GOLDEN = Path(__file__).parent / "golden"
 
 FAST_SHAPES = [(1, 0, 1), (1, 1, 1), (1, 0, 2), (2, 0, 2), (2, 2, 2), (3, 3, 2), (4, 4, 2)]
 GENERIC_SHAPES = [(0, 2, 1), (3, 1, 3), (5, 2, 4), (8, 8, 2), (2, 2, 0), (0, 0, 1)]
-VARIANTS = [1, 2, 9]   # direct-load, bulk-async ring, generic
+VARIANTS = [1, 2, 4, 9]   # direct-load, bulk-async ring, group ring, generic
 
 
 @pytest.fixture()
@@ -218,7 +218,7 @@ def test_solve_host_end_to_end(ssm, ctx):
         assert np.array_equal(x, x2)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 4])
 def test_full_size_config2_properties(ssm, ctx, variant):
     """BASELINE.json configs[1]: n=1024, l=u=2, r=2, 65,536 systems.  Every system: structured residual <= 1e-13;
     a sample of systems: solution within 1e-12 of the oracle, factors within 1e-13."""

@@ -208,6 +208,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="extra context option key=value (tuning aid)")
     ap.add_argument("--nb", type=int, default=0)
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--world", type=int, default=1)
@@ -221,4 +222,7 @@ if __name__ == "__main__":
         ctx.set_option("ab_variant", args.variant)
     if args.stages:
         ctx.set_option("pipeline_stages", args.stages)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     {"c2": c2, "c2m": c2m, "c3": c3, "c3rq": c3rq, "c4": c4, "c5": c5, "c5dist": c5dist}[args.which](args, ctx)
