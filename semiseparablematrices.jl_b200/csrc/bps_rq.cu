@@ -13,30 +13,53 @@
 // reference step and against dense R0*Q.
 #include "bps_core.cuh"
 #include "ssm_internal.cuh"
+#include "stream_loader.cuh"
+#include <type_traits>
 
 namespace ssm {
 
 struct RqOut { double *NEW; int64_t np2; int nfa2, tl2, tm2, tr2, tp2; };
 
-// split = 1: one warp per tile.  split = 2 / 4: the tile's 32 systems are spread over 2 / 4 warps (the other lanes shadow and do not
-// store) — the step is a long dependent chain, so small batches are latency bound and more warps in flight is what helps.
+// One warp per tile.  The step at row q looks L+M rows ahead into the factor, so the rows q..q+L+M stay in shared memory in
+// three bulk-async window rings (stream_loader.cuh WindowRing) that hold exactly the fields the sweep touches:
+//   ring A: the R part of the OUT records (pivot/d | alpha | beta | A'U)  — read at rows q..q+L+M
+//   ring B: S[:, 1:p] of the REC records                                 — read at rows q..q+L+M
+//   ring C: the Q part of the OUT records (reflector tail | k-bar | tau)  — read at row q only (shallow ring)
+// Every field is read from HBM once by the sweep (plus the reduction prologue's pass over U, S and A'U); the first version
+// read the window rows with direct global loads and spent its time waiting for them (18 ms -> see profiles/r1_measurements.md).
 template <int L, int M, int R, int P>
-__global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const double *OUT, RqOut o, int *flag, int n, int64_t np, int64_t npo, int split) {
+struct RqRings {
     using D = BpsDims<L, M, R, P>;
+    static constexpr int MW = L + M;
+    static constexpr int NSTA = MW + 6, NSTC = 5;          // window + 5 rows of look-ahead
+    using RingA = WindowRing<D::NFRP, NSTA, 1, D::NFO>;
+    using RingB = WindowRing<P, NSTA, 1, D::NFA>;
+    using RingC = WindowRing<D::NFQ, NSTC, 1, D::NFO>;
+    static constexpr size_t OFFB = (RingA::smem_bytes() + 127) / 128 * 128;
+    static constexpr size_t OFFC = OFFB + (RingB::smem_bytes() + 127) / 128 * 128;
+    static constexpr size_t BYTES = OFFC + RingC::smem_bytes();
+};
+
+template <int L, int M, int R, int P>
+__global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const double *OUT, RqOut o, int *flag, int n, int64_t np, int64_t npo) {
+    using D = BpsDims<L, M, R, P>;
+    using RR = RqRings<L, M, R, P>;
     static_assert(P == R, "symmetric BPS: p == r");
     constexpr int PW = P + R, MW = L + M;
-    const int lw = 32 / split;
-    const int lane = ((int)threadIdx.x & (lw - 1)) + lw * (int)(blockIdx.x % split);
-    const bool writer = (int)threadIdx.x < lw;
-    const int64_t tile = blockIdx.x / split;
-    const double *rec0 = REC + (tile * np + BPS_FRONT) * D::NFA * 32 + lane;
-    const double *out0 = OUT + tile * npo * D::NFO * 32 + lane;
-    auto recf = [&](int i, int f) -> double { return i < n ? rec0[((int64_t)i * D::NFA + f) * 32] : 0.0; };
-    auto outf = [&](int i, int f) -> double { return i < n ? out0[((int64_t)i * D::NFO + f) * 32] : 0.0; };
-    auto Bup = [&](int i, int k) -> double { return (k < n && k - i <= MW) ? outf(i, D::OD + (k - i)) : 0.0; };       // R0[i,k], k >= i
-    auto Wext = [&](int i, int c) -> double { return c < P ? outf(i, D::OWA + c) : outf(i, D::OWB + (c - P)); };
-    auto Sext = [&](int i, int c) -> double { return c < P ? recf(i, D::FS + c) : outf(i, D::OSU + (c - P)); };
-    auto Su = [&](int i, int a) -> double { return recf(i, D::FS + a); };                                            // = U0 (checked)
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = (int)threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const double *rec_t = REC + (tile * np + BPS_FRONT) * D::NFA * 32;
+    const double *out_t = OUT + tile * npo * D::NFO * 32;
+    const double *rec0 = rec_t + lane, *out0 = out_t + lane;
+    typename RR::RingA ra; typename RR::RingB rb; typename RR::RingC rc;
+    ra.init(out_t + D::OD * 32, smem, n);
+    rb.init(rec_t + D::FS * 32, smem + RR::OFFB, n);
+    rc.init(out_t, smem + RR::OFFC, n);
+    // global-memory accessors (prologue)
+    auto grec = [&](int i, int f) -> double { return rec0[((int64_t)i * D::NFA + f) * 32]; };
+    auto gout = [&](int i, int f) -> double { return out0[((int64_t)i * D::NFO + f) * 32]; };
+    constexpr bool writer = true;
     // new operand records
     const int nfb2 = o.tl2 + o.tm2 + 1, FU2 = nfb2, FV2 = nfb2 + o.tr2, FW2 = nfb2 + 2 * o.tr2, FS2 = nfb2 + 2 * o.tr2 + o.tp2;
     double *new0 = o.NEW + (tile * o.np2 + BPS_FRONT) * o.nfa2 * 32 + lane;
@@ -55,19 +78,22 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
         for (int a = 0; a < R; ++a) T2[c][a] = 0.0;
     }
     bool bad = false;
+#pragma unroll 8
     for (int i = 0; i < n; ++i) {
-        double su[R];
+        double su[R], sx[PW];
 #pragma unroll
-        for (int a = 0; a < R; ++a) { su[a] = Su(i, a); bad |= su[a] != recf(i, D::FU + a); }
+        for (int a = 0; a < R; ++a) { su[a] = grec(i, D::FS + a); bad |= su[a] != grec(i, D::FU + a); sx[a] = su[a]; }
+#pragma unroll
+        for (int c = P; c < PW; ++c) sx[c] = gout(i, D::OSU + (c - P));
 #pragma unroll
         for (int a = 0; a < R; ++a) {
 #pragma unroll
             for (int c = 0; c < R; ++c) T1[a][c] = fma(su[a], su[c], T1[a][c]);
         }
 #pragma unroll
-        for (int c = 0; c < PW; ++c) { const double s = Sext(i, c);
+        for (int c = 0; c < PW; ++c) {
 #pragma unroll
-            for (int a = 0; a < R; ++a) T2[c][a] = fma(s, su[a], T2[c][a]); }
+            for (int a = 0; a < R; ++a) T2[c][a] = fma(sx[c], su[a], T2[c][a]); }
     }
     if (bad) atomicOr(flag, 1);
 
@@ -85,7 +111,27 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
         for (int t = 0; t < L; ++t) Lam[s][t] = 0.0;
     }
 
-    for (int q = 0; q < n; ++q) {
+    // One step of the sweep.  EDGE = false: all of rows q..q+MW exist (q + MW < n), so every bounds test of the reference's
+    // index ranges folds away at compile time; the last MW steps run the general instance.  Window rows are addressed through
+    // per-step slot pointers (row q + t, t a compile-time constant after unrolling): no modulo arithmetic per access.
+    int sa = 0, sc = 0;                                   // ring slots of row q (rings A / B, ring C)
+    auto step = [&](auto edge, const int q) {
+        constexpr bool EDGE = decltype(edge)::value;
+        const double *pa[MW + 1], *pb[MW + 1];
+#pragma unroll
+        for (int t = 0; t <= MW; ++t) {
+            int sl = sa + t;
+            if (sl >= RR::NSTA) sl -= RR::NSTA;
+            pa[t] = ra.ring + sl * (D::NFRP * 32) + lane;
+            pb[t] = rb.ring + sl * (P * 32) + lane;
+        }
+        const double *pc = rc.ring + sc * (D::NFQ * 32) + lane;
+        // field f of the OUT record of row i = q + t (rows >= n read as zero); Q-part fields are only read at row q
+        auto outf = [&](int i, int f) -> double { return (!EDGE || i < n) ? (f >= D::OD ? pa[i - q][(f - D::OD) * 32] : pc[f * 32]) : 0.0; };
+        auto Bup = [&](int i, int k) -> double { return ((!EDGE || k < n) && k - i <= MW) ? outf(i, D::OD + (k - i)) : 0.0; };   // R0[i,k], k >= i
+        auto Wext = [&](int i, int c) -> double { return c < P ? outf(i, D::OWA + c) : outf(i, D::OWB + (c - P)); };
+        auto Su = [&](int i, int a) -> double { return (!EDGE || i < n) ? pb[i - q][a * 32] : 0.0; };                          // = U0 (checked)
+        auto Sext = [&](int i, int c) -> double { return c < P ? Su(i, c) : outf(i, D::OSU + (c - P)); };
         double u1[R];
 #pragma unroll
         for (int a = 0; a < R; ++a) u1[a] = Su(q, a);
@@ -112,7 +158,7 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
         }
 #pragma unroll
         for (int a = 0; a < R; ++a) if (a < o.tr2) { const double un = fma(d0, u1[a], rho[a]); put(q, FU2 + a, un); if (a < o.tp2) put(q, FS2 + a, un); }   // U_new = R0 U0 (fast_RU)
-        if (q == n - 1) {
+        if (EDGE && q == n - 1) {
             // last diagonal entry (:278; getindex :214-269 with k = i = n): the R0 U0 row of the last row is B[n,n] U0[n,:]
             double dg = d0;
 #pragma unroll
@@ -128,9 +174,9 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
             put(q, o.tl2, dg);
 #pragma unroll
             for (int a = 0; a < R; ++a) if (a < o.tr2) { put(q, FV2 + a, 0.0); if (a < o.tp2) put(q, FW2 + a, 0.0); }
-            break;
+            return;
         }
-        const int lb = min(L, n - 1 - q), nv = min(L, n - q);
+        const int lb = EDGE ? min(L, n - 1 - q) : L, nv = EDGE ? min(L, n - q) : L;
         const double tq = outf(q, D::OT);
         double b[L], kb[R];
 #pragma unroll
@@ -299,6 +345,17 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
 #pragma unroll
             for (int a = 0; a < R; ++a) Phi[s_][a] = PhiN[s_][a];
         }
+    };
+    for (int k = 0; k < MW && k < n; ++k) { ra.wait(k); rb.wait(k); }
+    for (int q = 0; q < n; ++q) {
+        if (q + MW < n) { ra.wait(q + MW); rb.wait(q + MW); }
+        rc.wait(q);
+        if (q + MW < n) step(std::false_type{}, q);
+        else step(std::true_type{}, q);
+        // row q leaves the window: re-arm its slots with rows q + NST
+        ra.release(q); rb.release(q); rc.release(q);
+        if (++sa == RR::NSTA) sa = 0;
+        if (++sc == RR::NSTC) sc = 0;
     }
 }
 
@@ -351,13 +408,14 @@ int ssm_bpsqr_rq_mul(const ssm_bpsqr *F, ssm_bps **out) {
     int rc = dev_alloc(c->device, 1, true, c->stream, flag);
     if (!rc) {
         RqOut o{Q->REC->p, Q->np, bps_nfa(Q->tl, Q->tm, Q->tr, Q->tp), Q->tl, Q->tm, Q->tr, Q->tp};
-        // spreading a tile over 2 / 4 warps was measured and does not pay here (the window rows are re-read from L1 / L2 by every
-        // warp of the tile: 16,384 systems 26 -> 42 ms); the knob stays for experiments (ab_variant 2 -> 2 warps per tile)
-        const int split = c->ab_variant == 2 ? 2 : 1;
         rc = SSM_E_UNSUPPORTED;
 #define X(L_, M_, R_, P_)                                                                                                   \
     if (F->tl == L_ && F->tm == M_ && F->tr == R_ && F->tp == P_) {                                                        \
-        bps_rq_kernel<L_, M_, R_, P_><<<(unsigned)(F->ntiles * split), 32, 0, c->stream>>>(F->REC->p, F->OUT->p, o, reinterpret_cast<int *>(flag->p), F->n, F->np, F->npo, split); \
+        auto kern = bps_rq_kernel<L_, M_, R_, P_>;                                                                         \
+        const size_t smem = RqRings<L_, M_, R_, P_>::BYTES;                                                                \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                \
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);        \
+        kern<<<(unsigned)F->ntiles, 32, smem, c->stream>>>(F->REC->p, F->OUT->p, o, reinterpret_cast<int *>(flag->p), F->n, F->np, F->npo); \
         rc = 0;                                                                                                            \
     }
         SSM_RQ_SHAPES(X)

@@ -247,7 +247,8 @@ struct GroupRing {
 // NW = 1: the ring belongs to one warp.  NW = 2: two warps of one CTA share it — each computes 16 of the tile's 32 systems (set
 // `col`), thread 0 issues the copies, and the slot is re-armed after a CTA barrier (kernels that are latency bound at one warp per
 // tile double their warps in flight this way without moving a byte more).  NST need not be a power of two.
-template <int NF, int NST, int NW = 1>
+// STRIDE: fields between consecutive records in global memory (> NF when only a field range of each record is wanted)
+template <int NF, int NST, int NW = 1, int STRIDE = NF>
 struct WindowRing {
     static constexpr uint32_t REC_BYTES = NF * 256;
     const double *g;      // tile base of record 0 of the sequence (not lane adjusted)
@@ -256,12 +257,12 @@ struct WindowRing {
     int col;              // lane column of the tile this thread reads
     bool issuer;
     int64_t nseq;
-    static __host__ __device__ size_t smem_bytes() { return (size_t)NST * REC_BYTES + (size_t)NST * 8; }
+    static constexpr __host__ __device__ size_t smem_bytes() { return (size_t)NST * REC_BYTES + (size_t)NST * 8; }
     __device__ __forceinline__ void issue(int64_t k) {
         const int s = (int)(k % NST);
         const uint32_t bar = bar0 + 8u * s;
         mbar_expect_tx(bar, REC_BYTES);
-        bulk_g2s(smem_u32(ring + (size_t)s * NF * 32), g + k * NF * 32, REC_BYTES, bar);
+        bulk_g2s(smem_u32(ring + (size_t)s * NF * 32), g + k * STRIDE * 32, REC_BYTES, bar);
     }
     __device__ __forceinline__ void sync() { if (NW == 1) __syncwarp(); else __syncthreads(); }
     __device__ __forceinline__ void init(const double *tile_first_record, void *smem, int64_t total) {
