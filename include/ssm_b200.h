@@ -96,6 +96,10 @@ int  ssm_ab_set_vcat(ssm_ab *A, const double *a, int64_t a_stride, const double 
  * A is not mutated (test_almostbanded.jl:146).  *F must be NULL (a new factor object is returned) or an
  * existing factor object of the same shape, which is overwritten (steady-state refactorisation).        */
 int  ssm_ab_qr(const ssm_ab *A, ssm_abqr **F);
+/* _almostbanded_qr!(A, tau, ncols) (:139-172): form only the first ncols reflectors (0 <= ncols <= n).  Rows and columns
+ * past ncols of F.factors hold the partially updated trailing matrix (widened band + updated fill U), tau[ncols+1:] = 0 —
+ * what adaptive / incremental callers continue from.  ssm_ab_qr(A, F) == ssm_ab_qr_cols(A, n - 1, F) (:137).            */
+int  ssm_ab_qr_cols(const ssm_ab *A, int ncols, ssm_abqr **F);
 int  ssm_abqr_destroy(ssm_abqr *F);
 /* F.factors (widened band storage (2l+u+1) x n), F.factors.fill U (n x r), F.tau (n) (:174-185)           */
 int  ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t f_stride, double *U, int64_t U_stride,

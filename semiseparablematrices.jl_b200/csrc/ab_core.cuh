@@ -67,7 +67,8 @@ SSM_HD void ab_prologue(AbState<L, U, R> &st, RecFn rec, VFn vcol, BFn bval) {
 
 // One column of the sweep.  PH = k mod (L+1) must be a compile-time constant at the call site (the caller
 // unrolls).  in_rec[f]: record of the entering row k+L;  in_v[q] = V[q, k+1+UB];  in_b = b[k+L].
-// act = (k < n-1): the reference forms n-1 reflectors for a real square matrix (:137), tau[n] = 0.
+// act = (k < ncols): the reference forms ncols = n-1 reflectors for a real square matrix (:137), tau[n] = 0; a caller of
+// _almostbanded_qr!(A, tau, ncols) may ask for fewer (partial factorisation) or for n.
 // Outputs: out_r[0..UB] = R[k, k..k+UB], out_r[UB+1+q] = Ufinal[k,q]; out_q[0..L-1] = v tail, out_q[L] = tau;
 //          out_c = (Q'b)[k].
 template <int L, int U, int R, bool RHS>
@@ -100,9 +101,9 @@ SSM_HD void ab_step(AbState<L, U, R> &st, const int PH, const double *in_rec, co
     const double xi1 = x0 + nu;
     const double inv_xi = nz ? fast_rcp(xi1) : 0.0;
     const double tau = nz ? xi1 * copysign(rs, x0) : 0.0;
-    double v[L > 0 ? L : 1];
+    double v[L > 0 ? L : 1], xraw[L > 0 ? L : 1];
 #pragma unroll
-    for (int i = 1; i <= L; ++i) v[i - 1] = st.A[(PH + i) % P][L - i] * inv_xi;
+    for (int i = 1; i <= L; ++i) { xraw[i - 1] = st.A[(PH + i) % P][L - i]; v[i - 1] = xraw[i - 1] * inv_xi; }
     st.A[s0][L] = nz ? -nu : x0;
     // (3) apply H = I - tau v v' to the live columns, to the U rows and to the right-hand side
 #pragma unroll
@@ -139,8 +140,10 @@ SSM_HD void ab_step(AbState<L, U, R> &st, const int PH, const double *in_rec, co
     for (int t = 0; t <= UB; ++t) out_r[t] = st.A[s0][t + L];
 #pragma unroll
     for (int q = 0; q < R; ++q) out_r[UB + 1 + q] = st.UC[s0][q];
+    // below the diagonal the factor storage holds v, or — for a column without a reflector (k >= ncols of a partial
+    // factorisation, or an exactly zero column) — the column itself, as _almostbanded_qr!(A, tau, ncols) leaves it
 #pragma unroll
-    for (int i = 1; i <= L; ++i) out_q[i - 1] = v[i - 1];
+    for (int i = 1; i <= L; ++i) out_q[i - 1] = nz ? v[i - 1] : xraw[i - 1];
     out_q[L] = tau;
     out_c = st.RH[s0];
     // (5) surviving rows gain column k+1+UB, which lies in their fill region

@@ -35,9 +35,11 @@ __device__ inline void generic_ab_qr(const AbArgs &a, int l, int u, int r, bool 
         double ssq = x0 * x0;
         for (int i = 1; i <= l; ++i) ssq = fma(W[i][0], W[i][0], ssq);
         const double nu = copysign(sqrt(ssq), x0), xi1 = x0 + nu;
-        const bool nz = (k < n - 1) && (ssq != 0.0);
+        const bool nz = (k < a.ncols) && (ssq != 0.0);
         const double inv_xi = nz ? 1.0 / xi1 : 0.0, tau = nz ? xi1 / nu : 0.0;
         for (int i = 1; i <= l; ++i) v[i - 1] = W[i][0] * inv_xi;
+        double tail[SSM_MAX_BW];      // what the factor storage holds below the diagonal: v, or the untouched column
+        for (int i = 1; i <= l; ++i) tail[i - 1] = nz ? v[i - 1] : W[i][0];
         W[0][0] = nz ? -nu : x0;
         for (int t = 1; t <= ub; ++t) {
             double s = W[0][t];
@@ -59,7 +61,7 @@ __device__ inline void generic_ab_qr(const AbArgs &a, int l, int u, int r, bool 
         }
         for (int t = 0; t <= ub; ++t) ru[((int64_t)k * nfr + t) * 32] = W[0][t];
         for (int q = 0; q < r; ++q) ru[((int64_t)k * nfr + ub + 1 + q) * 32] = UC[0][q];
-        if (store_q) { for (int i = 1; i <= l; ++i) qt[((int64_t)k * nfq + i - 1) * 32] = v[i - 1]; qt[((int64_t)k * nfq + l) * 32] = tau; }
+        if (store_q) { for (int i = 1; i <= l; ++i) qt[((int64_t)k * nfq + i - 1) * 32] = tail[i - 1]; qt[((int64_t)k * nfq + l) * 32] = tau; }
         if (with_rhs) rhs[(int64_t)k * 32] = RH[0];
         const int64_t c = (int64_t)k + 1 + ub;   // column gained by the surviving rows (fill region)
         for (int i = 1; i <= l; ++i) {

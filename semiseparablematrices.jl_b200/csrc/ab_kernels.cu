@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(32) ab_qr_kernel(const AbArgs a, const int nst
             double rec[NFA], vc[R > 0 ? R : 1], bb[1];
             ld.acquire(k, rec, vc, bb);
             double out_r[NFR], out_q[NFQ], out_c;
-            ab_step<L, U, R, RHS>(st, ph, rec, vc, bb[0], k < n - 1, out_r, out_q, out_c);
+            ab_step<L, U, R, RHS>(st, ph, rec, vc, bb[0], k < a.ncols, out_r, out_q, out_c);
             if (k < n) {
 #pragma unroll
                 for (int f = 0; f < NFR; ++f) ru[((int64_t)k * NFR + f) * 32] = out_r[f];
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(64) ab_qr_group_kernel(const AbArgs a, const i
             double rec[NFA], vc[R > 0 ? R : 1], bb[1];
             ld.read(ph, rec, vc, bb);
             double out_r[NFR], out_q[NFQ], out_c;
-            ab_step<L, U, R, RHS>(st, ph, rec, vc, bb[0], k < n - 1, out_r, out_q, out_c);
+            ab_step<L, U, R, RHS>(st, ph, rec, vc, bb[0], k < a.ncols, out_r, out_q, out_c);
             if (k < n) {
 #pragma unroll
                 for (int f = 0; f < NFR; ++f) ru[((int64_t)k * NFR + f) * 32] = out_r[f];

@@ -347,8 +347,9 @@ static int abqr_alloc(const ssm_ab *A, bool with_q, ssm_abqr **out) {
     return 0;
 }
 
-int ssm_ab_qr(const ssm_ab *A, ssm_abqr **out) {
+int ssm_ab_qr_cols(const ssm_ab *A, int ncols, ssm_abqr **out) {
     SSM_CHECK_ARG(A && out, "null argument");
+    if (ncols < 0 || ncols > A->n) { set_error("ssm_ab_qr_cols: ncols = %d outside 0..n = %d", ncols, A->n); return SSM_E_ARG; }
     ssm_ctx *c = A->ctx;
     DeviceGuard g(c->device);
     ssm_abqr *F = *out;
@@ -358,11 +359,16 @@ int ssm_ab_qr(const ssm_ab *A, ssm_abqr **out) {
     } else {
         SSM_TRY(abqr_alloc(A, true, &F));
     }
-    AbArgs a{A->AU->p, A->V->p, F->RU->p, F->QT->p, nullptr, nullptr, A->n, A->np};
+    AbArgs a{A->AU->p, A->V->p, F->RU->p, F->QT->p, nullptr, nullptr, A->n, A->np, ncols};
     int rc = launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, false, true);
     if (rc) { if (!*out) delete F; return rc; }
+    F->ncols = ncols;
     *out = F;
     return 0;
+}
+int ssm_ab_qr(const ssm_ab *A, ssm_abqr **out) {
+    SSM_CHECK_ARG(A && out, "null argument");
+    return ssm_ab_qr_cols(A, A->n - 1, out);     // min(m - 1, n) for a real square matrix (:137)
 }
 int ssm_abqr_destroy(ssm_abqr *F) { if (F) { cudaStreamSynchronize(F->ctx->stream); delete F; } return 0; }
 
@@ -439,7 +445,7 @@ int ssm_ab_solve(const ssm_ab *A, const ssm_vec *b, ssm_vec *x) {
     // R round-trips through HBM (the back-substitution runs against the sweep); reflectors are not kept.
     if (!A->scratch) SSM_TRY(dev_alloc(c->device, (size_t)(A->ntiles * A->np * (A->l + A->u + 1 + A->r) * 32), true, c->stream, A->scratch));
     DevBufPtr RU = A->scratch;
-    AbArgs a{A->AU->p, A->V->p, RU->p, nullptr, b->d->p, x->d->p, A->n, A->np};
+    AbArgs a{A->AU->p, A->V->p, RU->p, nullptr, b->d->p, x->d->p, A->n, A->np, A->n - 1};
     SSM_TRY(launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, true, false));
     AbSolveArgs s{RU->p, nullptr, A->V->p, x->d->p, x->d->p, A->n, A->np, 0};
     return launch_ab_backsolve(c, A->l, A->u, A->r, A->ntiles, s);

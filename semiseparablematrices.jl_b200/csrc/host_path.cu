@@ -86,7 +86,7 @@ extern "C" int ssm_ab_solve_host(ssm_ctx *c, int n, int l, int u, int r, int64_t
         const int64_t tiles = ntiles_of(cnt);
         if ((rc = launch_ab_pack(cx, A, sB, (int64_t)eb, sU, (int64_t)eu, sV, (int64_t)eu, 0, cnt))) break;
         if ((rc = launch_vec_pack(cx, v, sR, n, 0, cnt))) break;
-        AbArgs a{A->AU->p, A->V->p, hp->ru[slot]->p, nullptr, v->d->p, v->d->p, n, A->np};
+        AbArgs a{A->AU->p, A->V->p, hp->ru[slot]->p, nullptr, v->d->p, v->d->p, n, A->np, n - 1};
         if ((rc = launch_ab_qr(cx, l, u, r, tiles, a, true, false))) break;
         AbSolveArgs s{hp->ru[slot]->p, nullptr, A->V->p, v->d->p, v->d->p, n, A->np, 0};
         if ((rc = launch_ab_backsolve(cx, l, u, r, tiles, s))) break;

@@ -87,6 +87,7 @@ struct ssm_ab {
 
 struct ssm_abqr {
     ssm_ctx *ctx; int n, l, u, r; int64_t nb, ntiles, np;
+    int ncols = 0;              // reflectors formed (n-1 for qr(A); fewer after ssm_ab_qr_cols)
     ssm::DevBufPtr RU;          // [ntiles][np][l+u+1+r][32]   R[k, k .. k+ub], Ufinal[k, :]
     ssm::DevBufPtr QT;          // [ntiles][np][l+1][32]       reflector tail of column k, tau_k
     ssm::DevBufPtr V;           // shared with the operand batch (never written by the path)
@@ -132,6 +133,7 @@ struct AbArgs {
     const double *rhs_in;                    // b (may be null; may alias rhs)
     double *rhs;                             // out: Q'b
     int n; int64_t np;
+    int ncols;                               // reflectors formed: columns 0..ncols-1 (_almostbanded_qr!(A, tau, ncols), :137-139)
 };
 struct AbSolveArgs {
     const double *RU; const double *QT; const double *V;

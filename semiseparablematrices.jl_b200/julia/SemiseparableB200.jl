@@ -113,9 +113,9 @@ end
 
 # qr on the device, then F.factors / F.τ written straight into reference-layout storage:
 #   factors: (2l+u+1) x n band data with bandwidths (l, l+u); U: n x r (overwritten); τ: n
-function device_qr!(fdata::Matrix{Float64}, Uout::Matrix{Float64}, τ::Vector{Float64}, A::Handle)
+function device_qr!(fdata::Matrix{Float64}, Uout::Matrix{Float64}, τ::Vector{Float64}, A::Handle, ncols::Integer = size(fdata, 2) - 1)
     f = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:ssm_ab_qr, libssm), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), A.p, f))
+    check(ccall((:ssm_ab_qr_cols, libssm), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}), A.p, ncols, f))
     F = Handle(f[], :abqr)
     GC.@preserve fdata Uout τ check(ccall((:ssm_abqr_get, libssm), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64), F.p, pointer(fdata), 0, pointer(Uout), 0, pointer(τ), 0))
@@ -145,14 +145,17 @@ function _almostbanded_qr(_, A::DenseAB)
 end
 
 # in-place form (:135-172): A already widened to (l, l+u) by the caller, bands u+1..l+u hold the fill values
-function _almostbanded_qr!(A::DenseAB, τ::Vector{Float64})
+_almostbanded_qr!(A::DenseAB, τ::Vector{Float64}) = _almostbanded_qr!(A, τ, min(size(A, 1) - 1, size(A, 2)))   # :135-138
+
+# partial form (:139-172): only the first ncols reflectors; the trailing rows / columns come back partially updated
+function _almostbanded_qr!(A::DenseAB, τ::Vector{Float64}, ncols::Integer)
     B, L = bandpart(A), fillpart(A)
     l, ū = bandwidths(B)
     u = ū - l
-    (u >= 0 && size(A, 1) == size(A, 2)) || return invoke(_almostbanded_qr!, Tuple{AbstractMatrix{Float64},AbstractVector{Float64}}, A, τ)
+    (u >= 0 && size(A, 1) == size(A, 2)) || return invoke(_almostbanded_qr!, Tuple{AbstractMatrix,AbstractVector,Any}, A, τ, ncols)
     U, V = arguments(L)
     dA = upload(B.data[l+1:end, :], U, V, l, u)                   # rows of bands -l..u of the widened storage
-    dF = device_qr!(B.data, U, τ, dA)
+    dF = device_qr!(B.data, U, τ, dA, ncols)
     FACTORS[A] = (dA, dF)
     A, τ
 end

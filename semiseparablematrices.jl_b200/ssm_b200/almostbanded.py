@@ -320,15 +320,16 @@ class _UpperR:
 class AlmostBandedQR:
     """``QR{Float64,<:AlmostBandedMatrix}`` (:174-179): ``.factors`` (widened bands (l, l+u) + updated fill), ``.tau``."""
 
-    def __init__(self, A: AlmostBandedMatrix, handle=None):
+    def __init__(self, A: AlmostBandedMatrix, handle=None, ncols=None):
         self.ctx, self.n, self.l, self.u, self.r, self.nb, self.single = A.ctx, A.n, A.l, A.u, A.r, A.nb, A.single
         self._A = A      # V is shared with the operand batch
         self._h = handle if handle is not None else c_vp()
-        check(_lib.lib().ssm_ab_qr(A._h, C.byref(self._h)), "ssm_ab_qr")
+        self.ncols = A.n - 1 if ncols is None else int(ncols)      # min(m - 1, n) for a real square matrix (:137)
+        check(_lib.lib().ssm_ab_qr_cols(A._h, self.ncols, C.byref(self._h)), "ssm_ab_qr_cols")
 
     def refactor(self, A: AlmostBandedMatrix):
         """qr into the existing factor storage (no allocation): steady-state use and benchmarking."""
-        check(_lib.lib().ssm_ab_qr(A._h, C.byref(self._h)), "ssm_ab_qr")
+        check(_lib.lib().ssm_ab_qr_cols(A._h, self.ncols, C.byref(self._h)), "ssm_ab_qr_cols")
         self._A = A
         return self
 
@@ -402,9 +403,11 @@ class AlmostBandedQR:
             pass
 
 
-def qr(A: AlmostBandedMatrix) -> AlmostBandedQR:
-    """``qr(A)`` / ``factorize(A)`` (:125-133).  ``A`` is not mutated (test_almostbanded.jl:146)."""
-    return AlmostBandedQR(A)
+def qr(A: AlmostBandedMatrix, ncols=None) -> AlmostBandedQR:
+    """``qr(A)`` / ``factorize(A)`` (:125-133).  ``A`` is not mutated (test_almostbanded.jl:146).
+    ``ncols``: ``_almostbanded_qr!(A, tau, ncols)`` (:139-172) — only the first ``ncols`` reflectors; the rest of ``factors`` is
+    the partially updated trailing matrix."""
+    return AlmostBandedQR(A, ncols=ncols)
 
 
 factorize = qr

@@ -110,6 +110,38 @@ def test_qr_factors_and_solves_match_oracle(ssm, ctx, variant, l, u, r):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+def test_partial_qr_cols(ssm, ctx, variant):
+    """_almostbanded_qr!(A, tau, ncols) (:139-172): only the first ncols reflectors; the rest of factors is the partially updated
+    trailing matrix.  Factors, updated U and tau against the oracle for ncols inside a block, at a block edge, n-1 and n."""
+    with_variant(ctx, variant)
+    rng = np.random.default_rng(23)
+    for (n, l, u, r) in [(40, 2, 2, 2), (33, 1, 0, 1), (37, 4, 4, 2), (29, 3, 1, 3)]:
+        if (l, u, r) == (3, 1, 3) and variant != 9:
+            continue
+        nb = 37
+        bands, U, V, b = randn_system(rng, n, l, u, r, nb)
+        A = ssm.AlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
+        for ncols in sorted({1, 2, l + u + 1, l + u + 2, n // 2, n - 1, n}):
+            gF, gU, gtau = ssm.qr(A, ncols=ncols).get()
+            for s in range(0, nb, 6):
+                oF, oU, otau = oracle.ab_qr(bands[s], U[s], V[s], l, u, ncols=ncols)
+                scale = max(1.0, np.abs(oF).max())
+                assert np.abs(gF[s] - oF).max() <= 1e-12 * scale, (n, l, u, r, ncols, s)
+                assert np.abs(gU[s] - oU).max() <= 1e-12 * max(1.0, np.abs(oU).max())
+                assert np.abs(gtau[s] - otau).max() <= 1e-13 and np.all(gtau[s][ncols:] == 0.0)
+        # ncols = 0: nothing is factored; factors is the widened copy of A (:30-38), bit for bit
+        gF, gU, gtau = ssm.qr(A, ncols=0).get()
+        assert np.array_equal(gU, U) and not gtau.any()
+        for s in (0, nb - 1):
+            W = oracle.storage_to_dense(gF[s], l, l + u)
+            Ad = oracle.ab_dense(bands[s], U[s], V[s], l, u)
+            band = np.triu(np.tril(np.ones((n, n)), l + u), -l).astype(bool)
+            assert np.abs(W[band] - Ad[band]).max() <= 1e-15 * np.abs(Ad).max()
+    with pytest.raises(Exception):
+        ssm.qr(A, ncols=A.n + 1)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_dense_lapack_parity_on_randn(ssm, ctx, variant):
     """As the reference's tests do: compare with dense LinearAlgebra on randn data (test_almostbanded.jl:153)."""
     with_variant(ctx, variant)

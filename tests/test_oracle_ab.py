@@ -108,6 +108,49 @@ def test_one_column_qr():
     assert np.allclose(np.triu(QtA), np.triu(oracle.storage_to_dense(F, 1, 2)), atol=1e-14)
 
 
+def _dense_partial_householder(A, ncols):
+    """H_ncols ... H_1 A with LinearAlgebra.reflector! reflectors, and their tau."""
+    M = A.copy(); n = M.shape[0]; tau = np.zeros(n)
+    for k in range(ncols):
+        x = M[k:, k].copy()
+        nrm = np.linalg.norm(x)
+        if nrm == 0.0:
+            continue
+        nu = math.copysign(nrm, x[0]); v = x / (x[0] + nu); v[0] = 1.0; t = (x[0] + nu) / nu
+        M[k:, :] -= t * np.outer(v, v @ M[k:, :])
+        tau[k] = t
+    return M, tau
+
+
+def partial_factors_dense(F, Uf, V, l, u, ncols):
+    """The matrix a partially factored AlmostBandedMatrix stands for: R rows / trailing block from the widened band storage, fill Uf*V
+    beyond it, zeros below the diagonal of the ncols factored columns (the storage holds the reflector tails there)."""
+    n = F.shape[0]; ub = l + u
+    M = oracle.storage_to_dense(F, l, ub)
+    fill = Uf.T @ V.T if Uf.size else np.zeros((n, n))      # U is stored (r, n), V (n, r): column-major n x r and r x n
+    for k in range(n):
+        M[k, k + ub + 1:] = fill[k, k + ub + 1:]
+    for j in range(min(ncols, n)):
+        M[j + 1:, j] = 0.0
+    return M
+
+
+def test_partial_qr_matches_dense_householder():
+    """_almostbanded_qr!(A, tau, ncols) (:139-172) for every kind of ncols: inside a block, at a block edge, n-1 (the default), n."""
+    rng = np.random.default_rng(17)
+    for (n, l, u, r) in [(24, 2, 2, 2), (17, 1, 0, 1), (30, 4, 4, 2), (21, 3, 1, 3), (12, 0, 2, 1)]:
+        bands, U, V, _ = randn_system(rng, n, l, u, r)
+        A = oracle.ab_dense(bands, U, V, l, u)
+        for ncols in sorted({1, 2, l + u + 1, l + u + 2, n // 2, n - 1, n}):
+            F, Uf, tau = oracle.ab_qr(bands, U, V, l, u, ncols=ncols)
+            M, t = _dense_partial_householder(A, ncols)
+            if l == 0:            # reference quirk (SURVEY 8a): length-1 reflectors give tau = 2 and a negated row
+                assert np.allclose(tau[:ncols], 2.0) and np.all(tau[ncols:] == 0.0)
+                continue
+            assert np.abs(partial_factors_dense(F, Uf, V, l, u, ncols) - M).max() <= 1e-12 * np.abs(A).max(), (n, l, u, r, ncols)
+            assert np.abs(tau - t).max() <= 1e-13 and np.all(tau[ncols:] == 0.0)
+
+
 def test_generator_is_well_conditioned_and_deterministic():
     bands, U, V, b = oracle.ab_generate(64, 2, 2, 2, 3, seed=20261020)
     b2 = oracle.ab_generate(64, 2, 2, 2, 1, seed=20261020, s0=2)
