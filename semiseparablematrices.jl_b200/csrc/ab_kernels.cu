@@ -313,7 +313,7 @@ static int launch1(ssm_ctx *c, K kern, int64_t ntiles, size_t smem, const char *
 
 // GroupRing geometry for a grid of ntiles CTAs: as many stages of gm blocks as the shared memory left per CTA holds; returns
 // false when not even two single-block stages fit (the caller then keeps the per-step ring).
-static bool pick_group(const ssm_ctx *c, size_t block_bytes, int64_t ntiles, int *nstage, int *gm) {
+bool pick_group(const ssm_ctx *c, size_t block_bytes, int64_t ntiles, int *nstage, int *gm) {
     int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
     if (per_sm < 1) per_sm = 1;
     const size_t budget = (size_t)(200 * 1024) / (size_t)per_sm;

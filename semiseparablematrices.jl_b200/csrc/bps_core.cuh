@@ -19,6 +19,7 @@
 // Row records (all 0 outside the matrix):  field 0..L+M : B0[rho, rho-L+d];  then U[rho,0..R), V[rho,0..R),
 // W[rho,0..P), S[rho,0..P).   row(rel, f) returns field f of row q+rel, rel in [-M, L].
 #pragma once
+#include "fastmath.cuh"
 #include <cmath>
 
 #if defined(__CUDACC__)
@@ -495,27 +496,34 @@ SSM_HD double bps_qt_step(BpsQtState<L, R> &st, URowFn urow, const double *vq, c
 
 // ---- ldiv!(UpperTriangular{BPS}, b) (BandedPlusSemiseparableMatrix.jl:53-70), rows n-1 .. 0 -----------------
 // PW = p + r columns of W/S in the factor; MW = upper bandwidth of the factor's B (= L + M for QR factors).
+// The serial chain of the recurrence is kept to one FMA and one multiply per row: the W'S coupling with the newest solution
+// entry x[j+1] is folded into its band coefficient (sx lags one row behind: sx = sum_{k >= j+2} S[k,:] x[k], sprev = S[j+1,:]),
+// everything else of row j is accumulated before x[j+1] is needed, and 1 / B[j,j] is formed off the chain (fastmath.cuh).
 template <int MW, int PW>
-struct BpsBsState { double xw[MW > 0 ? MW : 1]; double sx[PW]; };   // xw[t] = x[j+1+t]
+struct BpsBsState { double xw[MW > 0 ? MW : 1]; double sx[PW]; double sprev[PW]; };   // xw[t] = x[j+1+t]
 
 template <int MW, int PW>
 SSM_HD void bps_bs_init(BpsBsState<MW, PW> &st) {
 #pragma unroll
     for (int t = 0; t < MW; ++t) st.xw[t] = 0.0;
 #pragma unroll
-    for (int c = 0; c < PW; ++c) st.sx[c] = 0.0;
+    for (int c = 0; c < PW; ++c) { st.sx[c] = 0.0; st.sprev[c] = 0.0; }
 }
 // d[0] = B[j,j], d[t] = B[j,j+t] (t = 1..MW); w[c] = W[j,c]; s[c] = S[j,c]; c_in = rhs[j]
 template <int MW, int PW>
 SSM_HD double bps_bs_step(BpsBsState<MW, PW> &st, const double *d, const double *w, const double *s, const double c_in) {
+    const double rinv = fast_rcp(d[0]);                                       // :64, off the chain
+    const double xnew = MW > 0 ? st.xw[0] : 0.0;                              // x[j+1], the newest entry
+    double coef = MW > 0 ? d[MW > 0 ? 1 : 0] : 0.0;                           // B[j,j+1] + W[j,:]'S[j+1,:]
     double acc = c_in;
 #pragma unroll
-    for (int c = 0; c < PW; ++c) acc = fma(-w[c], st.sx[c], acc);            // residual = W[j,:]'sx   (:60)
+    for (int c = 0; c < PW; ++c) { acc = fma(-w[c], st.sx[c], acc); coef = fma(w[c], st.sprev[c], coef); }   // W[j,:]'sx  (:60)
 #pragma unroll
-    for (int t = MW; t >= 1; --t) acc = fma(-d[t], st.xw[t - 1], acc);        // + sum B[j,k] b[k]      (:61-63)
-    const double x = acc / d[0];                                              // :64
+    for (int t = MW; t >= 2; --t) acc = fma(-d[t], st.xw[t - 1], acc);        // + sum B[j,k] b[k]      (:61-63)
+    acc = fma(-coef, xnew, acc);
+    const double x = acc * rinv;
 #pragma unroll
-    for (int c = 0; c < PW; ++c) st.sx[c] = fma(s[c], x, st.sx[c]);           // sx += S[j,:] b[j]      (:66)
+    for (int c = 0; c < PW; ++c) { st.sx[c] = fma(st.sprev[c], xnew, st.sx[c]); st.sprev[c] = s[c]; }   // sx += S[j+1,:] b[j+1]  (:66)
 #pragma unroll
     for (int t = MW - 1; t >= 1; --t) st.xw[t] = st.xw[t - 1];
     if (MW > 0) st.xw[0] = x;

@@ -188,6 +188,95 @@ __global__ void __launch_bounds__(32) bps_bs_kernel(const double *REC, const dou
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K7 / K8 for small batches: the same steps fed by a GroupRing (stream_loader.cuh) — a producer warp issues the copies, the
+// consumer waits once per group of rows instead of once per row.
+// ---------------------------------------------------------------------------------------------------------
+template <int L, int M, int R, int P>
+__global__ void __launch_bounds__(64) bps_qt_group_kernel(const double *REC, const double *OUT, const double *GT, const double *TT,
+                                                          const double *rhs_in, double *rhs, int n, int64_t np, int64_t npo, int64_t npv, int nstage, int gm) {
+    using D = BpsDims<L, M, R, P>;
+    using Ring = GroupRing<R, D::NFQ, 1, +1, 1, D::NFA, D::NFO, 1>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    const double *urec_t = REC + ((tile * np + BPS_FRONT) * D::NFA + D::FU) * 32;   // U fields of row 0
+    const double *qrec_t = OUT + (tile * npo * D::NFO + D::OB) * 32;                 // Q part of row 0
+    const double *rin_t = rhs_in + tile * npv * 32;
+    Ring::init_barriers(smem, nstage, gm, 1);
+    if (warp == 1) {
+        if (lane == 0) Ring::produce(urec_t + (int64_t)L * D::NFA * 32, qrec_t, rin_t + (int64_t)L * 32, smem, nstage, gm, n);
+        return;
+    }
+    const double *urec = urec_t + lane, *rin = rin_t + lane;
+    double *ro = rhs + tile * npv * 32 + lane;
+    double gt[R * R], tt[R];
+#pragma unroll
+    for (int e = 0; e < R * R; ++e) gt[e] = __ldg(GT + (tile * (R * R) + e) * 32 + lane);
+#pragma unroll
+    for (int a = 0; a < R; ++a) tt[a] = TT[(tile * R + a) * 32 + lane];
+    double uw[L + 1][R];                                   // U rows q .. q+L
+#pragma unroll
+    for (int s = 0; s < L; ++s)
+#pragma unroll
+        for (int a = 0; a < R; ++a) uw[s][a] = __ldg(urec + ((int64_t)s * D::NFA + a) * 32);
+    BpsQtState<L, R> st;
+    bps_qt_init<L, R>(st, gt, tt, [&](int row, int a) { return uw[row][a]; }, [&](int row) { return rin[(int64_t)row * 32]; });
+    Ring ld;
+    ld.attach(smem, nstage, gm, n, lane);
+    for (int q = 0; q < n; ++q) {
+        double un[R], qq[D::NFQ], bb[1];
+        ld.block_begin();
+        ld.read(0, un, qq, bb);
+        ld.block_end();
+#pragma unroll
+        for (int a = 0; a < R; ++a) uw[L][a] = un[a];
+        const double c = bps_qt_step<L, R>(st, [&](int rel, int a) { return uw[rel][a]; }, qq + D::OV, qq + D::OB, qq[D::OT], bb[0], q == n - 1);
+        ro[(int64_t)q * 32] = c;
+#pragma unroll
+        for (int s = 0; s < L; ++s)
+#pragma unroll
+            for (int a = 0; a < R; ++a) uw[s][a] = uw[s + 1][a];
+    }
+}
+
+template <int L, int M, int R, int P>
+__global__ void __launch_bounds__(64) bps_bs_group_kernel(const double *REC, const double *OUT, const double *rhs_in, double *rhs, int n,
+                                                          int64_t np, int64_t npo, int64_t npv, int nstage, int gm) {
+    using D = BpsDims<L, M, R, P>;
+    constexpr int LM = L + M, PW = P + R;
+    using Ring = GroupRing<D::NFRP, P, 1, -1, 1, D::NFO, D::NFA, 1>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    const double *srec_t = REC + ((tile * np + BPS_FRONT + (n - 1)) * D::NFA + D::FS) * 32;     // S fields of row n-1
+    const double *rrec_t = OUT + ((tile * npo + (n - 1)) * D::NFO + D::OD) * 32;                // R part of row n-1
+    const double *rin_t = rhs_in + (tile * npv + (n - 1)) * 32;
+    Ring::init_barriers(smem, nstage, gm, 1);
+    if (warp == 1) {
+        if (lane == 0) Ring::produce(rrec_t, srec_t, rin_t, smem, nstage, gm, n);
+        return;
+    }
+    double *ro = rhs + tile * npv * 32 + lane;
+    BpsBsState<LM, PW> st;
+    bps_bs_init<LM, PW>(st);
+    Ring ld;
+    ld.attach(smem, nstage, gm, n, lane);
+    for (int g = 0; g < n; ++g) {
+        const int j = n - 1 - g;
+        double rp[D::NFRP], sp[P], cc[1], sfull[PW];
+        ld.block_begin();
+        ld.read(0, rp, sp, cc);
+        ld.block_end();
+#pragma unroll
+        for (int c = 0; c < P; ++c) sfull[c] = sp[c];
+#pragma unroll
+        for (int a = 0; a < R; ++a) sfull[P + a] = rp[LM + 1 + P + R + a];
+        const double x = bps_bs_step<LM, PW>(st, rp, rp + LM + 1, sfull, cc[0]);
+        ro[(int64_t)j * 32] = x;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // boundary kernels (runtime dims = the padded kernel shape): thread = (tile, row, lane)
 // ---------------------------------------------------------------------------------------------------------
 struct BpsShape { int n, l, m, r, p, tl, tm, tr, tp; };
@@ -449,6 +538,20 @@ static int qt_shape(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double
     using D = BpsDims<L, M, R, P>;
     bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)F->ntiles, 128, 0, c->stream>>>(F->REC->p, rhs_in, nullptr, F->TT->p, F->n, F->np, npv);
     c->launches++;
+    if ((c->ab_variant == 0 && F->ntiles <= (int64_t)c->sm_count * c->group_max_per_sm) || c->ab_variant == 4) {
+        using RG = GroupRing<R, D::NFQ, 1, +1, 1, D::NFA, D::NFO, 1>;
+        int ns, gm;
+        if (pick_group(c, RG::BLOCK_BYTES, F->ntiles, &ns, &gm)) {
+            const size_t smem = RG::smem_bytes(ns, gm);
+            auto kern = bps_qt_group_kernel<L, M, R, P>;
+            if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            kern<<<(unsigned)F->ntiles, 64, smem, c->stream>>>(F->REC->p, F->OUT->p, F->GT->p, F->TT->p, rhs_in, rhs, F->n, F->np, F->npo, npv, ns, gm);
+            c->launches++;
+            SSM_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     if (c->ab_variant == 1) {
         bps_qt_kernel<L, M, R, P, DirectLoader><<<(unsigned)F->ntiles, 32, 0, c->stream>>>(F->REC->p, F->OUT->p, F->GT->p, F->TT->p, rhs_in, rhs, F->n,
                                                                                            F->np, F->npo, npv, 0);
@@ -467,6 +570,20 @@ static int qt_shape(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double
 template <int L, int M, int R, int P>
 static int bs_shape(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs, int64_t npv) {
     using D = BpsDims<L, M, R, P>;
+    if ((c->ab_variant == 0 && F->ntiles <= (int64_t)c->sm_count * c->group_max_per_sm) || c->ab_variant == 4) {
+        using RG = GroupRing<D::NFRP, P, 1, -1, 1, D::NFO, D::NFA, 1>;
+        int ns, gm;
+        if (pick_group(c, RG::BLOCK_BYTES, F->ntiles, &ns, &gm)) {
+            const size_t smem = RG::smem_bytes(ns, gm);
+            auto kern = bps_bs_group_kernel<L, M, R, P>;
+            if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            kern<<<(unsigned)F->ntiles, 64, smem, c->stream>>>(F->REC->p, F->OUT->p, rhs_in, rhs, F->n, F->np, F->npo, npv, ns, gm);
+            c->launches++;
+            SSM_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     if (c->ab_variant == 1) {
         bps_bs_kernel<L, M, R, P, DirectLoader><<<(unsigned)F->ntiles, 32, 0, c->stream>>>(F->REC->p, F->OUT->p, rhs_in, rhs, F->n, F->np, F->npo, npv, 0);
     } else {

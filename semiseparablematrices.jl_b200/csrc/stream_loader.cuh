@@ -161,7 +161,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int NF0, int NF1, int NF2, int DIR, int P>
+// STRs > NFs: stream s is a field range of wider records (STRs fields apart); its rows are then copied one by one (still by the
+// producer, still one mbarrier wait per group for the consumer).
+template <int NF0, int NF1, int NF2, int DIR, int P, int STR0 = NF0, int STR1 = NF1, int STR2 = NF2>
 struct GroupRing {
     static constexpr int RECD = (NF0 + NF1 + NF2) * 32;                 // doubles per step
     static constexpr size_t BLOCK_BYTES = (size_t)P * RECD * 8;
@@ -175,6 +177,14 @@ struct GroupRing {
             fence_barrier_init();
         }
         __syncthreads();
+    }
+    template <int NF, int STR>
+    static __device__ __forceinline__ void copy_stream(double *dst, const double *g, int64_t lo, int rows, uint32_t bar) {
+        if constexpr (NF > 0 && STR == NF) {
+            bulk_g2s(smem_u32(dst), g + lo * NF * 32, (uint32_t)rows * NF * 256u, bar);
+        } else if constexpr (NF > 0) {
+            for (int r = 0; r < rows; ++r) bulk_g2s(smem_u32(dst + (size_t)r * NF * 32), g + (lo + r) * STR * 32, NF * 256u, bar);
+        }
     }
     // producer thread: g0..g2 = tile base (not lane adjusted) of the record step 0 reads from each stream
     static __device__ __forceinline__ void produce(const double *g0, const double *g1, const double *g2, void *smem, int nstage,
@@ -191,9 +201,9 @@ struct GroupRing {
             const uint32_t bar = bars + 16u * s;
             double *dst = ring + (size_t)s * G * RECD;
             mbar_expect_tx(bar, (uint32_t)rows * RECD * 8u);
-            if (NF0 > 0) bulk_g2s(smem_u32(dst), g0 + lo * NF0 * 32, (uint32_t)rows * NF0 * 256u, bar);
-            if (NF1 > 0) bulk_g2s(smem_u32(dst + (size_t)G * NF0 * 32), g1 + lo * NF1 * 32, (uint32_t)rows * NF1 * 256u, bar);
-            if (NF2 > 0) bulk_g2s(smem_u32(dst + (size_t)G * (NF0 + NF1) * 32), g2 + lo * NF2 * 32, (uint32_t)rows * NF2 * 256u, bar);
+            copy_stream<NF0, STR0>(dst, g0, lo, rows, bar);
+            copy_stream<NF1, STR1>(dst + (size_t)G * NF0 * 32, g1, lo, rows, bar);
+            copy_stream<NF2, STR2>(dst + (size_t)G * (NF0 + NF1) * 32, g2, lo, rows, bar);
             if (++s == nstage) { s = 0; ++use; }
         }
     }
