@@ -202,10 +202,13 @@ SSM_HD void bps_step(BpsState<L, M, R, P> &st, RowFn row, const bool last, doubl
 #pragma unroll
     for (int t = 0; t < L; ++t) len2 = fma(b[t], b[t], len2);
     // reflector (:359-362).  copysign == -sign(pivot) of the reference whenever pivot != 0.
-    const double nu = copysign(sqrt(len2), pivot);
+    // Branch-free reciprocal square root / reciprocal (fastmath.cuh, ~1 ulp): sqrt + two IEEE divides are ~220 cycles of this
+    // step's serial chain on B200, the seed + Newton forms ~135, and without slow-path branches the compiler overlaps them.
+    const double rs = fast_rsqrt(len2);
+    const double nu = copysign(fast_sqrt_from_rsqrt(len2, rs), pivot);
     const double den = pivot + nu;
-    const double inv = 1.0 / den;
-    const double tau = den / nu;
+    const double inv = fast_rcp(den);
+    const double tau = den * copysign(rs, pivot);
 #pragma unroll
     for (int a = 0; a < R; ++a) { kb[a] *= inv; Ubtb[a] *= inv; G2k[a] *= inv; }
 #pragma unroll

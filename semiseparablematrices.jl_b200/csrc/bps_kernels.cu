@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(128) bps_reduce_kernel(const double *REC, cons
 // ---------------------------------------------------------------------------------------------------------
 // K6: QR sweep
 // ---------------------------------------------------------------------------------------------------------
-constexpr int BPS_NST = 16;   // window ring depth: M rows back + L rows ahead + look-ahead
+// Window ring depth of the one-warp-per-tile sweep: the M + L + 1 rows a step reads plus ONE slot in flight.  Shared memory per
+// CTA decides how many warps an SM holds (16 slots = 61 KB = 3 CTAs, 8 slots = 30.7 KB = 7 CTAs), and with 7 warps to switch
+// between deeper prefetch buys nothing: 131,072 systems 41.3 -> 27.7 ms (55 -> 80 % of the HBM peak) on B200.
+constexpr int bps_nst(int l, int m) { return l + m + 2; }
 
 // SPLIT = 1: one warp per tile of 32 systems.  SPLIT = 2: a CTA of two warps per tile, each warp owning 16 systems (lanes 16-31
 // shadow lanes 0-15 and do not store), both reading one shared window ring: the sweep is latency bound — a batch of 16,384 systems
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, c
     const int64_t tile = blockIdx.x;
     const int sl = SPLIT == 1 ? lane : (lane & 15) + 16 * (int)(threadIdx.x >> 5);    // system column of the tile this thread computes
     const bool writer = SPLIT == 1 || lane < 16;
-    WindowRing<D::NFA, SPLIT == 1 ? BPS_NST : BPS_NST_SPLIT, SPLIT> win;
+    WindowRing<D::NFA, SPLIT == 1 ? bps_nst(L, M) : BPS_NST_SPLIT, SPLIT> win;
     // sequence index k <-> row k - M; record of row rho sits at BPS_FRONT + rho
     win.init(REC + (tile * np + BPS_FRONT - M) * D::NFA * 32, smem, (int64_t)n + L + M);
     win.col = sl;
@@ -100,16 +103,24 @@ __global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, c
     BpsState<L, M, R, P> st;
     bps_init<L, M, R, P>(st, gt);
     double *out = OUT + tile * npo * D::NFO * 32 + sl;
+    constexpr int NST = SPLIT == 1 ? bps_nst(L, M) : BPS_NST_SPLIT;
     for (int k = 0; k < L + M; ++k) win.wait(k);          // rows -M .. L-1
+    int s0 = 0, sw = (L + M) % NST;                        // slots of sequence records q (row q-M) and q+L+M (row q+L)
+    uint32_t pw = ((L + M) / NST) & 1;
     for (int q = 0; q < n; ++q) {
-        win.wait((int64_t)q + L + M);                      // row q+L
+        win.wait_slot(sw, pw);                             // row q+L
+        const double *rp[L + M + 1];                       // window rows q-M .. q+L
+#pragma unroll
+        for (int t = 0; t <= L + M; ++t) { int sl = s0 + t; if (sl >= NST) sl -= NST; rp[t] = win.slot_ptr(sl); }
         double o[D::NFO];
-        bps_step<L, M, R, P>(st, [&](int rel, int f) { return win.rec((int64_t)q + rel + M)[f * 32]; }, q == n - 1, o);
+        bps_step<L, M, R, P>(st, [&](int rel, int f) { return rp[rel + M][f * 32]; }, q == n - 1, o);
         if (writer) {
 #pragma unroll
             for (int f = 0; f < D::NFO; ++f) out[((int64_t)q * D::NFO + f) * 32] = o[f];
         }
-        win.release(q);                                    // row q-M leaves the window
+        win.release_slot(q, s0);                           // row q-M leaves the window
+        if (++s0 == NST) s0 = 0;
+        if (++sw == NST) { sw = 0; pw ^= 1u; }
     }
 }
 
@@ -467,18 +478,26 @@ __global__ void __launch_bounds__(64) bps_qr_pair_kernel(const double *REC, cons
     __syncthreads();
     for (int k = 0; k < L + M; ++k) win.wait(k);          // rows -M .. L-1
     // one column; PARC::value = parity of the band-wide columns this warp owns at this step = (h + q) & 1
+    constexpr int NST = BPS_NST_SPLIT;
+    int s0 = 0, sw = (L + M) % NST;                        // slots of sequence records q (row q-M) and q+L+M (row q+L)
+    uint32_t pw = ((L + M) / NST) & 1;
     auto step = [&](auto parc, const int q) {
         constexpr int PAR = decltype(parc)::value;
-        win.wait((int64_t)q + L + M);                      // row q+L
+        win.wait_slot(sw, pw);                             // row q+L
+        const double *rp[L + M + 1];                       // window rows q-M .. q+L
+#pragma unroll
+        for (int t = 0; t <= L + M; ++t) { int sl = s0 + t; if (sl >= NST) sl -= NST; rp[t] = win.slot_ptr(sl); }
         double o[D::NFO];
-        bps_step<L, M, R, P, PAR>(st, [&](int rel, int f) { return win.rec((int64_t)q + rel + M)[f * 32]; }, q == n - 1, o, xch);
+        bps_step<L, M, R, P, PAR>(st, [&](int rel, int f) { return rp[rel + M][f * 32]; }, q == n - 1, o, xch);
 #pragma unroll
         for (int f = 0; f < D::NFO; ++f) {
             const bool band = f > D::OD && f <= D::OD + L + M;                       // R[q, q+t], t >= 1: written by the column's owner
             const bool mine = band ? (((f - D::OD) & 1) == PAR) : (h == 0);
             if (mine) out[((int64_t)q * D::NFO + f) * 32] = o[f];
         }
-        win.release(q);                                    // row q-M leaves the window
+        win.release_slot(q, s0);                           // row q-M leaves the window
+        if (++s0 == NST) s0 = 0;
+        if (++sw == NST) { sw = 0; pw ^= 1u; }
     };
     int q = 0;
     if (h == 1) { step(std::integral_constant<int, 1>{}, 0); q = 1; }
@@ -494,11 +513,15 @@ static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
     using D = BpsDims<L, M, R, P>;
     bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)A->ntiles, 128, 0, c->stream>>>(A->REC->p, nullptr, F->GT->p, nullptr, A->n, A->np, 0);
     c->launches++;
-    // split tiles over two warps while the batch cannot give every warp scheduler ~2 warps (ab_variant 1 / 2 force off / on)
-    // ab_variant: 0 auto, 1 one warp per tile, 2 two warps of 16 systems, 3 pair mode.  Measured at config 3 (512 tiles): 8.07 / 5.81 /
-    // 5.14 ms; at 2,048 tiles one warp per tile and pair mode tie (20.9 / 20.6 ms), so pair mode is the default below 16 tiles per SM.
+    // ab_variant: 0 auto, 1 one warp per tile, 2 two warps of 16 systems, 3 pair mode.  Measured on B200 (n = 4096, (3,3,2,2)):
+    //   systems    4,096   8,192   12,288   16,384 (config 3)   32,768   65,536
+    //   1 warp     4.28    4.29    4.33     4.45                6.65     13.7  ms
+    //   pair       3.81    3.84    4.98     4.99                9.77     19.7  ms
+    // A warp alone on its scheduler is bound by the step's serial chain (pair mode shortens it); from two warps per scheduler on,
+    // occupancy wins — the 8-slot window ring (30.7 KB) keeps 7 single-warp CTAs per SM resident, pair CTAs are register-limited
+    // to 4.  So pair mode only while its two warps per tile still find a scheduler each: at most 2 tiles per SM.
     const bool split = c->ab_variant == 2;
-    const bool pair = c->ab_variant == 3 || (c->ab_variant == 0 && A->ntiles < (int64_t)c->sm_count * 16);
+    const bool pair = c->ab_variant == 3 || (c->ab_variant == 0 && A->ntiles <= (int64_t)c->sm_count * 2);
     if (pair) {
         const size_t smem = WindowRing<D::NFA, BPS_NST_SPLIT, 2>::smem_bytes();
         auto kern = bps_qr_pair_kernel<L, M, R, P>;
@@ -510,7 +533,7 @@ static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
         SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)A->ntiles, 64, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
     } else {
-        const size_t smem = WindowRing<D::NFA, BPS_NST, 1>::smem_bytes();
+        const size_t smem = WindowRing<D::NFA, bps_nst(L, M), 1>::smem_bytes();
         auto kern = bps_qr_kernel<L, M, R, P, 1>;
         SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);

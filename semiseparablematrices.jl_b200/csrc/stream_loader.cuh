@@ -289,6 +289,17 @@ struct WindowRing {
         if (issuer) for (int64_t k = 0; k < NST && k < total; ++k) issue(k);
     }
     __device__ __forceinline__ void wait(int64_t k) { mbar_wait(bar0 + 8u * (uint32_t)(k % NST), (uint32_t)((k / NST) & 1)); }
+    // the same three operations for callers that track (slot, parity) of a record themselves — no division on the hot path
+    __device__ __forceinline__ void wait_slot(int slot, uint32_t parity) { mbar_wait(bar0 + 8u * (uint32_t)slot, parity); }
+    __device__ __forceinline__ const double *slot_ptr(int slot) const { return ring + slot * (NF * 32) + col; }
+    __device__ __forceinline__ void release_slot(int64_t k, int slot) {      // record k lives in `slot`
+        sync();
+        if (issuer && k + NST < nseq) {
+            const uint32_t bar = bar0 + 8u * slot;
+            mbar_expect_tx(bar, REC_BYTES);
+            bulk_g2s(smem_u32(ring + (size_t)slot * NF * 32), g + (k + NST) * STRIDE * 32, REC_BYTES, bar);
+        }
+    }
     __device__ __forceinline__ const double *rec(int64_t k) const { return ring + (size_t)(k % NST) * NF * 32 + col; }
     __device__ __forceinline__ void release(int64_t k) {
         sync();
