@@ -73,6 +73,10 @@ __global__ void __launch_bounds__(32) ab_qt_kernel(const AbSolveArgs a, const in
     const double *qt = a.QT + tile * a.np * NFQ * 32 + lane;
     double *rhs = a.rhs + tile * a.np * 32 + lane;
     const double *rin = a.rhs_in + tile * a.np * 32 + lane;
+#ifdef SSM_DEBUG_RING
+    const int dbg_id = (a.unit >> 8) & 511; const bool dbg_on = gridDim.x == 4096 && (a.unit >> 8) > 0;
+    if (dbg_on && lane == 0) atomicMax(&ssm_time_dbg[2 * dbg_id], ~gtimer());
+#endif
     QtState<L> st;
     qt_prologue<L>(st, [&](int rho) { return rin[rho * 32]; });
     const int64_t nsteps = ((n + P - 1) / P) * P;
@@ -88,6 +92,9 @@ __global__ void __launch_bounds__(32) ab_qt_kernel(const AbSolveArgs a, const in
             if (k < n) rhs[(int64_t)k * 32] = c;
         }
     }
+#ifdef SSM_DEBUG_RING
+    if (dbg_on && lane == 0) atomicMax(&ssm_time_dbg[2 * dbg_id + 1], gtimer());
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -105,6 +112,10 @@ __global__ void __launch_bounds__(32) ab_backsolve_kernel(const AbSolveArgs a, c
     const double *vv = a.V + tile * a.np * (R > 0 ? R : 1) * 32 + lane;
     double *rhs = a.rhs + tile * a.np * 32 + lane;
     const double *rin = a.rhs_in + tile * a.np * 32 + lane;
+#ifdef SSM_DEBUG_RING
+    const int dbg_id = (a.unit >> 8) & 511; const bool dbg_on = gridDim.x == 4096 && (a.unit >> 8) > 0;
+    if (dbg_on && lane == 0) atomicMax(&ssm_time_dbg[2 * dbg_id], ~gtimer());
+#endif
     BsState<UB, R> st;
     bs_init<UB, R>(st);
     const int nblk = (n + PX - 1) / PX;
@@ -112,7 +123,7 @@ __global__ void __launch_bounds__(32) ab_backsolve_kernel(const AbSolveArgs a, c
     const int64_t nsteps = (int64_t)nblk * PX;
     Loader<NFR, R, 1, -1> ld;
     ld.init(ru + (int64_t)itop * NFR * 32, vv + (int64_t)(itop + UB + 1) * R * 32, rin + (int64_t)itop * 32, smem, nstage, nsteps);
-    const bool unit = a.unit != 0;
+    const bool unit = (a.unit & 1) != 0;
     int64_t g = 0;
     for (int ib = (nblk - 1) * PX; ib >= 0; ib -= PX) {
 #pragma unroll
@@ -126,6 +137,9 @@ __global__ void __launch_bounds__(32) ab_backsolve_kernel(const AbSolveArgs a, c
             }
         }
     }
+#ifdef SSM_DEBUG_RING
+    if (dbg_on && lane == 0) atomicMax(&ssm_time_dbg[2 * dbg_id + 1], gtimer());
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -316,7 +330,8 @@ static int launch1(ssm_ctx *c, K kern, int64_t ntiles, size_t smem, const char *
 bool pick_group(const ssm_ctx *c, size_t block_bytes, int64_t ntiles, int *nstage, int *gm) {
     int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
     if (per_sm < 1) per_sm = 1;
-    const size_t budget = (size_t)(200 * 1024) / (size_t)per_sm;
+    size_t budget = (size_t)(200 * 1024) / (size_t)per_sm;
+    if (budget > (size_t)c->group_smem_kb * 1024) budget = (size_t)c->group_smem_kb * 1024;
     int g = (int)((size_t)c->group_bytes / block_bytes);   // aim at group_bytes per bulk copy group ...
     if (g < 1) g = 1;
     int s = (int)(budget / (g * block_bytes + 16));
@@ -382,7 +397,9 @@ static int qr_inst(ssm_ctx *c, int64_t ntiles, const AbArgs &a, bool with_rhs, b
             SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qr_ring"));                                               \
             kern<<<grid, block, smem, c->stream>>>(a, ns);                                                       \
         } else {                                                                                                 \
-            ab_qr_kernel<L, U, R, RHS_, SQ_, DirectLoaderD><<<grid, block, 0, c->stream>>>(a, 0);                 \
+            auto kern = ab_qr_kernel<L, U, R, RHS_, SQ_, DirectLoaderD>;                                         \
+            if (c->carveout_all) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+            kern<<<grid, block, 0, c->stream>>>(a, 0);                                                           \
         }                                                                                                        \
     }
     SSM_QR_CASE(false, true)
@@ -418,7 +435,9 @@ static int qt_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
         SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qt_ring"));
         kern<<<grid, block, smem, c->stream>>>(a, ns);
     } else {
-        ab_qt_kernel<L, DirectLoaderD><<<grid, block, 0, c->stream>>>(a, 0);
+        auto kern = ab_qt_kernel<L, DirectLoaderD>;
+        if (c->carveout_all) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        kern<<<grid, block, 0, c->stream>>>(a, 0);
     }
     c->launches++;
     SSM_CUDA(cudaGetLastError());
@@ -449,7 +468,9 @@ static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
         SSM_TRY(launch1(c, kern, ntiles, smem, "ab_bs_ring"));
         kern<<<grid, block, smem, c->stream>>>(a, ns);
     } else {
-        ab_backsolve_kernel<L, U, R, DirectLoaderD><<<grid, block, 0, c->stream>>>(a, 0);
+        auto kern = ab_backsolve_kernel<L, U, R, DirectLoaderD>;
+        if (c->carveout_all) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        kern<<<grid, block, 0, c->stream>>>(a, 0);
     }
     c->launches++;
     SSM_CUDA(cudaGetLastError());
@@ -530,3 +551,12 @@ int launch_ab_tri(ssm_ctx *c, const ssm_ab *A, double *rhs, bool upper, bool uni
 }
 
 }  // namespace ssm
+
+#ifdef SSM_DEBUG_RING
+extern "C" int ssm_debug_ring(unsigned long long *out8) { return (int)cudaMemcpyFromSymbol(out8, ssm::ssm_ring_dbg, 64); }
+extern "C" int ssm_debug_times(unsigned long long *out, int reset) {
+    int rc = (int)cudaMemcpyFromSymbol(out, ssm::ssm_time_dbg, sizeof(unsigned long long) * 1024);
+    if (reset) { static unsigned long long init[1024]; for (int i = 0; i < 512; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; } cudaMemcpyToSymbol(ssm::ssm_time_dbg, init, sizeof(init)); }
+    return rc;
+}
+#endif

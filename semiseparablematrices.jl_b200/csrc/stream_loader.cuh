@@ -47,6 +47,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// Orders this thread's (and, through a preceding barrier, its warp's / CTA's) generic-proxy accesses to shared memory before
+// subsequent async-proxy operations.  REQUIRED between the last LDS of a stage and the bulk copy that re-arms it: without it the
+// copy's data may land before the reads are performed.  (Found the hard way: a ring that passed every sequential test returned
+// wrong rows as soon as another stream kept the GPU busy; see profiles/r1_measurements.md.)
+__device__ __forceinline__ void fence_proxy_async() {
+#ifndef SSM_TEST_WITHOUT_PROXY_FENCE     // only for checking that tests/test_gpu_concurrent.py catches the hazard
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -85,6 +94,11 @@ struct DirectLoader {
     }
 };
 
+#ifdef SSM_DEBUG_RING
+static __device__ unsigned long long ssm_ring_dbg[8];
+static __device__ unsigned long long ssm_time_dbg[2 * 512];   // [2*id] min start, [2*id+1] max end of launch id (globaltimer ns)
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }   // [0] mismatching stage reads, [1] tile, [2] step, [3] stream/field, [4] total checks
+#endif
 // ---- RingLoader ---------------------------------------------------------------------------------------
 template <int NF0, int NF1, int NF2, int DIR, int STR0 = NF0, int STR1 = NF1, int STR2 = NF2>
 struct RingLoader {
@@ -139,7 +153,21 @@ struct RingLoader {
         for (int f = 0; f < NF1; ++f) r1[f] = src[(NF0 + f) * 32];
 #pragma unroll
         for (int f = 0; f < NF2; ++f) r2[f] = src[(NF0 + NF1 + f) * 32];
+#ifdef SSM_DEBUG_RING_CONTENT
+        {
+            bool bad = false; int where = -1;
+#pragma unroll
+            for (int f = 0; f < NF0; ++f) if (__double_as_longlong(r0[f]) != __double_as_longlong((g0 + (int64_t)DIR * g * STR0 * 32)[f * 32 + lane])) { bad = true; where = f; }
+#pragma unroll
+            for (int f = 0; f < NF1; ++f) if (__double_as_longlong(r1[f]) != __double_as_longlong((g1 + (int64_t)DIR * g * STR1 * 32)[f * 32 + lane])) { bad = true; where = 100 + f; }
+#pragma unroll
+            for (int f = 0; f < NF2; ++f) if (__double_as_longlong(r2[f]) != __double_as_longlong((g2 + (int64_t)DIR * g * STR2 * 32)[f * 32 + lane])) { bad = true; where = 200 + f; }
+            if (lane == 0) atomicAdd(&ssm_ring_dbg[4], 1ull);
+            if (bad) { if (atomicAdd(&ssm_ring_dbg[0], 1ull) == 0) { ssm_ring_dbg[1] = blockIdx.x; ssm_ring_dbg[2] = (unsigned long long)g; ssm_ring_dbg[3] = (unsigned long long)where; ssm_ring_dbg[5] = (unsigned long long)nstage; ssm_ring_dbg[6] = NF0 * 1000 + NF1 * 10 + NF2; } }
+        }
+#endif
         __syncwarp();   // every lane has its copy in registers before the stage is re-armed
+        fence_proxy_async();   // all lanes: their reads of this stage are performed before the re-arming bulk copy may write it
         if (lane == 0 && g + nstage < nsteps) issue(g + nstage, s);
         if (++cur == nstage) { cur = 0; parity ^= 1u; }
     }
@@ -194,7 +222,7 @@ struct GroupRing {
         const uint32_t bars = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)nstage * gm * BLOCK_BYTES);
         int s = 0; uint32_t use = 0;
         for (int64_t b0 = 0; b0 < nblocks; b0 += gm) {
-            if (use > 0) mbar_wait(bars + 16u * s + 8u, (use - 1) & 1u);
+            if (use > 0) { mbar_wait(bars + 16u * s + 8u, (use - 1) & 1u); fence_proxy_async(); }
             const int rows = (int)((nblocks - b0 < gm ? nblocks - b0 : gm)) * P;
             const int64_t r0 = b0 * P;                                   // first step of the group
             const int64_t lo = DIR > 0 ? r0 : -(r0 + rows - 1);          // lowest record of the group, relative to step 0's
@@ -241,6 +269,7 @@ struct GroupRing {
     }
     __device__ __forceinline__ void block_end() {
         if (++blk == cb) {
+            fence_proxy_async();          // this lane's reads of the stage precede the producer's next bulk copy into it
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + 16u * cur + 8u);
             blk = 0; blocks_left -= cb;
@@ -294,6 +323,7 @@ struct WindowRing {
     __device__ __forceinline__ const double *slot_ptr(int slot) const { return ring + slot * (NF * 32) + col; }
     __device__ __forceinline__ void release_slot(int64_t k, int slot) {      // record k lives in `slot`
         sync();
+        fence_proxy_async();
         if (issuer && k + NST < nseq) {
             const uint32_t bar = bar0 + 8u * slot;
             mbar_expect_tx(bar, REC_BYTES);
@@ -303,6 +333,7 @@ struct WindowRing {
     __device__ __forceinline__ const double *rec(int64_t k) const { return ring + (size_t)(k % NST) * NF * 32 + col; }
     __device__ __forceinline__ void release(int64_t k) {
         sync();
+        fence_proxy_async();
         if (issuer && k + NST < nseq) issue(k + NST);
     }
 };

@@ -106,6 +106,58 @@ def c5(args, ctx):
     print(json.dumps({"config": "c5 total", "systems": tot_sys, "ms": tot_ms, "systems_per_s": tot_sys / (tot_ms * 1e-3)}))
 
 
+def timeit_streams(fns, streams, steps, warm=3):
+    """fns[i] enqueues one step of piece i on streams[i]; all pieces run concurrently.  Device time from a common start event to
+    the last piece's end (CUDA events; every stream waits for the start event, the main stream waits for every end event)."""
+    main = torch.cuda.current_stream()
+
+    def run(k):
+        start = torch.cuda.Event(enable_timing=True); stop = torch.cuda.Event(enable_timing=True)
+        start.record(main)
+        for st in streams:
+            st.wait_event(start)
+        for _ in range(k):
+            for fn in fns:
+                fn()
+        for st in streams:
+            e = torch.cuda.Event(); e.record(st); main.wait_event(e)
+        stop.record(main)
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / k
+    run(warm)
+    return run(steps)
+
+
+def c5c(args, ctx):
+    """configs[4], this GPU's share, with the groups running CONCURRENTLY (one library context = one CUDA stream per group): small
+    shares of the large-n groups are latency bound on their own (a few warps per SM) and fill the GPU only together."""
+    groups = [(256, 524288), (512, 262144), (1024, 131072), (2048, 65536), (4096, 32768), (8192, 32768)]
+    dev = torch.cuda.current_device()
+    objs, streams = [], []
+    for n, nbt in groups:
+        nb = nbt // args.world
+        st = torch.cuda.Stream()
+        cx = ssm.Context(dev, stream=st.cuda_stream)
+        for kv in args.opt:
+            k, v = kv.split("="); cx.set_option(k, int(v))
+        A = ssm.AlmostBandedMatrix.generate(n, 2, 2, 2, nb, 20261019 + 4, ctx=cx)
+        b = ssm.Vec(cx, n, nb).generate(20261019 + 4)
+        x = ssm.Vec(cx, n, nb)
+        objs.append((A, b, x, ssm.qr(A), cx)); streams.append(st)
+    torch.cuda.synchronize()
+    fns = [(lambda A=A, b=b, x=x, F=F: (F.refactor(A), F.solve(b, out=x))) for A, b, x, F, _ in objs]
+    order = sorted(range(len(fns)), key=lambda i: -groups[i][0])          # longest serial chains first
+    t = timeit_streams([fns[i] for i in order], streams, args.steps)
+    rrs = [float(A.residual(x, b).max()) for A, b, x, F, _ in objs]
+    rr = max(rrs)
+    if rr > 1e-12:
+        print("per-group relres", rrs, file=sys.stderr)
+    tot = sum(nbt // args.world for _, nbt in groups)
+    byts = sum(8 * n * 33 * (nbt // args.world) for n, nbt in groups)
+    print(json.dumps({"config": "c5 concurrent groups", "share": f"1/{args.world}", "systems": tot, "ms": t, "systems_per_s": tot / (t * 1e-3),
+                      "frac_of_measured_peak": byts / t / 1e6 / PEAK, "relres_max": rr}))
+
+
 def c4(args, ctx):
     """configs[3]: one large almost-banded system, n = 2^24, l = u = 4, r = 2, chunked n-axis path (K10)."""
     from ssm_b200 import chunked
@@ -204,7 +256,7 @@ def c5dist(args, ctx):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["c2", "c2m", "c3", "c3rq", "c4", "c5", "c5dist"])
+    ap.add_argument("which", choices=["c2", "c2m", "c3", "c3rq", "c4", "c5", "c5c", "c5dist"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
@@ -225,4 +277,4 @@ if __name__ == "__main__":
     for kv in args.opt:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
-    {"c2": c2, "c2m": c2m, "c3": c3, "c3rq": c3rq, "c4": c4, "c5": c5, "c5dist": c5dist}[args.which](args, ctx)
+    {"c2": c2, "c2m": c2m, "c3": c3, "c3rq": c3rq, "c4": c4, "c5": c5, "c5c": c5c, "c5dist": c5dist}[args.which](args, ctx)
