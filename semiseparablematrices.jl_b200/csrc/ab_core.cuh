@@ -101,9 +101,12 @@ SSM_HD void ab_step(AbState<L, U, R> &st, const int PH, const double *in_rec, co
     const double xi1 = x0 + nu;
     const double inv_xi = nz ? fast_rcp(xi1) : 0.0;
     const double tau = nz ? xi1 * copysign(rs, x0) : 0.0;
-    double v[L > 0 ? L : 1], xraw[L > 0 ? L : 1];
+    // what the factor storage keeps below the diagonal: v = x_tail / xi, or — for a column without a reflector (k >= ncols of a
+    // partial factorisation, or an exactly zero column) — the column itself, as _almostbanded_qr!(A, tau, ncols) leaves it
+    const double keep = nz ? inv_xi : 1.0;
+    double v[L > 0 ? L : 1], vkeep[L > 0 ? L : 1];
 #pragma unroll
-    for (int i = 1; i <= L; ++i) { xraw[i - 1] = st.A[(PH + i) % P][L - i]; v[i - 1] = xraw[i - 1] * inv_xi; }
+    for (int i = 1; i <= L; ++i) { const double xi = st.A[(PH + i) % P][L - i]; v[i - 1] = xi * inv_xi; vkeep[i - 1] = xi * keep; }
     st.A[s0][L] = nz ? -nu : x0;
     // (3) apply H = I - tau v v' to the live columns, to the U rows and to the right-hand side
 #pragma unroll
@@ -140,10 +143,8 @@ SSM_HD void ab_step(AbState<L, U, R> &st, const int PH, const double *in_rec, co
     for (int t = 0; t <= UB; ++t) out_r[t] = st.A[s0][t + L];
 #pragma unroll
     for (int q = 0; q < R; ++q) out_r[UB + 1 + q] = st.UC[s0][q];
-    // below the diagonal the factor storage holds v, or — for a column without a reflector (k >= ncols of a partial
-    // factorisation, or an exactly zero column) — the column itself, as _almostbanded_qr!(A, tau, ncols) leaves it
 #pragma unroll
-    for (int i = 1; i <= L; ++i) out_q[i - 1] = nz ? v[i - 1] : xraw[i - 1];
+    for (int i = 1; i <= L; ++i) out_q[i - 1] = vkeep[i - 1];
     out_q[L] = tau;
     out_c = st.RH[s0];
     // (5) surviving rows gain column k+1+UB, which lies in their fill region

@@ -222,7 +222,11 @@ struct GroupRing {
         const uint32_t bars = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)nstage * gm * BLOCK_BYTES);
         int s = 0; uint32_t use = 0;
         for (int64_t b0 = 0; b0 < nblocks; b0 += gm) {
+#ifdef SSM_GROUP_NO_FENCE_P
+            if (use > 0) { mbar_wait(bars + 16u * s + 8u, (use - 1) & 1u); }
+#else
             if (use > 0) { mbar_wait(bars + 16u * s + 8u, (use - 1) & 1u); fence_proxy_async(); }
+#endif
             const int rows = (int)((nblocks - b0 < gm ? nblocks - b0 : gm)) * P;
             const int64_t r0 = b0 * P;                                   // first step of the group
             const int64_t lo = DIR > 0 ? r0 : -(r0 + rows - 1);          // lowest record of the group, relative to step 0's
@@ -269,7 +273,9 @@ struct GroupRing {
     }
     __device__ __forceinline__ void block_end() {
         if (++blk == cb) {
+#ifndef SSM_GROUP_NO_FENCE_C
             fence_proxy_async();          // this lane's reads of the stage precede the producer's next bulk copy into it
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + 16u * cur + 8u);
             blk = 0; blocks_left -= cb;

@@ -138,6 +138,7 @@ def c5c(args, ctx):
         nb = nbt // args.world
         st = torch.cuda.Stream()
         cx = ssm.Context(dev, stream=st.cuda_stream)
+        cx.set_option("group_smem_kb", 48)          # several contexts share the SMs
         for kv in args.opt:
             k, v = kv.split("="); cx.set_option(k, int(v))
         A = ssm.AlmostBandedMatrix.generate(n, 2, 2, 2, nb, 20261019 + 4, ctx=cx)
@@ -224,33 +225,53 @@ def c3rq(args, ctx):
 
 
 def c5dist(args, ctx):
-    """configs[4] on N GPUs, one process per GPU (torchrun): the sharder's group plan (ssm_b200.sharder.plan_groups) decides which
-    (n, system range) pieces this rank owns; time = max over ranks of the device time for the rank's whole list."""
+    """configs[4] on N GPUs, one process per GPU (torchrun).  --plan even (default): every group is cut into N contiguous shards
+    (ssm_shard_range) and a rank runs its six shards CONCURRENTLY, one library context (= CUDA stream) per shard, so that the small
+    shares of the large-n groups — latency bound on their own — fill the GPU together.  --plan lpt: whole groups as units
+    (sharder.plan_groups), run back to back.  Time = max over ranks of the device time for the rank's whole list."""
     from ssm_b200 import sharder
-    job = sharder.Job(backend="nccl", device=torch.device("cuda", torch.cuda.current_device()))
+    dev = torch.cuda.current_device()
+    job = sharder.Job(backend="nccl", device=torch.device("cuda", dev))
     groups = [(256, 524288), (512, 262144), (1024, 131072), (2048, 65536), (4096, 32768), (8192, 32768)]
-    plan = sharder.plan_groups(groups, job.world)
-    mine = plan[job.rank]
-    objs = []
+    if args.plan == "lpt":
+        mine = sharder.plan_groups(groups, job.world)[job.rank]
+    else:
+        mine = [(gi,) + sharder.shard_range(nb, job.rank, job.world) for gi, (n, nb) in enumerate(groups)]
+        mine = [p for p in mine if p[2] > p[1]]
+    objs, streams = [], []
     for gi, s0, s1 in mine:
         n, nb = groups[gi][0], s1 - s0
-        A = ssm.AlmostBandedMatrix.generate(n, 2, 2, 2, nb, 20261019 + 4 + 1000 * gi + s0, ctx=ctx)
-        b = ssm.Vec(ctx, n, nb).generate(20261019 + 4 + 1000 * gi + s0)
-        objs.append((A, b, ssm.Vec(ctx, n, nb), ssm.qr(A)))
+        if args.plan == "lpt":
+            cx = ctx
+        else:
+            st = torch.cuda.Stream(); streams.append(st)
+            cx = ssm.Context(dev, stream=st.cuda_stream)
+            cx.set_option("group_smem_kb", 48)      # several contexts share the SMs
+        A = ssm.AlmostBandedMatrix.generate(n, 2, 2, 2, nb, 20261019 + 4 + 1000 * gi + s0, ctx=cx)
+        b = ssm.Vec(cx, n, nb).generate(20261019 + 4 + 1000 * gi + s0)
+        objs.append((A, b, ssm.Vec(cx, n, nb), ssm.qr(A), cx))
+    torch.cuda.synchronize()
 
     def sweep():
-        for A, b, x, F in objs:
+        for A, b, x, F, _ in objs:
             F.refactor(A); F.solve(b, out=x)
     job.barrier()
-    t = timeit(sweep, args.steps) if objs else 0.0
+    if not objs:
+        t = 0.0
+    elif args.plan == "lpt":
+        t = timeit(sweep, args.steps)
+    else:
+        order = sorted(range(len(objs)), key=lambda i: -objs[i][0].n)          # longest serial chains first
+        fns = [(lambda A=A, b=b, x=x, F=F: (F.refactor(A), F.solve(b, out=x))) for A, b, x, F, _ in objs]
+        t = timeit_streams([fns[i] for i in order], streams, args.steps)
     tmax = job.max_over_ranks(t)
-    rr = max([float(A.residual(x, b).max()) for A, b, x, F in objs] or [0.0])
+    rr = max([float(A.residual(x, b).max()) for A, b, x, F, _ in objs] or [0.0])
     rrmax = job.max_over_ranks(rr)
     per_rank = job.gather({"rank": job.rank, "ms": t, "pieces": [(groups[gi][0], s1 - s0) for gi, s0, s1 in mine]})
     if job.rank == 0:
         tot = sum(nb for _, nb in groups)
-        print(json.dumps({"config": "c5 sharded sweep n=256..8192, 2^20 systems, qr+ldiv!", "n_gpus": job.world, "ms": tmax, "systems_per_s": tot / (tmax * 1e-3),
-                          "relres_max": rrmax, "per_rank": per_rank}))
+        print(json.dumps({"config": "c5 sharded sweep n=256..8192, 2^20 systems, qr+ldiv!", "plan": args.plan, "n_gpus": job.world, "ms": tmax,
+                          "systems_per_s": tot / (tmax * 1e-3), "relres_max": rrmax, "per_rank": per_rank}))
     job.close()
 
 
@@ -265,6 +286,7 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--world", type=int, default=1)
     ap.add_argument("--chunks", type=int, default=0)
+    ap.add_argument("--plan", choices=["even", "lpt"], default="even")
     args = ap.parse_args()
     import os
     dev = int(os.environ.get("LOCAL_RANK", "0"))
