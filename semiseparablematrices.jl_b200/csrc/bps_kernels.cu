@@ -78,14 +78,14 @@ __global__ void __launch_bounds__(128) bps_reduce_kernel(const double *REC, cons
 // Window ring depth of the one-warp-per-tile sweep: the M + L + 1 rows a step reads plus ONE slot in flight.  Shared memory per
 // CTA decides how many warps an SM holds (16 slots = 61 KB = 3 CTAs, 8 slots = 30.7 KB = 7 CTAs), and with 7 warps to switch
 // between deeper prefetch buys nothing: 131,072 systems 41.3 -> 27.7 ms (55 -> 80 % of the HBM peak) on B200.
-constexpr int bps_nst(int l, int m) { return l + m + 2; }
+constexpr int bps_nst(int l, int m, int look) { return l + m + 1 + look; }
 
 // SPLIT = 1: one warp per tile of 32 systems.  SPLIT = 2: a CTA of two warps per tile, each warp owning 16 systems (lanes 16-31
 // shadow lanes 0-15 and do not store), both reading one shared window ring: the sweep is latency bound — a batch of 16,384 systems
 // is only 512 warps, fewer than the 592 warp schedulers of a B200 — so halving the systems per warp doubles the warps in flight at
 // the cost of idle lanes, not of HBM or TMA traffic.
 constexpr int BPS_NST_SPLIT = 12;  // 46 KB per CTA: four CTAs (all 512 tiles of config 3) stay co-resident per SM
-template <int L, int M, int R, int P, int SPLIT>
+template <int L, int M, int R, int P, int SPLIT, int LOOK = 1>
 __global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, const double *GT, double *OUT, int n, int64_t np, int64_t npo) {
     using D = BpsDims<L, M, R, P>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, c
     const int64_t tile = blockIdx.x;
     const int sl = SPLIT == 1 ? lane : (lane & 15) + 16 * (int)(threadIdx.x >> 5);    // system column of the tile this thread computes
     const bool writer = SPLIT == 1 || lane < 16;
-    WindowRing<D::NFA, SPLIT == 1 ? bps_nst(L, M) : BPS_NST_SPLIT, SPLIT> win;
+    WindowRing<D::NFA, SPLIT == 1 ? bps_nst(L, M, LOOK) : BPS_NST_SPLIT, SPLIT> win;
     // sequence index k <-> row k - M; record of row rho sits at BPS_FRONT + rho
     win.init(REC + (tile * np + BPS_FRONT - M) * D::NFA * 32, smem, (int64_t)n + L + M);
     win.col = sl;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, c
     BpsState<L, M, R, P> st;
     bps_init<L, M, R, P>(st, gt);
     double *out = OUT + tile * npo * D::NFO * 32 + sl;
-    constexpr int NST = SPLIT == 1 ? bps_nst(L, M) : BPS_NST_SPLIT;
+    constexpr int NST = SPLIT == 1 ? bps_nst(L, M, LOOK) : BPS_NST_SPLIT;
     for (int k = 0; k < L + M; ++k) win.wait(k);          // rows -M .. L-1
     int s0 = 0, sw = (L + M) % NST;                        // slots of sequence records q (row q-M) and q+L+M (row q+L)
     uint32_t pw = ((L + M) / NST) & 1;
@@ -533,10 +533,19 @@ static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
         SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)A->ntiles, 64, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
     } else {
-        const size_t smem = WindowRing<D::NFA, bps_nst(L, M), 1>::smem_bytes();
-        auto kern = bps_qr_kernel<L, M, R, P, 1>;
-        SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+        // one slot in flight keeps 7 CTAs per SM resident; a second one (6 CTAs per SM) removes most of the wait for the entering
+        // row when the batch leaves room for it (config 3: 4.20 -> 3.87 ms; at 7 tiles per SM it would cost a second wave)
+        if (A->ntiles <= (int64_t)c->sm_count * 5) {
+            const size_t smem = WindowRing<D::NFA, bps_nst(L, M, 2), 1>::smem_bytes();
+            auto kern = bps_qr_kernel<L, M, R, P, 1, 2>;
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+        } else {
+            const size_t smem = WindowRing<D::NFA, bps_nst(L, M, 1), 1>::smem_bytes();
+            auto kern = bps_qr_kernel<L, M, R, P, 1, 1>;
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+        }
     }
     c->launches++;
     SSM_CUDA(cudaGetLastError());
