@@ -64,7 +64,7 @@ struct ssm_ctx {
     int          ab_variant = 0;       // 0 auto, 1 direct-load kernels, 2 bulk-async (TMA) ring kernels, 4 GroupRing kernels (producer warp + grouped bulk copies), 9 generic
     int          carveout_all = 0;     // experiment: direct-load kernels also ask for the max-shared carveout
     int          group_smem_kb = 200;  // GroupRing: shared memory one CTA may take.  Alone on the GPU the deep ring is worth 3-8 % at <= 2 tiles per
-                                       // SM; contexts that share the GPU on different streams set ~48 so that their CTAs fit side by side
+                                       // SM; contexts that share the GPU on different streams set ~96 so that their CTAs fit side by side
     int          group_bytes = 32768;  // GroupRing: target size of one bulk-copy group
     int          group_max_per_sm = 9; // auto: batches of at most this many tiles per SM run the GroupRing kernels
     int          pipeline_stages = 0;  // 0 = kernel default
