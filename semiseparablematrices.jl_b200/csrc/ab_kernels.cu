@@ -5,6 +5,7 @@
 //
 // Replaces: _almostbanded_qr! (AlmostBandedMatrix.jl:135-172) incl. the widening copy (:30-38),
 //           lmul!(Q',b) (:181,189), _almostbanded_upper_ldiv! (:215-240).
+#include <type_traits>
 #include "ab_core.cuh"
 #include "ab_generic.cuh"
 #include "ssm_internal.cuh"
@@ -179,7 +180,10 @@ __global__ void __launch_bounds__(64) ab_qr_group_kernel(const AbArgs a, const i
         [&](int c, int q) { return __ldg(vv + (c * R + q) * 32); }, [&](int rho) { return rin[rho * 32]; });
     Ring ld;
     ld.attach(smem, nstage, gm, nblocks, col);
-    for (int kb = 0; kb < n; kb += P) {
+    // one block of P columns; only the last block of a sweep can reach past row n-1, so every other block runs without the
+    // per-column bounds test (and the branch that comes with it)
+    auto block = [&](const int kb, auto guarded) {
+        constexpr bool GUARD = decltype(guarded)::value;
         ld.block_begin();
 #pragma unroll
         for (int ph = 0; ph < P; ++ph) {
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(64) ab_qr_group_kernel(const AbArgs a, const i
             ld.read(ph, rec, vc, bb);
             double out_r[NFR], out_q[NFQ], out_c;
             ab_step<L, U, R, RHS>(st, ph, rec, vc, bb[0], k < a.ncols, out_r, out_q, out_c);
-            if (k < n) {
+            if (!GUARD || k < n) {
 #pragma unroll
                 for (int f = 0; f < NFR; ++f) ru[((int64_t)k * NFR + f) * 32] = out_r[f];
                 if (STOREQ) {
@@ -199,7 +203,10 @@ __global__ void __launch_bounds__(64) ab_qr_group_kernel(const AbArgs a, const i
             }
         }
         ld.block_end();
-    }
+    };
+    int kb = 0;
+    for (; kb + P <= n; kb += P) block(kb, std::false_type{});
+    if (kb < n) block(kb, std::true_type{});
 }
 
 template <int L>
@@ -225,7 +232,8 @@ __global__ void __launch_bounds__(64) ab_qt_group_kernel(const AbSolveArgs a, co
     qt_prologue<L>(st, [&](int rho) { return rin[rho * 32]; });
     Ring ld;
     ld.attach(smem, nstage, gm, nblocks, col);
-    for (int kb = 0; kb < n; kb += P) {
+    auto block = [&](const int kb, auto guarded) {
+        constexpr bool GUARD = decltype(guarded)::value;
         ld.block_begin();
 #pragma unroll
         for (int ph = 0; ph < P; ++ph) {
@@ -233,10 +241,13 @@ __global__ void __launch_bounds__(64) ab_qt_group_kernel(const AbSolveArgs a, co
             double q[NFQ], bb[1], dummy[1];
             ld.read(ph, q, bb, dummy);
             const double c = qt_step<L>(st, ph, q, bb[0]);
-            if (k < n) rhs[(int64_t)k * 32] = c;
+            if (!GUARD || k < n) rhs[(int64_t)k * 32] = c;
         }
         ld.block_end();
-    }
+    };
+    int kb = 0;
+    for (; kb + P <= n; kb += P) block(kb, std::false_type{});
+    if (kb < n) block(kb, std::true_type{});
 }
 
 template <int L, int U, int R>
@@ -266,20 +277,25 @@ __global__ void __launch_bounds__(64) ab_backsolve_group_kernel(const AbSolveArg
     Ring ld;
     ld.attach(smem, nstage, gm, nblk, col);
     const bool unit = a.unit != 0;
-    for (int ib = (nblk - 1) * PX; ib >= 0; ib -= PX) {
+    // only the first (topmost) block can contain rows >= n
+    auto block = [&](const int ib, auto guarded) {
+        constexpr bool GUARD = decltype(guarded)::value;
         ld.block_begin();
 #pragma unroll
         for (int ph = PX - 1; ph >= 0; --ph) {
             const int i = ib + ph;
             double r[NFR], vc[R > 0 ? R : 1], cc[1];
             ld.read(PX - 1 - ph, r, vc, cc);
-            if (i < n) {
+            if (!GUARD || i < n) {
                 const double x = bs_step<UB, R>(st, ph, r, vc, cc[0], unit);
                 rhs[(int64_t)i * 32] = x;
             }
         }
         ld.block_end();
-    }
+    };
+    int ib = (nblk - 1) * PX;
+    block(ib, std::true_type{});
+    for (ib -= PX; ib >= 0; ib -= PX) block(ib, std::false_type{});
 }
 
 // ---------------------------------------------------------------------------------------------------------
