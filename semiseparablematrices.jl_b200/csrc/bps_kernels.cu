@@ -107,13 +107,16 @@ __global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, c
     for (int k = 0; k < L + M; ++k) win.wait(k);          // rows -M .. L-1
     int s0 = 0, sw = (L + M) % NST;                        // slots of sequence records q (row q-M) and q+L+M (row q+L)
     uint32_t pw = ((L + M) / NST) & 1;
-    for (int q = 0; q < n; ++q) {
+    // one column; LAST is a compile-time flag so that the n-1 ordinary steps carry no test for the final row (a branch in the
+    // middle of the step is a scheduling barrier for a warp that runs alone on its scheduler)
+    auto step = [&](const int q, auto last_tag) {
+        constexpr bool LAST = decltype(last_tag)::value;
         win.wait_slot(sw, pw);                             // row q+L
         const double *rp[L + M + 1];                       // window rows q-M .. q+L
 #pragma unroll
         for (int t = 0; t <= L + M; ++t) { int sl = s0 + t; if (sl >= NST) sl -= NST; rp[t] = win.slot_ptr(sl); }
         double o[D::NFO];
-        bps_step<L, M, R, P>(st, [&](int rel, int f) { return rp[rel + M][f * 32]; }, q == n - 1, o);
+        bps_step<L, M, R, P>(st, [&](int rel, int f) { return rp[rel + M][f * 32]; }, LAST, o);
         if (writer) {
 #pragma unroll
             for (int f = 0; f < D::NFO; ++f) out[((int64_t)q * D::NFO + f) * 32] = o[f];
@@ -121,7 +124,9 @@ __global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, c
         win.release_slot(q, s0);                           // row q-M leaves the window
         if (++s0 == NST) s0 = 0;
         if (++sw == NST) { sw = 0; pw ^= 1u; }
-    }
+    };
+    for (int q = 0; q < n - 1; ++q) step(q, std::false_type{});
+    step(n - 1, std::true_type{});
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -481,14 +486,15 @@ __global__ void __launch_bounds__(64) bps_qr_pair_kernel(const double *REC, cons
     constexpr int NST = BPS_NST_SPLIT;
     int s0 = 0, sw = (L + M) % NST;                        // slots of sequence records q (row q-M) and q+L+M (row q+L)
     uint32_t pw = ((L + M) / NST) & 1;
-    auto step = [&](auto parc, const int q) {
+    auto step = [&](auto parc, const int q, auto last_tag) {
         constexpr int PAR = decltype(parc)::value;
+        constexpr bool LAST = decltype(last_tag)::value;
         win.wait_slot(sw, pw);                             // row q+L
         const double *rp[L + M + 1];                       // window rows q-M .. q+L
 #pragma unroll
         for (int t = 0; t <= L + M; ++t) { int sl = s0 + t; if (sl >= NST) sl -= NST; rp[t] = win.slot_ptr(sl); }
         double o[D::NFO];
-        bps_step<L, M, R, P, PAR>(st, [&](int rel, int f) { return rp[rel + M][f * 32]; }, q == n - 1, o, xch);
+        bps_step<L, M, R, P, PAR>(st, [&](int rel, int f) { return rp[rel + M][f * 32]; }, LAST, o, xch);
 #pragma unroll
         for (int f = 0; f < D::NFO; ++f) {
             const bool band = f > D::OD && f <= D::OD + L + M;                       // R[q, q+t], t >= 1: written by the column's owner
@@ -499,13 +505,16 @@ __global__ void __launch_bounds__(64) bps_qr_pair_kernel(const double *REC, cons
         if (++s0 == NST) s0 = 0;
         if (++sw == NST) { sw = 0; pw ^= 1u; }
     };
+    // the last column runs the LAST instance; all others carry no test for it
     int q = 0;
-    if (h == 1) { step(std::integral_constant<int, 1>{}, 0); q = 1; }
-    while (q < n) {
-        step(std::integral_constant<int, 0>{}, q++);
-        if (q >= n) break;
-        step(std::integral_constant<int, 1>{}, q++);
+    if (h == 1) { if (n > 1) step(std::integral_constant<int, 1>{}, 0, std::false_type{}); else step(std::integral_constant<int, 1>{}, 0, std::true_type{}); q = 1; }
+    while (q + 2 < n) {
+        step(std::integral_constant<int, 0>{}, q++, std::false_type{});
+        step(std::integral_constant<int, 1>{}, q++, std::false_type{});
     }
+    // 1 or 2 columns left (q = n-2 or n-1); parity of the band-wide columns alternates: PAR = 0 at this q by construction
+    if (q + 1 < n) { step(std::integral_constant<int, 0>{}, q++, std::false_type{}); step(std::integral_constant<int, 1>{}, q++, std::true_type{}); }
+    else if (q < n) step(std::integral_constant<int, 0>{}, q++, std::true_type{});
 }
 
 template <int L, int M, int R, int P>
