@@ -157,18 +157,20 @@ __global__ void __launch_bounds__(32) bps_qt_kernel(const double *REC, const dou
     bps_qt_init<L, R>(st, gt, tt, [&](int row, int a) { return uw[row][a]; }, [&](int row) { return rin[(int64_t)row * 32]; });
     Loader<R, D::NFQ, 1, +1, D::NFA, D::NFO, 1> ld;
     ld.init(urec + (int64_t)L * D::NFA * 32, qrec, rin + (int64_t)L * 32, smem, nstage, n);
-    for (int q = 0; q < n; ++q) {
+    auto step = [&](const int q, auto last_tag) {          // the final row has its own instance: no test for it in the other n-1 steps
         double un[R], qq[D::NFQ], bb[1];
         ld.acquire(q, un, qq, bb);
 #pragma unroll
         for (int a = 0; a < R; ++a) uw[L][a] = un[a];
-        const double c = bps_qt_step<L, R>(st, [&](int rel, int a) { return uw[rel][a]; }, qq + D::OV, qq + D::OB, qq[D::OT], bb[0], q == n - 1);
+        const double c = bps_qt_step<L, R>(st, [&](int rel, int a) { return uw[rel][a]; }, qq + D::OV, qq + D::OB, qq[D::OT], bb[0], decltype(last_tag)::value);
         ro[(int64_t)q * 32] = c;
 #pragma unroll
         for (int s = 0; s < L; ++s)
 #pragma unroll
             for (int a = 0; a < R; ++a) uw[s][a] = uw[s + 1][a];
-    }
+    };
+    for (int q = 0; q < n - 1; ++q) step(q, std::false_type{});
+    step(n - 1, std::true_type{});
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -239,20 +241,22 @@ __global__ void __launch_bounds__(64) bps_qt_group_kernel(const double *REC, con
     bps_qt_init<L, R>(st, gt, tt, [&](int row, int a) { return uw[row][a]; }, [&](int row) { return rin[(int64_t)row * 32]; });
     Ring ld;
     ld.attach(smem, nstage, gm, n, lane);
-    for (int q = 0; q < n; ++q) {
+    auto step = [&](const int q, auto last_tag) {
         double un[R], qq[D::NFQ], bb[1];
         ld.block_begin();
         ld.read(0, un, qq, bb);
         ld.block_end();
 #pragma unroll
         for (int a = 0; a < R; ++a) uw[L][a] = un[a];
-        const double c = bps_qt_step<L, R>(st, [&](int rel, int a) { return uw[rel][a]; }, qq + D::OV, qq + D::OB, qq[D::OT], bb[0], q == n - 1);
+        const double c = bps_qt_step<L, R>(st, [&](int rel, int a) { return uw[rel][a]; }, qq + D::OV, qq + D::OB, qq[D::OT], bb[0], decltype(last_tag)::value);
         ro[(int64_t)q * 32] = c;
 #pragma unroll
         for (int s = 0; s < L; ++s)
 #pragma unroll
             for (int a = 0; a < R; ++a) uw[s][a] = uw[s + 1][a];
-    }
+    };
+    for (int q = 0; q < n - 1; ++q) step(q, std::false_type{});
+    step(n - 1, std::true_type{});
 }
 
 template <int L, int M, int R, int P>
