@@ -61,9 +61,11 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
     auto gout = [&](int i, int f) -> double { return out0[((int64_t)i * D::NFO + f) * 32]; };
     constexpr bool writer = true;
     // new operand records
-    const int nfb2 = o.tl2 + o.tm2 + 1, FU2 = nfb2, FV2 = nfb2 + o.tr2, FW2 = nfb2 + 2 * o.tr2, FS2 = nfb2 + 2 * o.tr2 + o.tp2;
-    double *new0 = o.NEW + (tile * o.np2 + BPS_FRONT) * o.nfa2 * 32 + lane;
-    auto put = [&](int i, int f, double v) { if (writer) new0[((int64_t)i * o.nfa2 + f) * 32] = v; };
+    // The result batch has the padded kernel shape of the factor it comes from (both are bps_pick_shape of a symmetric (l, l, r, r);
+    // the launcher checks it), so its record layout is compile-time: no runtime index arithmetic or shape tests around the stores.
+    constexpr int FU2 = D::FU, FV2 = D::FV, FW2 = D::FW, FS2 = D::FS;
+    double *new0 = o.NEW + (tile * o.np2 + BPS_FRONT) * D::NFA * 32 + lane;
+    auto put = [&](int i, int f, double v) { if (writer) new0[((int64_t)i * D::NFA + f) * 32] = v; };
 
     // ---- prologue: totals for the suffix sums; S[:, 1:r] must equal U (semiseparableqr.jl:199-201) ----
     double T1[R][R], T2[PW][R];
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
             rho[a] = s;
         }
 #pragma unroll
-        for (int a = 0; a < R; ++a) if (a < o.tr2) { const double un = fma(d0, u1[a], rho[a]); put(q, FU2 + a, un); if (a < o.tp2) put(q, FS2 + a, un); }   // U_new = R0 U0 (fast_RU)
+        for (int a = 0; a < R; ++a) { const double un = fma(d0, u1[a], rho[a]); put(q, FU2 + a, un); put(q, FS2 + a, un); }   // U_new = R0 U0 (fast_RU)
         if (EDGE && q == n - 1) {
             // last diagonal entry (:278; getindex :214-269 with k = i = n): the R0 U0 row of the last row is B[n,n] U0[n,:]
             double dg = d0;
@@ -171,9 +173,9 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
                 dg = fma(Phi[0][a], u1[a], dg);
             }
             dg += Lam[0][0];
-            put(q, o.tl2, dg);
+            put(q, L, dg);
 #pragma unroll
-            for (int a = 0; a < R; ++a) if (a < o.tr2) { put(q, FV2 + a, 0.0); if (a < o.tp2) put(q, FW2 + a, 0.0); }
+            for (int a = 0; a < R; ++a) { put(q, FV2 + a, 0.0); put(q, FW2 + a, 0.0); }
             return;
         }
         const int lb = EDGE ? min(L, n - 1 - q) : L, nv = EDGE ? min(L, n - q) : L;
@@ -286,14 +288,14 @@ __global__ void __launch_bounds__(32) bps_rq_kernel(const double *REC, const dou
             dg += -tq * gam[0] + p0u + d0 * uPs - tq * phid2[0] + rPs - tq * d4[0] + Lam[0][0];
         }
         // write row q of the result: diagonal, V_new = mu (= W_new), and the new sub-diagonal column tail, mirrored
-        put(q, o.tl2, dg);
+        put(q, L, dg);
 #pragma unroll
-        for (int a = 0; a < R; ++a) if (a < o.tr2) { put(q, FV2 + a, mu[a]); if (a < o.tp2) put(q, FW2 + a, mu[a]); }
+        for (int a = 0; a < R; ++a) { put(q, FV2 + a, mu[a]); put(q, FW2 + a, mu[a]); }
 #pragma unroll
         for (int t = 0; t < L; ++t) {
-            if (t < lb && t + 1 <= o.tl2 && t + 1 <= o.tm2) {
-                put(q + 1 + t, o.tl2 - (t + 1), eta[t]);       // A[q+1+t, q]
-                put(q, o.tl2 + (t + 1), eta[t]);               // A[q, q+1+t]   (symmetrize_from_lower!, :837-845)
+            if (t < lb) {
+                put(q + 1 + t, L - (t + 1), eta[t]);           // A[q+1+t, q]
+                put(q, L + (t + 1), eta[t]);                   // A[q, q+1+t]   (symmetrize_from_lower!, :837-845)
             }
         }
         // next submatrix (:739-784)
@@ -408,6 +410,12 @@ int ssm_bpsqr_rq_mul(const ssm_bpsqr *F, ssm_bps **out) {
     int rc = dev_alloc(c->device, 1, true, c->stream, flag);
     if (!rc) {
         RqOut o{Q->REC->p, Q->np, bps_nfa(Q->tl, Q->tm, Q->tr, Q->tp), Q->tl, Q->tm, Q->tr, Q->tp};
+        if (Q->tl != F->tl || Q->tm != F->tm || Q->tr != F->tr || Q->tp != F->tp) {
+            set_error("ssm_bpsqr_rq_mul: result batch padded to (%d,%d,%d,%d), factors to (%d,%d,%d,%d)", Q->tl, Q->tm, Q->tr, Q->tp, F->tl, F->tm, F->tr, F->tp);
+            cudaSetDevice(prev);
+            if (fresh) ssm_bps_destroy(Q);
+            return SSM_E_UNSUPPORTED;
+        }
         rc = SSM_E_UNSUPPORTED;
 #define X(L_, M_, R_, P_)                                                                                                   \
     if (F->tl == L_ && F->tm == M_ && F->tr == R_ && F->tp == P_) {                                                        \
