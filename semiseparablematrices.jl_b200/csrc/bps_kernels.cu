@@ -29,12 +29,15 @@ int bps_nfo(int tl, int tm, int tr, int tp) { return tl + tr + 1 + tl + tm + 1 +
 
 // ---------------------------------------------------------------------------------------------------------
 // K5: per-system reductions over the rows: G = U'U (R x R) and, if rhs != null, t = U'b (R).
-// 4 warps per tile, each sums a quarter of the rows; combined through shared memory.
+// RW warps per tile, each sums a slice of the rows (loads of 8 rows in flight per warp); combined through shared memory.  The pass
+// reads 2 of the 15 fields of a record, so it is bound by the latency of strided loads, not by bandwidth: 16 warps per tile
+// instead of 4 took it from 0.41 to ~0.15 ms at config 3 (it runs once before the QR sweep and once before every Q'b).
 // ---------------------------------------------------------------------------------------------------------
+constexpr int BPS_RW = 16;
 template <int NFA, int FU, int R>
-__global__ void __launch_bounds__(128) bps_reduce_kernel(const double *REC, const double *rhs, double *GT, double *TT, int n, int64_t np,
-                                                         int64_t np_vec) {
-    __shared__ double sh[4][R * R + R][32];
+__global__ void __launch_bounds__(32 * BPS_RW) bps_reduce_kernel(const double *REC, const double *rhs, double *GT, double *TT, int n, int64_t np,
+                                                                 int64_t np_vec) {
+    __shared__ double sh[BPS_RW][R * R + R][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t tile = blockIdx.x;
     const double *rec = REC + (tile * np + BPS_FRONT) * NFA * 32 + lane;
@@ -44,8 +47,8 @@ __global__ void __launch_bounds__(128) bps_reduce_kernel(const double *REC, cons
     for (int a = 0; a < R; ++a) { t[a] = 0.0;
 #pragma unroll
         for (int c = 0; c < R; ++c) G[a][c] = 0.0; }
-    const int chunk = (n + 3) / 4, i0 = w * chunk, i1 = min(n, i0 + chunk);
-#pragma unroll 4
+    const int chunk = (n + BPS_RW - 1) / BPS_RW, i0 = w * chunk, i1 = min(n, i0 + chunk);
+#pragma unroll 8
     for (int i = i0; i < i1; ++i) {
         double u[R];
 #pragma unroll
@@ -65,8 +68,10 @@ __global__ void __launch_bounds__(128) bps_reduce_kernel(const double *REC, cons
 #pragma unroll
         for (int c = 0; c < R; ++c) sh[w][a * R + c][lane] = (c >= a) ? G[a][c] : G[c][a]; }
     __syncthreads();
-    for (int e = w; e < R * R + R; e += 4) {
-        const double s = (sh[0][e][lane] + sh[1][e][lane]) + (sh[2][e][lane] + sh[3][e][lane]);
+    for (int e = w; e < R * R + R; e += BPS_RW) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < BPS_RW; ++k) s += sh[k][e][lane];
         if (e < R * R) { if (GT) GT[(tile * (R * R) + e) * 32 + lane] = s; }
         else if (TT) TT[(tile * R + (e - R * R)) * 32 + lane] = s;
     }
@@ -524,7 +529,7 @@ __global__ void __launch_bounds__(64) bps_qr_pair_kernel(const double *REC, cons
 template <int L, int M, int R, int P>
 static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
     using D = BpsDims<L, M, R, P>;
-    bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)A->ntiles, 128, 0, c->stream>>>(A->REC->p, nullptr, F->GT->p, nullptr, A->n, A->np, 0);
+    bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)A->ntiles, 32 * BPS_RW, 0, c->stream>>>(A->REC->p, nullptr, F->GT->p, nullptr, A->n, A->np, 0);
     c->launches++;
     // ab_variant: 0 auto, 1 one warp per tile, 2 two warps of 16 systems, 3 pair mode.  Measured on B200 (n = 4096, (3,3,2,2)):
     //   systems    4,096   8,192   12,288   16,384 (config 3)   32,768   65,536
@@ -581,7 +586,7 @@ static int bps_stages(const ssm_ctx *c, size_t stage_bytes) {
 template <int L, int M, int R, int P>
 static int qt_shape(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs, int64_t npv) {
     using D = BpsDims<L, M, R, P>;
-    bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)F->ntiles, 128, 0, c->stream>>>(F->REC->p, rhs_in, nullptr, F->TT->p, F->n, F->np, npv);
+    bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)F->ntiles, 32 * BPS_RW, 0, c->stream>>>(F->REC->p, rhs_in, nullptr, F->TT->p, F->n, F->np, npv);
     c->launches++;
     if ((c->ab_variant == 0 && F->ntiles <= (int64_t)c->sm_count * c->group_max_per_sm) || c->ab_variant == 4) {
         using RG = GroupRing<R, D::NFQ, 1, +1, 1, D::NFA, D::NFO, 1>;
