@@ -74,10 +74,6 @@ __global__ void __launch_bounds__(32) ab_qt_kernel(const AbSolveArgs a, const in
     const double *qt = a.QT + tile * a.np * NFQ * 32 + lane;
     double *rhs = a.rhs + tile * a.np * 32 + lane;
     const double *rin = a.rhs_in + tile * a.np * 32 + lane;
-#ifdef SSM_DEBUG_RING
-    const int dbg_id = (a.unit >> 8) & 511; const bool dbg_on = gridDim.x == 4096 && (a.unit >> 8) > 0;
-    if (dbg_on && lane == 0) atomicMax(&ssm_time_dbg[2 * dbg_id], ~gtimer());
-#endif
     QtState<L> st;
     qt_prologue<L>(st, [&](int rho) { return rin[rho * 32]; });
     const int64_t nsteps = ((n + P - 1) / P) * P;
@@ -93,9 +89,6 @@ __global__ void __launch_bounds__(32) ab_qt_kernel(const AbSolveArgs a, const in
             if (k < n) rhs[(int64_t)k * 32] = c;
         }
     }
-#ifdef SSM_DEBUG_RING
-    if (dbg_on && lane == 0) atomicMax(&ssm_time_dbg[2 * dbg_id + 1], gtimer());
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -113,10 +106,6 @@ __global__ void __launch_bounds__(32) ab_backsolve_kernel(const AbSolveArgs a, c
     const double *vv = a.V + tile * a.np * (R > 0 ? R : 1) * 32 + lane;
     double *rhs = a.rhs + tile * a.np * 32 + lane;
     const double *rin = a.rhs_in + tile * a.np * 32 + lane;
-#ifdef SSM_DEBUG_RING
-    const int dbg_id = (a.unit >> 8) & 511; const bool dbg_on = gridDim.x == 4096 && (a.unit >> 8) > 0;
-    if (dbg_on && lane == 0) atomicMax(&ssm_time_dbg[2 * dbg_id], ~gtimer());
-#endif
     BsState<UB, R> st;
     bs_init<UB, R>(st);
     const int nblk = (n + PX - 1) / PX;
@@ -138,9 +127,6 @@ __global__ void __launch_bounds__(32) ab_backsolve_kernel(const AbSolveArgs a, c
             }
         }
     }
-#ifdef SSM_DEBUG_RING
-    if (dbg_on && lane == 0) atomicMax(&ssm_time_dbg[2 * dbg_id + 1], gtimer());
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -568,11 +554,3 @@ int launch_ab_tri(ssm_ctx *c, const ssm_ab *A, double *rhs, bool upper, bool uni
 
 }  // namespace ssm
 
-#ifdef SSM_DEBUG_RING
-extern "C" int ssm_debug_ring(unsigned long long *out8) { return (int)cudaMemcpyFromSymbol(out8, ssm::ssm_ring_dbg, 64); }
-extern "C" int ssm_debug_times(unsigned long long *out, int reset) {
-    int rc = (int)cudaMemcpyFromSymbol(out, ssm::ssm_time_dbg, sizeof(unsigned long long) * 1024);
-    if (reset) { static unsigned long long init[1024]; for (int i = 0; i < 512; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; } cudaMemcpyToSymbol(ssm::ssm_time_dbg, init, sizeof(init)); }
-    return rc;
-}
-#endif

@@ -10,29 +10,35 @@
 //   stage 2  abc_merge   cyclic reduction of the block-bidiagonal separator system F_c z_c + G_c z_{c+1} = h_c by QR of
 //                        [G_a; F_b], one warp per merge, log2(P) launches; abc_root solves the last block; abc_expand
 //                        recovers the eliminated separators top-down.
-//   stage 3  abc_bs      one warp per chunk: back-substitution of the interior unknowns (one 22-double record per row,
-//                        dot product with the lane-resident multipliers, butterfly reduction).
+//   stage 3  abc_bs      back-substitution of the interior unknowns.  Many chunks (>= ssm_ctx option "abc_tiled_min_chunks"):
+//                        abc_bs_tiled, ONE LANE PER CHUNK — stage 1 writes its R-row records interleaved over tiles of 32 chunks
+//                        (lane fastest, the batched layout of DESIGN.md section 3), a warp streams its tile through a bulk-async
+//                        ring and every lane runs the plain scalar recurrence of its own chunk.  Few chunks: abc_bs, one warp
+//                        per chunk with lanes = rows of a 32-row block (row-major records).
 //
 // The numpy restatement tests/emul/sof_reference.py documents the algebra and is the CPU check of this file.
 // Layout (row-major, one system): REC[n+pad][lp+1+r] = A[i, i-l .. i+u] | U[i, :];  V[n+pad][r];  lp = l + u.
+#include <algorithm>
 #include "../../include/ssm_rng.h"
 #include "fastmath.cuh"
 #include "ssm_internal.cuh"
+#include "stream_loader.cuh"
 
 namespace ssm {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int ABC_PAD = 128;
+constexpr int ABC_PAD = 512;    // identity rows behind the system: room for the regular chunk layout (abc_layout) and read-ahead
 constexpr int ABC_CPW = 4;      // chunks per warp in stage 1: chunk lengths change only at multiples of this
 
 struct AbcArgs {
     const double *REC, *V, *b;   // operands
-    double *FR;                  // [n][NC] R-row records, canonical column order
+    double *FR;                  // R-row records, canonical column order: [n][NC] (row-major) or tiled (see npf)
     double *E0;                  // [P][W][2W+1] level-0 reduced blocks [F | G | h]
     const double *Z;             // [(P+1)][W] separator solution (stage 3)
     double *x;
     int64_t n; int l, u; int P;
     int m0, jx, pw;              // chunk c has m0 + pw*(c < jx) rows: every chunk length is == lp (mod lp+1), see abc_layout()
+    int64_t npf;                 // tiled FR: records per tile of 32 chunks, FR[tile][npf][NC][32]
 };
 
 // Regular chunks: the system is padded with < lp+1 identity rows to n' = P*m0 + jx*pw so that every chunk eliminates a
@@ -59,11 +65,14 @@ struct AbcDims {
 // col = slot*GS + gl, slot = 0..CS-1, of the chunk's active block.  (GS = 32 is one chunk per warp; GS = 8 cuts the shuffle and
 // redundant-reflector cost per chunk by 4 — every shuffle instruction serves four chunks.)  All chunks of one warp have the
 // same length (abc_layout makes jx a multiple of 32/GS), so the groups stay in lock step.
-template <int LP, int R, int GS>
+// TILED: the R-row records go to FR[c / 32][k][field][c % 32]; a store instruction still writes whole 32-byte sectors (4 adjacent
+// chunks x 8 bytes per field), the eight warps that share a tile complete its 256-byte segments in L2.
+template <int LP, int R, int GS, bool TILED>
 __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     using D = AbcDims<LP, R>;
     constexpr int PW = D::PW, NR = D::NR, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, NF = D::NF, W = D::W;
     constexpr int CS = (NC + GS - 1) / GS, CPW = 32 / GS, RQ = R > 0 ? R : 1;
+    constexpr int FSTR = TILED ? 32 : 1, RSTR = TILED ? NC * 32 : NC;   // field / record strides of FR in doubles
     __shared__ double stage[4][CS][NR][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane % GS, grp = lane / GS;
     int c = (blockIdx.x * 4 + wib) * CPW + grp;
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         else if (isB[sl]) { ep[sl] = b0 + LP; estride[sl] = 1; }
         else { ep[sl] = zero; estride[sl] = 0; }
         nxt[sl] = (isB[sl] && brem <= 0) ? 0.0 : ep[sl][d[sl]];
-        fr[sl] = a.FR + r0 * NC + (isW[sl] ? 0 : col[sl]);
+        fr[sl] = (TILED ? a.FR + (int64_t)(c >> 5) * a.npf * NC * 32 + (c & 31) : a.FR + r0 * NC) + (isW[sl] ? 0 : col[sl]) * FSTR;
         emit[sl] = live && col[sl] < NC;
     }
     const double *vp = v0 + (int64_t)(LP + 1) * R;            // V row of the column entering after step 0
@@ -206,8 +215,8 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             // emit the finished row (canonical order: window entry of column k+t at position t)
 #pragma unroll
             for (int sl = 0; sl < CS; ++sl) {
-                if (emit[sl]) fr[sl][isW[sl] ? d[sl] : 0] = A[sl][PH];
-                fr[sl] += NC;
+                if (emit[sl]) fr[sl][(isW[sl] ? d[sl] : 0) * FSTR] = A[sl][PH];
+                fr[sl] += RSTR;
                 d[sl] = isW[sl] ? (d[sl] == 0 ? LP : d[sl] - 1) : 0;
             }
             // the window slides: local column k+LP+1 replaces the pivot column (fill region of every surviving row)
@@ -568,6 +577,107 @@ __global__ void __launch_bounds__(128) abc_bs_kernel(const AbcArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// stage 3, many chunks: ONE LANE PER CHUNK over the tiled records.  Row k of a chunk is
+//     x_k = ( h_k - C_k . z_sep - T_k . z_tail - sum_{t=1..LP} R[k,k+t] x_{k+t} - Ufinal[k,:] . S_{k+LP+1} ) / R[k,k],
+//     S_j = S_{j+1} + V[:,j] x_j  (tail sum over the chunk's columns >= j, started from the separator solution),
+// a scalar recurrence whose only serial part is one FMA and one multiply per row; the x window is a ring of LP+1 registers
+// indexed at compile time (the sweep is unrolled by LP+1, which divides every chunk's row count).  All 32 lanes do useful work
+// on every instruction (the lanes = rows kernel above spends ~35 warp instructions per ROW, this one ~3), so the stage is bound
+// by streaming the records: NC coalesced 256-byte fields per row and tile, pulled through a per-warp bulk-async ring.  The V rows
+// of the tail-sum update are the one gather (R doubles per lane and row, consecutive rows adjacent in memory): they do not depend
+// on the recurrence, so a block's rows are loaded one block (LP+1 rows) ahead.
+// ---------------------------------------------------------------------------------------------------------------
+template <int LP, int R>
+__global__ void __launch_bounds__(32) abc_bs_tiled_kernel(const AbcArgs a, const int nstage) {
+    using D = AbcDims<LP, R>;
+    constexpr int PW = D::PW, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, W = D::W;
+    constexpr int RQ = R > 0 ? R : 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    int c = (int)(tile * 32 + lane);
+    const bool live = c < a.P;
+    if (!live) c = a.P - 1;                                    // spare lanes of the last tile shadow chunk P-1 and store nothing
+    const int64_t r0 = chunk_start(a, c);
+    const int m = a.m0 + (c < a.jx ? PW : 0), nsteps = m - LP;  // the same for every chunk of a tile (abc_layout: jx % 32 == 0 or jx == P)
+    const int64_t r1 = r0 + m;
+    const int u = a.u, l = a.l;
+    const double *zc = a.Z + (int64_t)c * W, *zn = zc + W;
+    double *xloc = a.x + r0 + u;                               // x of local column 0
+    const int64_t xrows = live ? a.n - (r0 + u) : 0;           // local columns that exist in the caller's x
+    // separator columns: S_{c+1} = local columns m-LP .. m-1 (global r1-l .. r1+u-1); chunk 0 also owns S_0's real columns
+    if (live) {
+#pragma unroll
+        for (int t = 0; t < LP; ++t) {
+            const int64_t g = r1 - l + t;
+            if (g >= 0 && g < a.n) a.x[g] = zn[t];
+            const int64_t g0 = r0 - l + t;
+            if (c == 0 && g0 >= 0 && g0 < a.n) a.x[g0] = zc[t];
+        }
+    }
+    double zl[W > 0 ? W : 1];
+#pragma unroll
+    for (int t = 0; t < W; ++t) zl[t] = zc[t];
+    // xr[j mod PW] = x of local column j for the PW columns right of the current row; the slot of column k+PW is the one x_k takes
+    double xr[PW];
+#pragma unroll
+    for (int t = 0; t < LP; ++t) xr[t] = zn[t];                // columns nsteps .. nsteps+LP-1 (nsteps is a multiple of PW)
+    xr[LP] = 0.0;                                              // column m belongs to the next chunk: it is part of the incoming tail
+    double sb[RQ];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) sb[q] = R > 0 ? zn[LP + q] : 0.0;
+    RingLoader<NC, 0, 0, -1> ld;
+    ld.init(a.FR + (tile * a.npf + (nsteps - 1)) * NC * 32 + lane, nullptr, nullptr, smem, nstage, nsteps);
+    // vb[ph][:] = V row of local column kb+PW+ph, the column that leaves the band of row kb+ph (rows behind the system are zero)
+    const double *vloc = a.V + (r0 + u) * RQ;
+    double vb[PW][RQ], vnext[PW][RQ];
+    auto load_v = [&](double (&dst)[PW][RQ], const int kb) {
+#pragma unroll
+        for (int ph = 0; ph < PW; ++ph) {
+            const double *src = vloc + (int64_t)(kb + PW + ph) * R;
+            if constexpr (R == 2) { const double2 t = __ldg(reinterpret_cast<const double2 *>(src)); dst[ph][0] = t.x; dst[ph][1] = t.y; }
+            else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) dst[ph][q] = __ldg(src + q);
+            }
+        }
+    };
+    if (R > 0) load_v(vb, nsteps - PW);
+    int64_t g = 0;
+    for (int kb = nsteps - PW; kb >= 0; kb -= PW) {
+        if (R > 0 && kb >= PW) load_v(vnext, kb - PW);
+#pragma unroll
+        for (int ph = PW - 1; ph >= 0; --ph) {
+            const int k = kb + ph;
+            double rec[NC], d1[1], d2[1];
+            ld.acquire(g++, rec, d1, d2);
+            const double xold = xr[ph];                        // x of column k+PW leaves the band: the tail sum now covers columns >= k+LP+1
+#pragma unroll
+            for (int q = 0; q < R; ++q) sb[q] = fma(vb[ph][q], xold, sb[q]);
+            const double inv = fast_rcp(rec[0]);
+            double acc = rec[B0];
+#pragma unroll
+            for (int t = 0; t < LP; ++t) acc = fma(-rec[C0 + t], zl[t], acc);
+#pragma unroll
+            for (int q = 0; q < R; ++q) acc = fma(-rec[T0 + q], zl[LP + q], acc);
+#pragma unroll
+            for (int q = 0; q < R; ++q) acc = fma(-rec[G0 + q], sb[q], acc);
+#pragma unroll
+            for (int t = LP; t >= 1; --t) acc = fma(-rec[t], xr[(ph + t) % PW], acc);     // x_{k+1} last: the only term on the serial chain
+            const double x = acc * inv;
+            xr[ph] = x;
+            if (k < xrows) xloc[k] = x;
+        }
+        if (R > 0) {
+#pragma unroll
+            for (int ph = 0; ph < PW; ++ph)
+#pragma unroll
+                for (int q = 0; q < R; ++q) vb[ph][q] = vnext[ph][q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // boundary kernels: pack (reference layout -> row records), generator, residual
 // ---------------------------------------------------------------------------------------------------------------
 // rows n .. n+ABC_PAD-1 are identity rows (the chunked sweep pads the system to a multiple of its unroll period)
@@ -711,6 +821,8 @@ struct ssm_abc {
     DevBufPtr REC, V;                 // operands
     DevBufPtr FR, E, TOP, Z, tmp;     // workspace of the last solve (allocated on first use)
     int P = 0, m0 = 0, jx = 0;
+    bool tiled = false;               // layout of FR in the last solve
+    int64_t npf = 0;
 };
 
 #define SSM_CHECK_ARG(cond, msg) do { if (!(cond)) { set_error("%s: %s", __func__, msg); return SSM_E_ARG; } } while (0)
@@ -735,7 +847,8 @@ static int to_device(ssm_ctx *c, const double *p, size_t count, DevBufPtr &hold,
 }
 
 // regular chunk layout for P chunks: base length m0 = pw*q - 1, the first jx chunks get pw more rows; P is reduced until q >= 2
-static void abc_layout(int64_t n, int lp, int &P, int &m0, int &jx) {
+// `same` = how many consecutive chunks must share a length: the 4 chunks of a stage-1 warp, or the 32 of a stage-3 tile
+static void abc_layout(int64_t n, int lp, int same, int &P, int &m0, int &jx) {
     const int pw = lp + 1;
     if (P < 1) P = 1;
     while (P > 1 && (n / P + 1) / pw < 2) --P;
@@ -744,7 +857,7 @@ static void abc_layout(int64_t n, int lp, int &P, int &m0, int &jx) {
     m0 = (int)(pw * q - 1);
     const int64_t rem = n - (int64_t)P * m0;
     jx = rem > 0 ? (int)((rem + pw - 1) / pw) : 0;
-    jx = ((jx + ABC_CPW - 1) / ABC_CPW) * ABC_CPW;            // all chunks of one stage-1 warp have the same length
+    jx = ((jx + same - 1) / same) * same;
     if (jx > P) jx = P;
 }
 
@@ -763,11 +876,13 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     ssm_ctx *c = A->ctx;
     using D = AbcDims<LP, R>;
     constexpr int W = D::W, EW = 2 * W + 1, TW = 3 * W + 1;
-    AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P, A->m0, A->jx, LP + 1};
+    AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P, A->m0, A->jx, LP + 1, A->npf};
     const unsigned gchunks = (unsigned)((P + 3) / 4);
     constexpr int GS = 8;                                      // lanes per chunk in stage 1 (4 chunks per warp)
     static_assert(ABC_CPW == 32 / GS, "abc_layout must round jx to the chunks-per-warp of stage 1");
-    abc_qr_kernel<LP, R, GS><<<(unsigned)((P + 4 * ABC_CPW - 1) / (4 * ABC_CPW)), 128, 0, c->stream>>>(a);
+    const unsigned gqr = (unsigned)((P + 4 * ABC_CPW - 1) / (4 * ABC_CPW));
+    if (A->tiled) abc_qr_kernel<LP, R, GS, true><<<gqr, 128, 0, c->stream>>>(a);
+    else abc_qr_kernel<LP, R, GS, false><<<gqr, 128, 0, c->stream>>>(a);
     c->launches++;
     // levels: level t has cnt[t] blocks stored at E + eoff[t]; levels with more than 32 blocks are one launch each, the rest of the
     // tree (merges, root, expansions) is a single launch
@@ -803,7 +918,23 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
         abc_expand_kernel<W><<<(unsigned)((nmerge + 3) / 4), 128, 0, c->stream>>>(A->TOP->p + toff[t], A->Z->p, nmerge, 1 << t, P);
         c->launches++;
     }
-    abc_bs_kernel<LP, R><<<gchunks, 128, 0, c->stream>>>(a);
+    if (A->tiled) {
+        // ring depth: the shared memory an SM has, shared by the single-warp CTAs the grid puts on it (at most 16 stages)
+        using LD = RingLoader<D::NC, 0, 0, -1>;
+        const int64_t ntiles = (P + 31) / 32;
+        int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
+        per_sm = std::min<int64_t>(std::max<int64_t>(per_sm, 1), 16);
+        int ns = (int)((size_t)(208 * 1024) / (size_t)per_sm / (LD::STAGE_BYTES + 8));
+        ns = std::min(std::max(ns, 2), 16);
+        if (c->pipeline_stages > 0) ns = c->pipeline_stages;
+        const size_t smem = LD::smem_bytes(ns);
+        auto kern = abc_bs_tiled_kernel<LP, R>;
+        if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        kern<<<(unsigned)ntiles, 32, smem, c->stream>>>(a, ns);
+    } else {
+        abc_bs_kernel<LP, R><<<gchunks, 128, 0, c->stream>>>(a);
+    }
     c->launches++;
     SSM_CUDA(cudaGetLastError());
     return 0;
@@ -875,19 +1006,23 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     int P = nchunks > 0 ? nchunks : abc_default_chunks(A);
     int m0 = 0, jx = 0;
-    abc_layout(A->n, A->lp, P, m0, jx);
+    abc_layout(A->n, A->lp, ABC_CPW, P, m0, jx);
+    const bool tiled = P >= c->abc_tiled_min_chunks;          // P only shrinks for tiny n, where neither rounding changes it
+    if (tiled) abc_layout(A->n, A->lp, 32, P, m0, jx);
+    const int64_t npf = (int64_t)m0 + 1;                      // rows eliminated by a long chunk: m0 + (lp+1) - lp
     int rc = 0;
     if ((int64_t)P * m0 + (int64_t)jx * (A->lp + 1) > A->n + ABC_PAD - 8) { set_error("ssm_abc_solve: internal chunk layout exceeds the padding"); rc = SSM_E_ARG; }
     const int W = A->w;
-    if (!rc && (!A->FR || A->P != P)) {
+    if (!rc && (!A->FR || A->P != P || A->tiled != tiled || A->npf != npf)) {
         A->FR.reset(); A->E.reset(); A->TOP.reset(); A->Z.reset();
-        rc = dev_alloc(c->device, (size_t)(A->n + ABC_PAD + 40) * A->nc, false, c->stream, A->FR);
+        const size_t frcount = tiled ? (size_t)((P + 31) / 32) * (size_t)npf * (size_t)A->nc * 32 : (size_t)(A->n + ABC_PAD + 40) * A->nc;
+        rc = dev_alloc(c->device, frcount, tiled, c->stream, A->FR);   // tiled: spare lanes of the last tile are read, so they are defined
         if (!rc) rc = dev_alloc(c->device, (size_t)(2 * (int64_t)P + 64) * W * (2 * W + 1), true, c->stream, A->E);
         if (!rc) rc = dev_alloc(c->device, (size_t)((int64_t)P + 64) * W * (3 * W + 1), true, c->stream, A->TOP);
         if (!rc) rc = dev_alloc(c->device, (size_t)((int64_t)P + 2) * W, true, c->stream, A->Z);
         A->P = P;
     }
-    A->m0 = m0; A->jx = jx;
+    A->m0 = m0; A->jx = jx; A->tiled = tiled; A->npf = npf;
     DevBufPtr hb, hx;
     const double *db = nullptr; double *dx = nullptr;
     if (!rc) rc = to_device(c, b, (size_t)A->n, hb, &db);

@@ -151,6 +151,7 @@ int ssm_ctx_set_option(ssm_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "group_bytes")) c->group_bytes = value;
     else if (!strcmp(key, "group_smem_kb")) c->group_smem_kb = value;
     else if (!strcmp(key, "carveout_all")) c->carveout_all = value;
+    else if (!strcmp(key, "abc_tiled_min_chunks")) c->abc_tiled_min_chunks = value;
     else { set_error("unknown option '%s'", key); return SSM_E_ARG; }
     return 0;
 }
@@ -161,6 +162,7 @@ int ssm_ctx_get_option(ssm_ctx *c, const char *key, int *value) {
     else if (!strcmp(key, "group_max_per_sm")) *value = c->group_max_per_sm;
     else if (!strcmp(key, "group_bytes")) *value = c->group_bytes;
     else if (!strcmp(key, "group_smem_kb")) *value = c->group_smem_kb;
+    else if (!strcmp(key, "abc_tiled_min_chunks")) *value = c->abc_tiled_min_chunks;
     else if (!strcmp(key, "sm_count")) *value = c->sm_count;
     else { set_error("unknown option '%s'", key); return SSM_E_ARG; }
     return 0;
@@ -433,15 +435,9 @@ int ssm_abqr_solve(const ssm_abqr *F, const ssm_vec *b, ssm_vec *x) {
     SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, x));
     if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
     DeviceGuard g(F->ctx->device);
-#ifdef SSM_DEBUG_RING
-    static int dbg_seq = 0;
-    const int u1 = F->ntiles == 4096 ? ((++dbg_seq) << 8) : 0, u2 = F->ntiles == 4096 ? ((++dbg_seq) << 8) : 0;
-#else
-    const int u1 = 0, u2 = 0;
-#endif
-    AbSolveArgs q{F->RU->p, F->QT->p, F->V->p, b->d->p, x->d->p, F->n, F->np, u1};       // x <- Q'b
+    AbSolveArgs q{F->RU->p, F->QT->p, F->V->p, b->d->p, x->d->p, F->n, F->np, 0};        // x <- Q'b
     SSM_TRY(launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, q, true));
-    AbSolveArgs s{F->RU->p, F->QT->p, F->V->p, x->d->p, x->d->p, F->n, F->np, u2};       // x <- R \ x
+    AbSolveArgs s{F->RU->p, F->QT->p, F->V->p, x->d->p, x->d->p, F->n, F->np, 0};        // x <- R \ x
     return launch_ab_backsolve(F->ctx, F->l, F->u, F->r, F->ntiles, s);
 }
 int ssm_abqr_ldiv(const ssm_abqr *F, ssm_vec *b) { return ssm_abqr_solve(F, b, b); }

@@ -94,11 +94,6 @@ struct DirectLoader {
     }
 };
 
-#ifdef SSM_DEBUG_RING
-static __device__ unsigned long long ssm_ring_dbg[8];
-static __device__ unsigned long long ssm_time_dbg[2 * 512];   // [2*id] min start, [2*id+1] max end of launch id (globaltimer ns)
-__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }   // [0] mismatching stage reads, [1] tile, [2] step, [3] stream/field, [4] total checks
-#endif
 // ---- RingLoader ---------------------------------------------------------------------------------------
 template <int NF0, int NF1, int NF2, int DIR, int STR0 = NF0, int STR1 = NF1, int STR2 = NF2>
 struct RingLoader {
@@ -153,19 +148,6 @@ struct RingLoader {
         for (int f = 0; f < NF1; ++f) r1[f] = src[(NF0 + f) * 32];
 #pragma unroll
         for (int f = 0; f < NF2; ++f) r2[f] = src[(NF0 + NF1 + f) * 32];
-#ifdef SSM_DEBUG_RING_CONTENT
-        {
-            bool bad = false; int where = -1;
-#pragma unroll
-            for (int f = 0; f < NF0; ++f) if (__double_as_longlong(r0[f]) != __double_as_longlong((g0 + (int64_t)DIR * g * STR0 * 32)[f * 32 + lane])) { bad = true; where = f; }
-#pragma unroll
-            for (int f = 0; f < NF1; ++f) if (__double_as_longlong(r1[f]) != __double_as_longlong((g1 + (int64_t)DIR * g * STR1 * 32)[f * 32 + lane])) { bad = true; where = 100 + f; }
-#pragma unroll
-            for (int f = 0; f < NF2; ++f) if (__double_as_longlong(r2[f]) != __double_as_longlong((g2 + (int64_t)DIR * g * STR2 * 32)[f * 32 + lane])) { bad = true; where = 200 + f; }
-            if (lane == 0) atomicAdd(&ssm_ring_dbg[4], 1ull);
-            if (bad) { if (atomicAdd(&ssm_ring_dbg[0], 1ull) == 0) { ssm_ring_dbg[1] = blockIdx.x; ssm_ring_dbg[2] = (unsigned long long)g; ssm_ring_dbg[3] = (unsigned long long)where; ssm_ring_dbg[5] = (unsigned long long)nstage; ssm_ring_dbg[6] = NF0 * 1000 + NF1 * 10 + NF2; } }
-        }
-#endif
         __syncwarp();   // every lane has its copy in registers before the stage is re-armed
         fence_proxy_async();   // all lanes: their reads of this stage are performed before the re-arming bulk copy may write it
         if (lane == 0 && g + nstage < nsteps) issue(g + nstage, s);

@@ -45,9 +45,10 @@ def chunk_bounds(n, P):
     return [(c * n) // P for c in range(P + 1)]
 
 
-def regular_layout(n, lp, P):
+def regular_layout(n, lp, P, same=4):
     """The CUDA path's chunk layout (abc_layout in csrc/abc_kernels.cu): every chunk length is == lp (mod lp+1), so each chunk
-    eliminates a multiple of lp+1 columns; the system is padded with < lp+1 identity rows to n' = bounds[-1].
+    eliminates a multiple of lp+1 columns; the system is padded with identity rows to n' = bounds[-1].  `same` consecutive chunks
+    share a length: the 4 chunks one stage-1 warp sweeps, or the 32 chunks of a stage-3 tile (many chunks / tiled records).
     Returns (P, bounds)."""
     pw = lp + 1
     P = max(P, 1)
@@ -57,7 +58,7 @@ def regular_layout(n, lp, P):
     m0 = pw * q - 1
     rem = n - P * m0
     jx = (rem + pw - 1) // pw if rem > 0 else 0
-    jx = min(P, -(-jx // 4) * 4)            # chunk lengths change only at multiples of the 4 chunks one stage-1 warp sweeps
+    jx = min(P, -(-jx // same) * same)      # chunk lengths change only at multiples of `same`
     return P, [c * m0 + pw * min(c, jx) for c in range(P + 1)]
 
 

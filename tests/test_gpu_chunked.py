@@ -37,13 +37,21 @@ def _rand(rng, n, l, u, r):
 @pytest.mark.parametrize("n,l,u,r,P", [(64, 2, 2, 2, 4), (50, 1, 0, 1, 3), (97, 4, 4, 2, 4), (40, 2, 0, 2, 2), (33, 1, 1, 1, 1),
                                        (200, 3, 1, 2, 8), (500, 2, 2, 2, 16), (777, 4, 4, 2, 7), (130, 1, 1, 2, 5), (64, 2, 1, 1, 3),
                                        (300, 2, 2, 0, 6), (90, 1, 0, 0, 3), (128, 1, 1, 0, 4)])
-def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P, tiled):
+    """`tiled`: stage 3 with one lane per chunk over tile-interleaved records (the path large systems take) forced onto the
+    small case; otherwise one warp per chunk over row-major records."""
     rng = np.random.default_rng(n * 13 + P)
     bands, U, V, b = _rand(rng, n, l, u, r)
     A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
-    x = A.solve(b, nchunks=P)
+    default = ctx.get_option("abc_tiled_min_chunks")
+    ctx.set_option("abc_tiled_min_chunks", 1 if tiled else 1 << 30)
+    try:
+        x = A.solve(b, nchunks=P)
+    finally:
+        ctx.set_option("abc_tiled_min_chunks", default)
     lp, w = l + u, l + u + r
-    P, bnd = regular_layout(n, lp, P)
+    P, bnd = regular_layout(n, lp, P, same=32 if tiled else 4)
     assert A.chunks == P
     pb, pU, pV, pbv = pad_system(bands, U, V, b, l, u, bnd[-1])
     # stage 1 output: level-0 reduced blocks [F | G | h] per chunk, against the numpy restatement (rows may differ by
@@ -92,6 +100,12 @@ def test_chunked_matches_oracle_sweep(chunked, ctx, n, l, u, r, dist):
     A2 = chunked.LargeAlmostBandedMatrix(bands[0], (U[0], V[0]), (l, u), ctx=ctx)
     x2 = A2.solve(b[0], nchunks=A.chunks)
     assert np.array_equal(x2, xs)
+    # many short chunks: stage 3 runs one lane per chunk over tiled records (a partial last tile included)
+    assert ctx.get_option("abc_tiled_min_chunks") <= 2500
+    for P in (2500, 4096):
+        x3 = A.solve(bd, nchunks=P).cpu().numpy()
+        assert A.chunks >= ctx.get_option("abc_tiled_min_chunks")         # (P itself shrinks when the chunks would get too short)
+        assert np.linalg.norm(x3 - ox) / np.linalg.norm(ox) <= 1e-12, P
 
 
 def test_config4_full_size(chunked, ctx):

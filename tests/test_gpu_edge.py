@@ -39,6 +39,12 @@ def test_chunked_path_tiny_systems(ctx, l, u, r):
     for n in (1, 2, 3, 5, 9, 17, 18, 40):
         bands, U, V, b = oracle.ab_generate(n, l, u, r, 1, seed=4)
         A = chunked.LargeAlmostBandedMatrix(bands[0], (U[0], V[0]), (l, u), ctx=ctx)
-        x = A.solve(b[0])
         x0 = np.linalg.solve(dense(bands[0], U[0], V[0], l, u), b[0])
-        assert np.linalg.norm(x - x0) <= 1e-12 * np.linalg.norm(x0), (n, A.chunks)
+        default = ctx.get_option("abc_tiled_min_chunks")
+        try:
+            for min_chunks in (default, 1):                 # 1: the tiled stage 3 of large systems, forced onto the tiny one
+                ctx.set_option("abc_tiled_min_chunks", min_chunks)
+                x = A.solve(b[0])
+                assert np.linalg.norm(x - x0) <= 1e-12 * np.linalg.norm(x0), (n, A.chunks, min_chunks)
+        finally:
+            ctx.set_option("abc_tiled_min_chunks", default)
