@@ -89,11 +89,25 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     const double *zero = a.V + (a.n + 8) * RQ;                // a V pad row: always 0.0
 
     // column roles of this lane's slots
+    // COLOC: the R generator columns sit in ONE lane (consecutive slots of lane G0 % GS) instead of R neighbouring lanes, so the
+    // fill value of a surviving row is formed where the generator lives and travels in one shuffle instead of R (the LSU pipe
+    // that executes shuffles is the busiest unit of this kernel).  Generator column q > 0 trades places with whatever canonical
+    // column (or spare position) its new position held.
+    constexpr bool COLOC = R >= 2 && (G0 / GS + R <= CS);
+    constexpr int GLANE = G0 % GS, GSLOT = G0 / GS;
     bool isW[CS], isG[CS], isC[CS], isT[CS], isB[CS];
     int col[CS];
 #pragma unroll
     for (int sl = 0; sl < CS; ++sl) {
         col[sl] = sl * GS + gl;
+        if (COLOC) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) {
+                const int moved = (GSLOT + q) * GS + GLANE;       // position that now holds generator column q
+                if (sl * GS + gl == moved) col[sl] = G0 + q;
+                else if (sl * GS + gl == G0 + q) col[sl] = moved;
+            }
+        }
         isW[sl] = col[sl] < PW; isG[sl] = col[sl] >= G0 && col[sl] < C0; isC[sl] = col[sl] >= C0 && col[sl] < T0;
         isT[sl] = col[sl] >= T0 && col[sl] < B0; isB[sl] = col[sl] == B0;
     }
@@ -104,7 +118,9 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         for (int s = 0; s < NR; ++s) A[sl][s] = 0.0;
 
     // generator value q of row slot s, broadcast inside the group
-    auto gen_of = [&](int s, int q) -> double { return __shfl_sync(FULL, A[(G0 + q) / GS][s], (G0 + q) % GS, GS); };
+    auto gen_of = [&](int s, int q) -> double {
+        return COLOC ? __shfl_sync(FULL, A[GSLOT + q][s], GLANE, GS) : __shfl_sync(FULL, A[(G0 + q) / GS][s], (G0 + q) % GS, GS);
+    };
 
     // ---- prologue: band rows 0..LP-1 (slot = row) and the R tail rows (slots PW..) ----
 #pragma unroll
@@ -224,8 +240,14 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             for (int s = 0; s < NR; ++s) {
                 if (s == PH) continue;
                 double f = 0.0;
+                if (COLOC) {
 #pragma unroll
-                for (int q = 0; q < R; ++q) f = fma(gen_of(s, q), vn[q], f);
+                    for (int q = 0; q < R; ++q) f = fma(A[GSLOT + q][s], vn[q], f);     // meaningful in the generator lane only
+                    f = __shfl_sync(FULL, f, GLANE, GS);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) f = fma(gen_of(s, q), vn[q], f);
+                }
                 if (gl == pl) A[ps][s] = f;
             }
         }
