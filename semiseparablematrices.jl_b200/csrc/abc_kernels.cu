@@ -11,9 +11,9 @@
 //                        [G_a; F_b], one warp per merge, log2(P) launches; abc_root solves the last block; abc_expand
 //                        recovers the eliminated separators top-down.
 //   stage 3  abc_bs      back-substitution of the interior unknowns.  Many chunks (>= ssm_ctx option "abc_tiled_min_chunks"):
-//                        abc_bs_tiled, ONE LANE PER CHUNK — stage 1 writes its R-row records interleaved over tiles of 32 chunks
-//                        (lane fastest, the batched layout of DESIGN.md section 3), a warp streams its tile through a bulk-async
-//                        ring and every lane runs the plain scalar recurrence of its own chunk.  Few chunks: abc_bs, one warp
+//                        abc_bs_tiled, ONE LANE PER CHUNK — stage 1 writes its R-row records interleaved over mini-tiles of 4
+//                        chunks (one stage-1 warp), a stage-3 warp streams eight mini-tiles through a bulk-async ring and every
+//                        lane runs the plain scalar recurrence of its own chunk.  Few chunks: abc_bs, one warp
 //                        per chunk with lanes = rows of a 32-row block (row-major records).
 //
 // The numpy restatement tests/emul/sof_reference.py documents the algebra and is the CPU check of this file.
@@ -38,7 +38,7 @@ struct AbcArgs {
     double *x;
     int64_t n; int l, u; int P;
     int m0, jx, pw;              // chunk c has m0 + pw*(c < jx) rows: every chunk length is == lp (mod lp+1), see abc_layout()
-    int64_t npf;                 // tiled FR: records per tile of 32 chunks, FR[tile][npf][NC][32]
+    int64_t npf;                 // tiled FR: records per mini-tile of 4 chunks, FR[c / 4][npf][NC][c % 4]
 };
 
 // Regular chunks: the system is padded with < lp+1 identity rows to n' = P*m0 + jx*pw so that every chunk eliminates a
@@ -65,14 +65,15 @@ struct AbcDims {
 // col = slot*GS + gl, slot = 0..CS-1, of the chunk's active block.  (GS = 32 is one chunk per warp; GS = 8 cuts the shuffle and
 // redundant-reflector cost per chunk by 4 — every shuffle instruction serves four chunks.)  All chunks of one warp have the
 // same length (abc_layout makes jx a multiple of 32/GS), so the groups stay in lock step.
-// TILED: the R-row records go to FR[c / 32][k][field][c % 32]; a store instruction still writes whole 32-byte sectors (4 adjacent
-// chunks x 8 bytes per field), the eight warps that share a tile complete its 256-byte segments in L2.
+// TILED: the R-row records are interleaved over the FOUR chunks this warp sweeps, FR[c / 4][k][field][c % 4]: one store
+// instruction (8 lanes = 8 fields, 4 chunks each) then covers 256 contiguous bytes — 2-3 cache lines against ~5 for row-major
+// records and 8 for 32-wide tiles — which matters because the LSU pipe (shuffles + global accesses) is this kernel's busiest unit.
 template <int LP, int R, int GS, bool TILED>
 __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     using D = AbcDims<LP, R>;
     constexpr int PW = D::PW, NR = D::NR, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, NF = D::NF, W = D::W;
     constexpr int CS = (NC + GS - 1) / GS, CPW = 32 / GS, RQ = R > 0 ? R : 1;
-    constexpr int FSTR = TILED ? 32 : 1, RSTR = TILED ? NC * 32 : NC;   // field / record strides of FR in doubles
+    constexpr int FSTR = TILED ? 4 : 1, RSTR = TILED ? NC * 4 : NC;     // field / record strides of FR in doubles
     __shared__ double stage[4][CS][NR][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane % GS, grp = lane / GS;
     int c = (blockIdx.x * 4 + wib) * CPW + grp;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         else if (isB[sl]) { ep[sl] = b0 + LP; estride[sl] = 1; }
         else { ep[sl] = zero; estride[sl] = 0; }
         nxt[sl] = (isB[sl] && brem <= 0) ? 0.0 : ep[sl][d[sl]];
-        fr[sl] = (TILED ? a.FR + (int64_t)(c >> 5) * a.npf * NC * 32 + (c & 31) : a.FR + r0 * NC) + (isW[sl] ? 0 : col[sl]) * FSTR;
+        fr[sl] = (TILED ? a.FR + (int64_t)(c >> 2) * a.npf * NC * 4 + (c & 3) : a.FR + r0 * NC) + (isW[sl] ? 0 : col[sl]) * FSTR;
         emit[sl] = live && col[sl] < NC;
     }
     const double *vp = v0 + (int64_t)(LP + 1) * R;            // V row of the column entering after step 0
@@ -605,10 +606,55 @@ __global__ void __launch_bounds__(128) abc_bs_kernel(const AbcArgs a) {
 // a scalar recurrence whose only serial part is one FMA and one multiply per row; the x window is a ring of LP+1 registers
 // indexed at compile time (the sweep is unrolled by LP+1, which divides every chunk's row count).  All 32 lanes do useful work
 // on every instruction (the lanes = rows kernel above spends ~35 warp instructions per ROW, this one ~3), so the stage is bound
-// by streaming the records: NC coalesced 256-byte fields per row and tile, pulled through a per-warp bulk-async ring.  The V rows
+// by streaming the records: NC x 32 contiguous bytes per row and mini-tile of 4 chunks, pulled through a per-warp bulk-async ring
+// (a warp = 32 chunks = 8 mini-tiles).  The V rows
 // of the tail-sum update are the one gather (R doubles per lane and row, consecutive rows adjacent in memory): they do not depend
 // on the recurrence, so a block's rows are loaded one block (LP+1 rows) ahead.
 // ---------------------------------------------------------------------------------------------------------------
+// The ring that feeds it: a stage holds ONE row of the warp's eight mini-tiles (8 x NC x 4 doubles); eight lanes issue one
+// bulk-async copy each (NC*32 bytes, contiguous in the mini-tile's stream) onto the stage's mbarrier.  Mini-tile blocks are
+// padded by 4 doubles in shared memory so that a half warp's 8-byte reads fall into distinct banks.
+template <int NC>
+struct MiniTileRing {
+    static constexpr int MT_STRIDE = NC * 4 + 4, STAGE_DOUBLES = 8 * MT_STRIDE;
+    static constexpr uint32_t ROW_BYTES = NC * 32;
+    static __host__ __device__ size_t smem_bytes(int nstage) { return (size_t)nstage * STAGE_DOUBLES * 8 + (size_t)nstage * 8; }
+    const double *src;            // lanes 0..7: row 0 of mini-tile `lane` of this tile
+    double *ring; uint32_t bar0; int nstage, lane; int64_t nsteps, last;
+    int cur = 0; uint32_t parity = 0;
+    // step g reads row last - g
+    __device__ __forceinline__ void issue(int64_t g, int s) {
+        const uint32_t bar = bar0 + 8u * s;
+        if (lane == 0) mbar_expect_tx(bar, 8 * ROW_BYTES);
+        __syncwarp();
+        if (lane < 8) bulk_g2s(smem_u32(ring + (size_t)s * STAGE_DOUBLES + lane * MT_STRIDE), src + (last - g) * NC * 4, ROW_BYTES, bar);
+    }
+    __device__ __forceinline__ void init(const double *fr, int64_t tile, int64_t npf, void *smem, int nst, int64_t total_steps) {
+        lane = threadIdx.x & 31; nstage = nst; nsteps = total_steps; last = total_steps - 1;
+        src = fr + (tile * 8 + (lane & 7)) * npf * NC * 4;
+        ring = reinterpret_cast<double *>(smem);
+        bar0 = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)nst * STAGE_DOUBLES * 8);
+        if (lane == 0) {
+            for (int s = 0; s < nst; ++s) mbar_init(bar0 + 8u * s, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        for (int g = 0; g < nst && g < total_steps; ++g) issue(g, g);
+    }
+    // steps must be acquired in order g = 0, 1, 2, ...; rec[f] = field f of this lane's chunk
+    __device__ __forceinline__ void acquire(int64_t g, double *rec) {
+        const int s = cur;
+        mbar_wait(bar0 + 8u * s, parity);
+        const double *p = ring + (size_t)s * STAGE_DOUBLES + (lane >> 2) * MT_STRIDE + (lane & 3);
+#pragma unroll
+        for (int f = 0; f < NC; ++f) rec[f] = p[f * 4];
+        __syncwarp();                 // every lane has its copy in registers before the stage is re-armed
+        fence_proxy_async();          // ... and those reads are ordered before the re-arming bulk copies (see stream_loader.cuh)
+        if (g + nstage < nsteps) issue(g + nstage, s);
+        if (++cur == nstage) { cur = 0; parity ^= 1u; }
+    }
+};
+
 template <int LP, int R>
 __global__ void __launch_bounds__(32) abc_bs_tiled_kernel(const AbcArgs a, const int nstage) {
     using D = AbcDims<LP, R>;
@@ -648,8 +694,8 @@ __global__ void __launch_bounds__(32) abc_bs_tiled_kernel(const AbcArgs a, const
     double sb[RQ];
 #pragma unroll
     for (int q = 0; q < RQ; ++q) sb[q] = R > 0 ? zn[LP + q] : 0.0;
-    RingLoader<NC, 0, 0, -1> ld;
-    ld.init(a.FR + (tile * a.npf + (nsteps - 1)) * NC * 32 + lane, nullptr, nullptr, smem, nstage, nsteps);
+    MiniTileRing<NC> ld;
+    ld.init(a.FR, tile, a.npf, smem, nstage, nsteps);
     // vb[ph][:] = V row of local column kb+PW+ph, the column that leaves the band of row kb+ph (rows behind the system are zero)
     const double *vloc = a.V + (r0 + u) * RQ;
     double vb[PW][RQ], vnext[PW][RQ];
@@ -671,8 +717,8 @@ __global__ void __launch_bounds__(32) abc_bs_tiled_kernel(const AbcArgs a, const
 #pragma unroll
         for (int ph = PW - 1; ph >= 0; --ph) {
             const int k = kb + ph;
-            double rec[NC], d1[1], d2[1];
-            ld.acquire(g++, rec, d1, d2);
+            double rec[NC];
+            ld.acquire(g++, rec);
             const double xold = xr[ph];                        // x of column k+PW leaves the band: the tail sum now covers columns >= k+LP+1
 #pragma unroll
             for (int q = 0; q < R; ++q) sb[q] = fma(vb[ph][q], xold, sb[q]);
@@ -942,11 +988,11 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     }
     if (A->tiled) {
         // ring depth: the shared memory an SM has, shared by the single-warp CTAs the grid puts on it (at most 16 stages)
-        using LD = RingLoader<D::NC, 0, 0, -1>;
+        using LD = MiniTileRing<D::NC>;
         const int64_t ntiles = (P + 31) / 32;
         int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
         per_sm = std::min<int64_t>(std::max<int64_t>(per_sm, 1), 16);
-        int ns = (int)((size_t)(208 * 1024) / (size_t)per_sm / (LD::STAGE_BYTES + 8));
+        int ns = (int)((size_t)(208 * 1024) / (size_t)per_sm / (LD::STAGE_DOUBLES * 8 + 8));
         ns = std::min(std::max(ns, 2), 16);
         if (c->pipeline_stages > 0) ns = c->pipeline_stages;
         const size_t smem = LD::smem_bytes(ns);
