@@ -101,11 +101,15 @@ def test_chunked_matches_oracle_sweep(chunked, ctx, n, l, u, r, dist):
     x2 = A2.solve(b[0], nchunks=A.chunks)
     assert np.array_equal(x2, xs)
     # many short chunks: stage 3 runs one lane per chunk over tiled records (a partial last tile included)
-    assert ctx.get_option("abc_tiled_min_chunks") <= 2500
-    for P in (2500, 4096):
-        x3 = A.solve(bd, nchunks=P).cpu().numpy()
-        assert A.chunks >= ctx.get_option("abc_tiled_min_chunks")         # (P itself shrinks when the chunks would get too short)
-        assert np.linalg.norm(x3 - ox) / np.linalg.norm(ox) <= 1e-12, P
+    default = ctx.get_option("abc_tiled_min_chunks")
+    ctx.set_option("abc_tiled_min_chunks", 2048)
+    try:
+        for P in (2500, 4096):
+            x3 = A.solve(bd, nchunks=P).cpu().numpy()
+            assert A.chunks >= 2048                            # (P itself shrinks when the chunks would get too short)
+            assert np.linalg.norm(x3 - ox) / np.linalg.norm(ox) <= 1e-12, P
+    finally:
+        ctx.set_option("abc_tiled_min_chunks", default)
 
 
 def test_config4_full_size(chunked, ctx):
