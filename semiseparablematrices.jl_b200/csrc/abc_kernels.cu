@@ -68,14 +68,38 @@ struct AbcDims {
 // TILED: the R-row records are interleaved over the FOUR chunks this warp sweeps, FR[c / 4][k][field][c % 4]: one store
 // instruction (8 lanes = 8 fields, 4 chunks each) then covers 256 contiguous bytes — 2-3 cache lines against ~5 for row-major
 // records and 8 for 32-wide tiles — which matters because the LSU pipe (shuffles + global accesses) is this kernel's busiest unit.
+#ifndef ABC_STAGE1_RING
+#define ABC_STAGE1_RING 1
+#endif
+// Shared memory of stage 1 (dynamic).  Each warp owns one region: a ring of NSTG stages, a stage = the PW operand rows and the PW
+// V rows that enter during one block of PW steps, for each of the warp's chunks (one bulk-async copy per chunk and stream; the
+// copies start at the 16-byte boundary at or below the first row, hence the 16 spare bytes and a per-block shift of 0 or 1
+// doubles).  The same region is the transposition buffer of the epilogue once the ring has drained.
+template <int LP, int R, int GS>
+struct AbcQrSmem {
+    using D = AbcDims<LP, R>;
+    static constexpr int CPW = 32 / GS, CS = (D::NC + GS - 1) / GS, NSTG = 3;
+    static constexpr int CBR = ((D::PW * D::NF * 8 + 15) / 16) * 16 + 16;                     // bytes per chunk and stage: operand rows
+    static constexpr int CBV = R > 0 ? ((D::PW * R * 8 + 15) / 16) * 16 + 16 : 0;             // ... V rows
+    static constexpr int SGB = CPW * (CBR + CBV);                                            // bytes per stage
+    static constexpr int EPI = CS * D::NR * 32 * 8;                                          // epilogue buffer of one warp
+    static constexpr int WREG = ((((ABC_STAGE1_RING ? NSTG * SGB : 0) > EPI ? NSTG * SGB : EPI) + 127) / 128) * 128;
+    static constexpr int BARS = 4 * WREG, ZERO = BARS + 4 * NSTG * 8, TOTAL = ZERO + 16;
+};
+
 template <int LP, int R, int GS, bool TILED>
 __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     using D = AbcDims<LP, R>;
+    using SM = AbcQrSmem<LP, R, GS>;
     constexpr int PW = D::PW, NR = D::NR, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, NF = D::NF, W = D::W;
     constexpr int CS = (NC + GS - 1) / GS, CPW = 32 / GS, RQ = R > 0 ? R : 1;
     constexpr int FSTR = TILED ? 4 : 1, RSTR = TILED ? NC * 4 : NC;     // field / record strides of FR in doubles
-    __shared__ double stage[4][CS][NR][32];
+    constexpr bool RING = ABC_STAGE1_RING != 0;
+    constexpr int NSTG = SM::NSTG;
+    extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane % GS, grp = lane / GS;
+    unsigned char *wreg = smem + wib * SM::WREG;                       // this warp's ring / epilogue region
+    double (*stage)[NR][32] = reinterpret_cast<double (*)[NR][32]>(wreg);
     int c = (blockIdx.x * 4 + wib) * CPW + grp;
     if ((blockIdx.x * 4 + wib) * CPW >= a.P) return;
     const bool live = c < a.P;                                // a partial last warp repeats chunk P-1 in its spare groups (no stores)
@@ -88,6 +112,49 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     const double *b0 = a.b + r0;
     const int64_t brows = a.n - r0;                           // rows of b that exist from r0 on (pad rows have b = 0)
     const double *zero = a.V + (a.n + 8) * RQ;                // a V pad row: always 0.0
+    // ---- ring of entering rows (RING): lanes 0..CPW-1 copy the operand rows of the warp's chunks, lanes CPW..2CPW-1 their V rows ----
+    const uint32_t bar0 = smem_u32(smem + SM::BARS + wib * NSTG * 8);
+    double *zero_s = reinterpret_cast<double *>(smem + SM::ZERO);
+    const int nblk_ring = nsteps / PW + 1;                    // the row fetched ahead at the last step belongs to one more block
+    const double *csrc = nullptr;                             // issuing lanes: first row / V row of block 0 of "their" chunk
+    if (RING) {
+        int cc = (blockIdx.x * 4 + wib) * CPW + (lane % CPW);
+        if (cc >= a.P) cc = a.P - 1;
+        const int64_t rc = chunk_start(a, cc);
+        csrc = lane < CPW ? a.REC + (rc + LP) * NF : a.V + (rc + u + LP + 1) * RQ;
+        if (lane == 0) {
+            for (int st = 0; st < NSTG; ++st) mbar_init(bar0 + 8u * st, 1);
+            fence_barrier_init();
+            *zero_s = 0.0;
+        }
+        __syncwarp();
+    }
+    auto ring_issue = [&](const int j, const int st) {         // block j into stage st (whole warp calls)
+        const uint32_t bar = bar0 + 8u * st;
+        if (lane == 0) mbar_expect_tx(bar, SM::SGB);
+        __syncwarp();
+        if (lane < CPW) {
+            const double *src = csrc + (int64_t)j * PW * NF;
+            bulk_g2s(smem_u32(wreg + st * SM::SGB + lane * SM::CBR), reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15), SM::CBR, bar);
+        } else if (R > 0 && lane < 2 * CPW) {
+            const double *src = csrc + (int64_t)j * PW * R;
+            bulk_g2s(smem_u32(wreg + st * SM::SGB + CPW * SM::CBR + (lane - CPW) * SM::CBV), reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15), SM::CBV, bar);
+        }
+    };
+    // this lane's view of block j in stage st: first operand row / first V row of its own chunk
+    auto ring_rec = [&](const int j, const int st) -> const double * {
+        const uintptr_t g = reinterpret_cast<uintptr_t>(rec0 + (int64_t)(LP + j * PW) * NF);
+        return reinterpret_cast<const double *>(wreg + st * SM::SGB + grp * SM::CBR + (g & 15));
+    };
+    auto ring_v = [&](const int j, const int st) -> const double * {
+        const uintptr_t g = reinterpret_cast<uintptr_t>(v0 + (int64_t)(LP + 1 + j * PW) * R);
+        return reinterpret_cast<const double *>(wreg + st * SM::SGB + CPW * SM::CBR + grp * SM::CBV + (g & 15));
+    };
+    int rstage = 0, rblock = 0; uint32_t rparity = 0;          // stage / block being read, parity of that stage's barrier
+    if (RING) {
+        for (int j = 0; j < NSTG && j < nblk_ring; ++j) ring_issue(j, j);
+        mbar_wait(bar0, 0);
+    }
 
     // column roles of this lane's slots
     // COLOC: the R generator columns sit in ONE lane (consecutive slots of lane G0 % GS) instead of R neighbouring lanes, so the
@@ -162,19 +229,26 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     // Per-slot stream of the entering rows: window / generator columns walk the row records, the rhs column walks b, all other
     // columns re-read one zero, so the load needs no predicate.  A window column reads field d = (col - k) mod PW, which is also
     // the position of its entry in the emitted record.
+    // With RING the window / generator columns read the ring (their pointer is re-based at every block), the rhs column keeps its
+    // own global load (b has no padding to copy from), everything else reads a zero in shared memory.
     int d[CS]; const double *ep[CS]; int estride[CS]; double nxt[CS]; double *fr[CS]; bool emit[CS];
     int64_t brem = brows - LP;                                // rows of b left for the rhs column
+    bool hasB = false;
+#pragma unroll
+    for (int sl = 0; sl < CS; ++sl) hasB = hasB || isB[sl];
+    const double *bp = b0 + LP;
+    double bnx = (hasB && brem > 0) ? *bp : 0.0;
 #pragma unroll
     for (int sl = 0; sl < CS; ++sl) {
         d[sl] = isW[sl] ? col[sl] : 0;                        // phase 0
-        if (isW[sl] || isG[sl]) { ep[sl] = rec0 + (int64_t)LP * NF + (isG[sl] ? PW + col[sl] - G0 : 0); estride[sl] = NF; }
-        else if (isB[sl]) { ep[sl] = b0 + LP; estride[sl] = 1; }
-        else { ep[sl] = zero; estride[sl] = 0; }
-        nxt[sl] = (isB[sl] && brem <= 0) ? 0.0 : ep[sl][d[sl]];
+        if (isW[sl] || isG[sl]) { ep[sl] = (RING ? ring_rec(0, 0) : rec0 + (int64_t)LP * NF) + (isG[sl] ? PW + col[sl] - G0 : 0); estride[sl] = NF; }
+        else if (isB[sl] && !RING) { ep[sl] = b0 + LP; estride[sl] = 1; }
+        else { ep[sl] = RING ? zero_s : zero; estride[sl] = 0; }
+        nxt[sl] = (!RING && isB[sl] && brem <= 0) ? 0.0 : ep[sl][d[sl]];
         fr[sl] = (TILED ? a.FR + (int64_t)(c >> 2) * a.npf * NC * 4 + (c & 3) : a.FR + r0 * NC) + (isW[sl] ? 0 : col[sl]) * FSTR;
         emit[sl] = live && col[sl] < NC;
     }
-    const double *vp = v0 + (int64_t)(LP + 1) * R;            // V row of the column entering after step 0
+    const double *vp = RING ? ring_v(0, 0) : v0 + (int64_t)(LP + 1) * R;            // V row of the column entering after step 0
     double vnx[RQ];
 #pragma unroll
     for (int q = 0; q < R; ++q) vnx[q] = vp[q];
@@ -186,15 +260,31 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             const int pl = PH % GS, ps = PH / GS;             // lane-in-group / column slot of the pivot column
             --brem;
 #pragma unroll
+            for (int sl = 0; sl < CS; ++sl) A[sl][es] = (RING && isB[sl]) ? bnx : nxt[sl];
+            if (RING) {
+                ++bp;
+                bnx = (hasB && brem > 0) ? *bp : 0.0;
+            }
+            if (RING && PH == PW - 1) {
+                // the rows fetched from here on belong to the next block: wait for its stage, hand this block's stage back
+                const int old = rstage;
+                if (++rstage == NSTG) { rstage = 0; rparity ^= 1u; }
+                ++rblock;
+                mbar_wait(bar0 + 8u * rstage, rparity);
+                __syncwarp();                                 // every lane's reads of the old stage are in registers ...
+                fence_proxy_async();                          // ... and ordered before the bulk copies that re-arm it
+                if (rblock - 1 + NSTG < nblk_ring) ring_issue(rblock - 1 + NSTG, old);
+            }
+#pragma unroll
             for (int sl = 0; sl < CS; ++sl) {
-                A[sl][es] = nxt[sl];
                 // prefetch the row entering at the next step (rows past the chunk are the next chunk's or the identity pad)
-                ep[sl] += estride[sl];
+                if (RING && PH == PW - 1) { if (isW[sl] || isG[sl]) ep[sl] = ring_rec(rblock, rstage) + (isG[sl] ? PW + col[sl] - G0 : 0); }
+                else ep[sl] += estride[sl];
                 const int dn = isW[sl] ? (d[sl] == 0 ? LP : d[sl] - 1) : 0;
-                nxt[sl] = (isB[sl] && brem <= 0) ? 0.0 : ep[sl][dn];
+                nxt[sl] = (!RING && isB[sl] && brem <= 0) ? 0.0 : ep[sl][dn];
             }
             double vn[RQ];
-            vp += R;
+            if (RING && PH == PW - 1) vp = ring_v(rblock, rstage); else vp += R;
 #pragma unroll
             for (int q = 0; q < R; ++q) { vn[q] = vnx[q]; vnx[q] = vp[q]; }   // one step ahead
             // reflector from the pivot column, LinearAlgebra.reflector! convention
@@ -257,7 +347,7 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
 #pragma unroll
     for (int sl = 0; sl < CS; ++sl)
 #pragma unroll
-        for (int s = 0; s < NR; ++s) stage[wib][sl][s][lane] = A[sl][s];
+        for (int s = 0; s < NR; ++s) stage[sl][s][lane] = A[sl][s];       // (the ring has drained: every issued block was waited for)
     __syncwarp();
     if (!live) return;
     double *E = a.E0 + (int64_t)c * W * (2 * W + 1);
@@ -274,7 +364,7 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         if (dst >= 0) {
             for (int row = 0; row < W; ++row) {
                 const int slot = row < LP ? (m - LP + row) % PW : PW + (row - LP);
-                E[row * (2 * W + 1) + dst] = stage[wib][sl][slot][lane];
+                E[row * (2 * W + 1) + dst] = stage[sl][slot][lane];
             }
         }
     }
@@ -949,8 +1039,17 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     constexpr int GS = 8;                                      // lanes per chunk in stage 1 (4 chunks per warp)
     static_assert(ABC_CPW == 32 / GS, "abc_layout must round jx to the chunks-per-warp of stage 1");
     const unsigned gqr = (unsigned)((P + 4 * ABC_CPW - 1) / (4 * ABC_CPW));
-    if (A->tiled) abc_qr_kernel<LP, R, GS, true><<<gqr, 128, 0, c->stream>>>(a);
-    else abc_qr_kernel<LP, R, GS, false><<<gqr, 128, 0, c->stream>>>(a);
+    {
+        constexpr int smem = AbcQrSmem<LP, R, GS>::TOTAL;
+        auto launch = [&](auto kern) -> int {
+            if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            kern<<<gqr, 128, smem, c->stream>>>(a);
+            return 0;
+        };
+        if (A->tiled) SSM_TRY(launch(abc_qr_kernel<LP, R, GS, true>));
+        else SSM_TRY(launch(abc_qr_kernel<LP, R, GS, false>));
+    }
     c->launches++;
     // levels: level t has cnt[t] blocks stored at E + eoff[t]; levels with more than 32 blocks are one launch each, the rest of the
     // tree (merges, root, expansions) is a single launch
