@@ -1178,7 +1178,9 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
     if (tiled) abc_layout(A->n, A->lp, 32, P, m0, jx);
     const int64_t npf = (int64_t)m0 + 1;                      // rows eliminated by a long chunk: m0 + (lp+1) - lp
     int rc = 0;
-    if ((int64_t)P * m0 + (int64_t)jx * (A->lp + 1) > A->n + ABC_PAD - 8) { set_error("ssm_abc_solve: internal chunk layout exceeds the padding"); rc = SSM_E_ARG; }
+    // rows the sweeps may touch behind the padded system: one more block of lp+1 operand rows (stage-1 ring, fetched ahead at the
+    // last step) and the V rows of u + lp + 2 further columns, plus the 16-byte slack of the bulk copies
+    if ((int64_t)P * m0 + (int64_t)jx * (A->lp + 1) > A->n + ABC_PAD - (2 * (A->lp + 1) + A->u + 8)) { set_error("ssm_abc_solve: internal chunk layout exceeds the padding"); rc = SSM_E_ARG; }
     const int W = A->w;
     if (!rc && (!A->FR || A->P != P || A->tiled != tiled || A->npf != npf)) {
         A->FR.reset(); A->E.reset(); A->TOP.reset(); A->Z.reset();
