@@ -104,3 +104,39 @@ def test_bps_sweeps_are_exact_while_another_stream_is_busy(ssm):
         torch.cuda.synchronize()
         assert np.array_equal(x.get(), ref)
         assert all(np.array_equal(a, c) for a, c in zip(F.get(), reff))
+
+
+@pytest.mark.parametrize("tiled", [False, True])
+def test_chunked_solve_is_exact_while_another_stream_is_busy(ssm, tiled):
+    """K10 (one large system): stage 1 reads its entering rows through a bulk-async ring, the tiled stage 3 streams mini-tiles
+    through another; the solution must not change by a bit when a second stream keeps the GPU busy."""
+    import torch
+    from ssm_b200 import chunked
+    n, l, u, r, seed = 1 << 21, 4, 4, 2, 20261019 + 3
+    st0, c0 = _ctx_on_new_stream(ssm, torch)
+    c0.set_option("abc_tiled_min_chunks", 1 if tiled else 1 << 30)
+    A = chunked.LargeAlmostBandedMatrix.generate(n, l, u, r, seed, dist=1, ctx=c0)
+    with torch.cuda.stream(st0):
+        b = torch.empty(n, dtype=torch.float64, device="cuda")
+        x = torch.empty_like(b)
+    A.generate_rhs(b, seed)
+    A.solve(b, out=x, nchunks=4096)
+    c0.sync()
+    assert A.residual(x, b) <= 1e-13
+    ref = x.cpu().numpy().copy()
+    st1 = torch.cuda.Stream()
+    t1 = torch.empty(1 << 27, dtype=torch.float64, device="cuda")
+    t2 = torch.empty_like(t1)
+    torch.cuda.synchronize()
+    for rep in range(2):
+        with torch.cuda.stream(st0):
+            x.fill_(float(rep + 1))      # scribble, so a stale result cannot pass
+        c0.sync()
+        for _ in range(3):
+            with torch.cuda.stream(st1):
+                t2.copy_(t1)
+            A.solve(b, out=x, nchunks=4096, sync=False)
+            with torch.cuda.stream(st1):
+                t1.copy_(t2)
+        torch.cuda.synchronize()
+        assert np.array_equal(x.cpu().numpy(), ref), (tiled, rep)
