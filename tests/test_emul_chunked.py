@@ -43,3 +43,26 @@ def test_chunked_algebra_matches_oracle_on_generated_inputs():
         ox = oracle.ab_solve(bands, U, V, b, l, u)[0]
         x = solve_chunked(bands[0], U[0], V[0], b[0], l, u, 5)
         assert np.linalg.norm(x - ox) / np.linalg.norm(ox) <= 1e-13
+
+
+def test_regular_layout_invariants():
+    """The chunk layout the CUDA path uses (abc_layout in csrc/abc_kernels.cu, mirrored by regular_layout): every chunk eliminates a
+    whole number of unroll periods, groups of `same` consecutive chunks share a length (4 = one stage-1 warp, 32 = one stage-3
+    tile of the many-chunk path), the chunks tile the padded system, and the padding stays inside what the library allocates
+    behind the operands (ABC_PAD = 512 rows minus the rows the sweeps read ahead)."""
+    from sof_reference import regular_layout
+    rng = np.random.default_rng(5)
+    cases = [(n, lp, P) for n in (1, 7, 33, 500, 4097, 100_000, 1 << 20, (1 << 24) + 3) for lp in (1, 2, 4, 8) for P in (1, 3, 64, 1000, 32768)]
+    cases += [(int(rng.integers(1, 3_000_000)), int(rng.choice([1, 2, 3, 4, 6, 8])), int(rng.integers(1, 40_000))) for _ in range(300)]
+    for n, lp, P0 in cases:
+        for same in (4, 32):
+            P, bnd = regular_layout(n, lp, P0, same=same)
+            pw = lp + 1
+            lens = np.diff(bnd)
+            assert 1 <= P <= max(P0, 1) and len(bnd) == P + 1 and bnd[0] == 0
+            assert np.all(lens % pw == lp) and np.all(lens >= 2 * pw - 1), (n, lp, P0, same)
+            assert bnd[-1] >= n, (n, lp, P0, same)                                   # the chunks cover the system ...
+            assert bnd[-1] - n <= 512 - (2 * pw + lp + 8), (n, lp, P0, same)         # ... and the padding fits (u <= lp)
+            for g in range(0, P, same):                                              # groups share a length
+                assert len(set(lens[g:g + same])) == 1, (n, lp, P0, same, g)
+            assert np.all(lens[:-1] >= lens[1:])                                     # long chunks first
