@@ -1020,10 +1020,16 @@ static void abc_layout(int64_t n, int lp, int same, int &P, int &m0, int &jx) {
 }
 
 static int abc_default_chunks(const ssm_abc *A) {
-    // ~512 rows per chunk (measured best at n = 2^24: 8192 stage-1 warps of 4 chunks), at most 32768 chunks
+    // Stage 1 holds 12 warps of 4 chunks per SM, and all chunks are equally long, so its time moves in whole WAVES of
+    // sm_count * 48 chunks.  Large systems: ~512 rows per chunk, rounded down to whole waves, at most 4 (measured at n = 2^24:
+    // 28,416 and 32,768 chunks 2.89 ms, 35,520 2.96, 42,624 3.14).  Below one wave of 512-row chunks the sweep is latency bound and
+    // shorter chunks win until the separator tree takes over: 128 rows per chunk, at most one wave (n = 10^6: 1,953 chunks 0.50 ms,
+    // 7,104 0.40 ms; n = 65,536: 128 chunks 0.37 ms, 512 0.20 ms).
+    const int64_t wave = (int64_t)(A->ctx->sm_count > 0 ? A->ctx->sm_count : 148) * 12 * ABC_CPW;
     int64_t P = A->n / 512;
+    if (P >= wave) P = std::min<int64_t>(P / wave, 4) * wave;
+    else P = std::min<int64_t>(A->n / 128, wave);
     const int64_t pmax = A->n / (2 * A->lp + 2 + 8);
-    if (P > 32768) P = 32768;
     if (P > pmax) P = pmax;
     if (P < 1) P = 1;
     return (int)P;
