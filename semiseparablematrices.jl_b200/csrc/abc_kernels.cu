@@ -3,10 +3,11 @@
 // :224-238) cannot fill a GPU, the whole `A \ b` (AlmostBandedMatrix.jl:125-133, 187-199) by a stable partitioned
 // orthogonal factorisation that returns the same SOLUTION (the factors are not the reference's):
 //
-//   stage 1  abc_qr      one WARP per row chunk: Householder elimination of the chunk's interior columns.  Lanes hold the
-//                        COLUMNS of the active block (window | generator | separator coefficients | tail coefficients | rhs),
-//                        reflectors are broadcast with shuffles; rows and window columns rotate through fixed slots/lanes
-//                        so nothing moves when the window slides.
+//   stage 1  abc_qr      Householder elimination of each row chunk's interior columns, 8 lanes per chunk and 4 chunks per warp.
+//                        Lanes hold the COLUMNS of the active block (window | generator | separator coefficients | tail
+//                        coefficients | rhs), reflectors are broadcast with shuffles; rows and window columns rotate through fixed
+//                        slots/lanes so nothing moves when the window slides.  The entering operand rows and V rows arrive through
+//                        a per-warp bulk-async ring (TMA 1-D copies), so the sweep's only global load is the rhs value.
 //   stage 2  abc_merge   cyclic reduction of the block-bidiagonal separator system F_c z_c + G_c z_{c+1} = h_c by QR of
 //                        [G_a; F_b], one warp per merge, log2(P) launches; abc_root solves the last block; abc_expand
 //                        recovers the eliminated separators top-down.
