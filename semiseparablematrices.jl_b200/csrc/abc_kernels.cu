@@ -75,7 +75,8 @@ struct AbcDims {
 // Shared memory of stage 1 (dynamic).  Each warp owns one region: a ring of NSTG stages, a stage = the PW operand rows and the PW
 // V rows that enter during one block of PW steps, for each of the warp's chunks (one bulk-async copy per chunk and stream; the
 // copies start at the 16-byte boundary at or below the first row, hence the 16 spare bytes and a per-block shift of 0 or 1
-// doubles).  The same region is the transposition buffer of the epilogue once the ring has drained.
+// doubles).  The rhs values of a block (caller's array: no padding to over-read) come by 8-byte cp.async with zero fill past the end.
+// The ring part of the region is the transposition buffer of the epilogue once the ring has drained.
 template <int LP, int R, int GS>
 struct AbcQrSmem {
     using D = AbcDims<LP, R>;
@@ -84,7 +85,9 @@ struct AbcQrSmem {
     static constexpr int CBV = R > 0 ? ((D::PW * R * 8 + 15) / 16) * 16 + 16 : 0;             // ... V rows
     static constexpr int SGB = CPW * (CBR + CBV);                                            // bytes per stage
     static constexpr int EPI = CS * D::NR * 32 * 8;                                          // epilogue buffer of one warp
-    static constexpr int WREG = ((((ABC_STAGE1_RING ? NSTG * SGB : 0) > EPI ? NSTG * SGB : EPI) + 127) / 128) * 128;
+    static constexpr int PWE = D::PW + (D::PW & 1);                                          // rhs values per chunk and stage (even count)
+    static constexpr int BOFF = (NSTG * SGB > EPI ? NSTG * SGB : EPI);                       // rhs buffer [NSTG][CPW][PWE] behind the ring
+    static constexpr int WREG = (((ABC_STAGE1_RING ? BOFF + NSTG * CPW * PWE * 8 : EPI) + 127) / 128) * 128;
     static constexpr int BARS = 4 * WREG, ZERO = BARS + 4 * NSTG * 8, TOTAL = ZERO + 16;
 };
 
@@ -151,10 +154,25 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         const uintptr_t g = reinterpret_cast<uintptr_t>(v0 + (int64_t)(LP + 1 + j * PW) * R);
         return reinterpret_cast<const double *>(wreg + st * SM::SGB + CPW * SM::CBR + grp * SM::CBV + (g & 15));
     };
+    // rhs values of block j -> b buffer of stage st: lane gl of a group fetches entries gl, gl + GS, ... of its chunk's block
+    double *bbuf = reinterpret_cast<double *>(wreg + SM::BOFF) + grp * SM::PWE;
+    auto b_issue = [&](const int j, const int st) {
+#pragma unroll
+        for (int t = gl; t < PW; t += GS) {
+            const int64_t i = (int64_t)LP + (int64_t)j * PW + t;           // row of the chunk
+            const bool valid = j < nblk_ring && i < brows;
+            const double *src = valid ? b0 + i : a.b;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(bbuf + st * CPW * SM::PWE + t)), "l"(src), "r"(valid ? 8 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     int rstage = 0, rblock = 0; uint32_t rparity = 0;          // stage / block being read, parity of that stage's barrier
     if (RING) {
         for (int j = 0; j < NSTG && j < nblk_ring; ++j) ring_issue(j, j);
+        for (int j = 0; j < NSTG; ++j) b_issue(j, j);          // always NSTG groups in flight (empty past the last block)
+        asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 1) : "memory");
         mbar_wait(bar0, 0);
+        __syncwarp();
     }
 
     // column roles of this lane's slots
@@ -230,15 +248,12 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     // Per-slot stream of the entering rows: window / generator columns walk the row records, the rhs column walks b, all other
     // columns re-read one zero, so the load needs no predicate.  A window column reads field d = (col - k) mod PW, which is also
     // the position of its entry in the emitted record.
-    // With RING the window / generator columns read the ring (their pointer is re-based at every block), the rhs column keeps its
-    // own global load (b has no padding to copy from), everything else reads a zero in shared memory.
+    // With RING the window / generator columns read the ring (their pointer is re-based at every block), the rhs column reads
+    // the rhs buffer, everything else reads a zero in shared memory.
     int d[CS]; const double *ep[CS]; int estride[CS]; double nxt[CS]; double *fr[CS]; bool emit[CS];
-    int64_t brem = brows - LP;                                // rows of b left for the rhs column
-    bool hasB = false;
-#pragma unroll
-    for (int sl = 0; sl < CS; ++sl) hasB = hasB || isB[sl];
-    const double *bp = b0 + LP;
-    double bnx = (hasB && brem > 0) ? *bp : 0.0;
+    int64_t brem = brows - LP;                                // rows of b left for the rhs column (direct-load variant)
+    const double *bcur = bbuf;                                // this block's rhs values
+    double bnx = RING ? bcur[0] : 0.0;
 #pragma unroll
     for (int sl = 0; sl < CS; ++sl) {
         d[sl] = isW[sl] ? col[sl] : 0;                        // phase 0
@@ -262,20 +277,20 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             --brem;
 #pragma unroll
             for (int sl = 0; sl < CS; ++sl) A[sl][es] = (RING && isB[sl]) ? bnx : nxt[sl];
-            if (RING) {
-                ++bp;
-                bnx = (hasB && brem > 0) ? *bp : 0.0;
-            }
             if (RING && PH == PW - 1) {
                 // the rows fetched from here on belong to the next block: wait for its stage, hand this block's stage back
                 const int old = rstage;
                 if (++rstage == NSTG) { rstage = 0; rparity ^= 1u; }
                 ++rblock;
+                asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 2) : "memory");    // the next block's rhs values have landed
                 mbar_wait(bar0 + 8u * rstage, rparity);
                 __syncwarp();                                 // every lane's reads of the old stage are in registers ...
                 fence_proxy_async();                          // ... and ordered before the bulk copies that re-arm it
                 if (rblock - 1 + NSTG < nblk_ring) ring_issue(rblock - 1 + NSTG, old);
+                b_issue(rblock - 1 + NSTG, old);
+                bcur = bbuf + rstage * CPW * SM::PWE;
             }
+            if (RING) bnx = bcur[(PH + 1) % PW];
 #pragma unroll
             for (int sl = 0; sl < CS; ++sl) {
                 // prefetch the row entering at the next step (rows past the chunk are the next chunk's or the identity pad)
