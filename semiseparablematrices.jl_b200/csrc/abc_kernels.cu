@@ -310,6 +310,19 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
             for (int s = 0; s < NR; ++s) { if (s % 3 == 0) q0 = fma(x[s], x[s], q0); else if (s % 3 == 1) q1 = fma(x[s], x[s], q1); else q2 = fma(x[s], x[s], q2); }
+            // projections of this lane's columns on the RAW pivot column: they need nothing of the reflector's scalars, so they run
+            // beside the rsqrt / rcp chain instead of behind it (v_s = x_s * inv is never formed; inv joins at the end)
+            double raw[CS];
+#pragma unroll
+            for (int sl = 0; sl < CS; ++sl) {
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int s = 0; s < NR; ++s) {
+                    if (s == PH) continue;
+                    if (s & 1) d1 = fma(x[s], A[sl][s], d1); else d0 = fma(x[s], A[sl][s], d0);
+                }
+                raw[sl] = d0 + d1;
+            }
             const double ssq = (q0 + q1) + q2;
             const double xp = x[PH];
             const bool nz = ssq != 0.0;
@@ -321,18 +334,11 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             const double inv = nz ? fast_rcp(xi) : 0.0;
             const double tau = nz ? xi * copysign(rs, xp) : 0.0;
 #pragma unroll
-            for (int s = 0; s < NR; ++s) if (s != PH) x[s] *= inv;    // v_s
-#pragma unroll
             for (int sl = 0; sl < CS; ++sl) {
-                double d0 = A[sl][PH], d1 = 0.0;
+                const double dot = fma(inv, raw[sl], A[sl][PH]) * tau;     // tau * v'a, v = (1, x_s * inv)
+                const double cf = dot * inv;
 #pragma unroll
-                for (int s = 0; s < NR; ++s) {
-                    if (s == PH) continue;
-                    if (s & 1) d1 = fma(x[s], A[sl][s], d1); else d0 = fma(x[s], A[sl][s], d0);
-                }
-                const double dot = (d0 + d1) * tau;
-#pragma unroll
-                for (int s = 0; s < NR; ++s) A[sl][s] = (s == PH) ? A[sl][s] - dot : fma(-x[s], dot, A[sl][s]);
+                for (int s = 0; s < NR; ++s) A[sl][s] = (s == PH) ? A[sl][s] - dot : fma(-x[s], cf, A[sl][s]);
             }
             if (gl == pl) A[ps][PH] = nz ? -nu : xp;
             // emit the finished row (canonical order: window entry of column k+t at position t)
