@@ -69,9 +69,6 @@ struct AbcDims {
 // TILED: the R-row records are interleaved over the FOUR chunks this warp sweeps, FR[c / 4][k][field][c % 4]: one store
 // instruction (8 lanes = 8 fields, 4 chunks each) then covers 256 contiguous bytes — 2-3 cache lines against ~5 for row-major
 // records and 8 for 32-wide tiles — which matters because the LSU pipe (shuffles + global accesses) is this kernel's busiest unit.
-#ifndef ABC_STAGE1_RING
-#define ABC_STAGE1_RING 1
-#endif
 // Shared memory of stage 1 (dynamic).  Each warp owns one region: a ring of NSTG stages, a stage = the PW operand rows and the PW
 // V rows that enter during one block of PW steps, for each of the warp's chunks (one bulk-async copy per chunk and stream; the
 // copies start at the 16-byte boundary at or below the first row, hence the 16 spare bytes and a per-block shift of 0 or 1
@@ -87,7 +84,7 @@ struct AbcQrSmem {
     static constexpr int EPI = CS * D::NR * 32 * 8;                                          // epilogue buffer of one warp
     static constexpr int PWE = D::PW + (D::PW & 1);                                          // rhs values per chunk and stage (even count)
     static constexpr int BOFF = (NSTG * SGB > EPI ? NSTG * SGB : EPI);                       // rhs buffer [NSTG][CPW][PWE] behind the ring
-    static constexpr int WREG = (((ABC_STAGE1_RING ? BOFF + NSTG * CPW * PWE * 8 : EPI) + 127) / 128) * 128;
+    static constexpr int WREG = ((BOFF + NSTG * CPW * PWE * 8 + 127) / 128) * 128;
     static constexpr int BARS = 4 * WREG, ZERO = BARS + 4 * NSTG * 8, TOTAL = ZERO + 16;
 };
 
@@ -98,7 +95,6 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     constexpr int PW = D::PW, NR = D::NR, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, NF = D::NF, W = D::W;
     constexpr int CS = (NC + GS - 1) / GS, CPW = 32 / GS, RQ = R > 0 ? R : 1;
     constexpr int FSTR = TILED ? 4 : 1, RSTR = TILED ? NC * 4 : NC;     // field / record strides of FR in doubles
-    constexpr bool RING = ABC_STAGE1_RING != 0;
     constexpr int NSTG = SM::NSTG;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane % GS, grp = lane / GS;
@@ -115,13 +111,12 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
     const double *v0 = a.V + (r0 + u) * RQ;                   // V row of local column 0
     const double *b0 = a.b + r0;
     const int64_t brows = a.n - r0;                           // rows of b that exist from r0 on (pad rows have b = 0)
-    const double *zero = a.V + (a.n + 8) * RQ;                // a V pad row: always 0.0
-    // ---- ring of entering rows (RING): lanes 0..CPW-1 copy the operand rows of the warp's chunks, lanes CPW..2CPW-1 their V rows ----
+    // ---- ring of entering rows: lanes 0..CPW-1 copy the operand rows of the warp's chunks, lanes CPW..2CPW-1 their V rows ----
     const uint32_t bar0 = smem_u32(smem + SM::BARS + wib * NSTG * 8);
     double *zero_s = reinterpret_cast<double *>(smem + SM::ZERO);
     const int nblk_ring = nsteps / PW + 1;                    // the row fetched ahead at the last step belongs to one more block
     const double *csrc = nullptr;                             // issuing lanes: first row / V row of block 0 of "their" chunk
-    if (RING) {
+    {
         int cc = (blockIdx.x * 4 + wib) * CPW + (lane % CPW);
         if (cc >= a.P) cc = a.P - 1;
         const int64_t rc = chunk_start(a, cc);
@@ -167,7 +162,7 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     int rstage = 0, rblock = 0; uint32_t rparity = 0;          // stage / block being read, parity of that stage's barrier
-    if (RING) {
+    {
         for (int j = 0; j < NSTG && j < nblk_ring; ++j) ring_issue(j, j);
         for (int j = 0; j < NSTG; ++j) b_issue(j, j);          // always NSTG groups in flight (empty past the last block)
         asm volatile("cp.async.wait_group %0;" ::"n"(NSTG - 1) : "memory");
@@ -245,26 +240,22 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             A[sl][PW + t] = val;
         }
 
-    // Per-slot stream of the entering rows: window / generator columns walk the row records, the rhs column walks b, all other
-    // columns re-read one zero, so the load needs no predicate.  A window column reads field d = (col - k) mod PW, which is also
-    // the position of its entry in the emitted record.
-    // With RING the window / generator columns read the ring (their pointer is re-based at every block), the rhs column reads
-    // the rhs buffer, everything else reads a zero in shared memory.
+    // Per-slot stream of the entering rows: window / generator columns walk the row records in the ring (their pointer is re-based
+    // at every block), the rhs column reads the rhs buffer, all other columns re-read one zero in shared memory, so the load needs
+    // no predicate.  A window column reads field d = (col - k) mod PW, which is also the position of its entry in the emitted record.
     int d[CS]; const double *ep[CS]; int estride[CS]; double nxt[CS]; double *fr[CS]; bool emit[CS];
-    int64_t brem = brows - LP;                                // rows of b left for the rhs column (direct-load variant)
     const double *bcur = bbuf;                                // this block's rhs values
-    double bnx = RING ? bcur[0] : 0.0;
+    double bnx = bcur[0];
 #pragma unroll
     for (int sl = 0; sl < CS; ++sl) {
         d[sl] = isW[sl] ? col[sl] : 0;                        // phase 0
-        if (isW[sl] || isG[sl]) { ep[sl] = (RING ? ring_rec(0, 0) : rec0 + (int64_t)LP * NF) + (isG[sl] ? PW + col[sl] - G0 : 0); estride[sl] = NF; }
-        else if (isB[sl] && !RING) { ep[sl] = b0 + LP; estride[sl] = 1; }
-        else { ep[sl] = RING ? zero_s : zero; estride[sl] = 0; }
-        nxt[sl] = (!RING && isB[sl] && brem <= 0) ? 0.0 : ep[sl][d[sl]];
+        if (isW[sl] || isG[sl]) { ep[sl] = ring_rec(0, 0) + (isG[sl] ? PW + col[sl] - G0 : 0); estride[sl] = NF; }
+        else { ep[sl] = zero_s; estride[sl] = 0; }
+        nxt[sl] = ep[sl][d[sl]];
         fr[sl] = (TILED ? a.FR + (int64_t)(c >> 2) * a.npf * NC * 4 + (c & 3) : a.FR + r0 * NC) + (isW[sl] ? 0 : col[sl]) * FSTR;
         emit[sl] = live && col[sl] < NC;
     }
-    const double *vp = RING ? ring_v(0, 0) : v0 + (int64_t)(LP + 1) * R;            // V row of the column entering after step 0
+    const double *vp = ring_v(0, 0);                          // V row of the column entering after step 0
     double vnx[RQ];
 #pragma unroll
     for (int q = 0; q < R; ++q) vnx[q] = vp[q];
@@ -274,10 +265,9 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         for (int PH = 0; PH < PW; ++PH) {
             const int es = (PH + LP) % PW;                    // slot of the entering row
             const int pl = PH % GS, ps = PH / GS;             // lane-in-group / column slot of the pivot column
-            --brem;
 #pragma unroll
-            for (int sl = 0; sl < CS; ++sl) A[sl][es] = (RING && isB[sl]) ? bnx : nxt[sl];
-            if (RING && PH == PW - 1) {
+            for (int sl = 0; sl < CS; ++sl) A[sl][es] = isB[sl] ? bnx : nxt[sl];
+            if (PH == PW - 1) {
                 // the rows fetched from here on belong to the next block: wait for its stage, hand this block's stage back
                 const int old = rstage;
                 if (++rstage == NSTG) { rstage = 0; rparity ^= 1u; }
@@ -290,17 +280,17 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
                 b_issue(rblock - 1 + NSTG, old);
                 bcur = bbuf + rstage * CPW * SM::PWE;
             }
-            if (RING) bnx = bcur[(PH + 1) % PW];
+            bnx = bcur[(PH + 1) % PW];
 #pragma unroll
             for (int sl = 0; sl < CS; ++sl) {
                 // prefetch the row entering at the next step (rows past the chunk are the next chunk's or the identity pad)
-                if (RING && PH == PW - 1) { if (isW[sl] || isG[sl]) ep[sl] = ring_rec(rblock, rstage) + (isG[sl] ? PW + col[sl] - G0 : 0); }
+                if (PH == PW - 1) { if (isW[sl] || isG[sl]) ep[sl] = ring_rec(rblock, rstage) + (isG[sl] ? PW + col[sl] - G0 : 0); }
                 else ep[sl] += estride[sl];
                 const int dn = isW[sl] ? (d[sl] == 0 ? LP : d[sl] - 1) : 0;
-                nxt[sl] = (!RING && isB[sl] && brem <= 0) ? 0.0 : ep[sl][dn];
+                nxt[sl] = ep[sl][dn];
             }
             double vn[RQ];
-            if (RING && PH == PW - 1) vp = ring_v(rblock, rstage); else vp += R;
+            if (PH == PW - 1) vp = ring_v(rblock, rstage); else vp += R;
 #pragma unroll
             for (int q = 0; q < R; ++q) { vn[q] = vnx[q]; vnx[q] = vp[q]; }   // one step ahead
             // reflector from the pivot column, LinearAlgebra.reflector! convention
