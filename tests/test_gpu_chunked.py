@@ -78,6 +78,21 @@ def test_chunked_readme_known_answer(chunked, ctx):
         assert np.linalg.norm(x[:16] - ref) / np.linalg.norm(ref) <= 1e-14
 
 
+def test_chunked_readme_million(chunked, ctx):
+    """BASELINE.json configs[0] at its large size (README.md:96-97, n = 1,000,000): `A \\ b` of the README system through the
+    chunked path, against the known answer 1/k!, the oracle's sequential sweep and the structured residual."""
+    n = 1_000_000
+    (l, u, r), bands, U, V, b = readme_expz(n)
+    ox = oracle.ab_solve(bands[None], U[None], V[None], b[None], l, u)[0]
+    A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
+    x = A.solve(b)
+    assert A.chunks > 1000
+    ref = np.array([1 / math.factorial(k) for k in range(16)])
+    assert np.linalg.norm(x[:16] - ref) / np.linalg.norm(ref) <= 1e-14
+    assert np.linalg.norm(x - ox) / np.linalg.norm(ox) <= 1e-12
+    assert A.residual(x, b) <= 1e-13
+
+
 @pytest.mark.parametrize("n,l,u,r,dist", [(100_000, 4, 4, 2, 1), (100_000, 2, 2, 2, 0), (262_144, 1, 0, 1, 0), (65_537, 4, 4, 2, 0)])
 def test_chunked_matches_oracle_sweep(chunked, ctx, n, l, u, r, dist):
     import torch
