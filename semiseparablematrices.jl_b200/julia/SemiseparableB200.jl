@@ -211,9 +211,10 @@ for (UNIT, unitflag) in (('N', 0), ('U', 1))
     end
 end
 
-# A \ b for ONE large system (README.md:96-97, n = 10^6 and beyond): the chunked n-axis path returns the same solution without
-# the strictly sequential sweep (solution parity, not factor parity — DESIGN.md section 6).  Smaller systems keep qr + ldiv!.
-const CHUNKED_MIN_N = Ref(1 << 16)
+# A \ b for ONE system (README.md:96-97, n = 10^6 and beyond): the chunked n-axis path returns the same solution without the
+# strictly sequential sweep (solution parity, not factor parity — DESIGN.md section 6).  Measured on B200 for a single system:
+# n = 1024: 0.11 ms chunked against 0.44 ms for the sweep; n = 65,536: 0.19 against 27.7 ms.  Smaller systems keep qr + ldiv!.
+const CHUNKED_MIN_N = Ref(1 << 10)
 function Base.:\(A::DenseAB, b::Vector{Float64})
     n = size(A, 2)
     (size(A, 1) == n && n >= CHUNKED_MIN_N[]) || return ldiv!(qr(A), copy(b))
