@@ -1006,13 +1006,30 @@ static bool abc_supported(int lp, int r) {
     return false;
 }
 
-// device pointer for a caller array of `count` doubles (host arrays are staged into `hold`)
-static int to_device(ssm_ctx *c, const double *p, size_t count, DevBufPtr &hold, const double **out) {
-    if (!p) { *out = nullptr; return 0; }
-    if (is_device_ptr(p)) { *out = p; return 0; }
-    SSM_TRY(dev_alloc(c->device, count, false, c->stream, hold));
-    SSM_CUDA(cudaMemcpyAsync(hold->p, p, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    *out = hold->p;
+// Device views of up to four caller arrays: device pointers pass through, host arrays share ONE carve-up of the context's
+// grow-only staging buffer (no cudaMalloc / cudaFree per call: for a single system of n <= 10^6 those cost more than the solve).
+// `copy_in[k]` = the array is an input (copied host -> device on the context's stream).
+struct Staged {
+    const double *host[4]; size_t count[4]; bool copy_in[4]; double *dev[4]; bool staged[4]; int n = 0;
+    int add(const double *p, size_t cnt, bool in) { host[n] = p; count[n] = cnt; copy_in[n] = in; dev[n] = nullptr; staged[n] = false; return n++; }
+};
+static int stage_arrays(ssm_ctx *c, Staged &st) {
+    size_t total = 0;
+    for (int k = 0; k < st.n; ++k) {
+        if (!st.host[k]) continue;
+        if (is_device_ptr(st.host[k])) { st.dev[k] = const_cast<double *>(st.host[k]); continue; }
+        st.staged[k] = true;
+        total += (st.count[k] + 1) & ~(size_t)1;               // keep every carve-out 16-byte aligned
+    }
+    if (total == 0) return 0;
+    double *base;
+    SSM_TRY(staging_dev(c, total, &base));
+    for (int k = 0; k < st.n; ++k) {
+        if (!st.staged[k]) continue;
+        st.dev[k] = base;
+        base += (st.count[k] + 1) & ~(size_t)1;
+        if (st.copy_in[k]) SSM_CUDA(cudaMemcpyAsync(st.dev[k], st.host[k], st.count[k] * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
     return 0;
 }
 
@@ -1125,6 +1142,15 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     return 0;
 }
 
+// A context keeps the last two destroyed objects of moderate size (operands + workspace of one system, <= ~300 MB each): a caller
+// that solves one system after another of the same shape (`A \ b` from the Julia glue creates and destroys an object per call)
+// then pays no cudaMalloc / cudaFree / memset per solve.  Every entry point overwrites what it reads, so a recycled object needs no
+// clearing: ssm_abc_set / ssm_abc_generate write all n + ABC_PAD operand rows, a solve writes every workspace entry it later reads.
+constexpr int64_t ABC_CACHE_MAX_N = 1 << 20;
+void ssm::abc_cache_free(ssm_ctx *c) {
+    for (auto &slot : c->abc_cache) { delete static_cast<ssm_abc *>(slot); slot = nullptr; }
+}
+
 extern "C" {
 
 int ssm_abc_create(ssm_ctx *c, int64_t n, int l, int u, int r, ssm_abc **out) {
@@ -1132,6 +1158,10 @@ int ssm_abc_create(ssm_ctx *c, int64_t n, int l, int u, int r, ssm_abc **out) {
     SSM_CHECK_ARG(n >= 1 && l >= 0 && u >= 0 && r >= 0, "bad sizes");
     if (n > (int64_t)0x7fffffff - 1024) { set_error("ssm_abc_create: n too large"); return SSM_E_UNSUPPORTED; }
     if (!abc_supported(l + u, r)) { set_error("ssm_abc: (l+u, r) = (%d, %d) has no compiled chunked kernel", l + u, r); return SSM_E_UNSUPPORTED; }
+    for (auto &slot : c->abc_cache) {
+        auto *C = static_cast<ssm_abc *>(slot);
+        if (C && C->n == n && C->l == l && C->u == u && C->r == r) { slot = nullptr; *out = C; return 0; }
+    }
     auto *A = new ssm_abc();
     A->ctx = c; A->n = n; A->l = l; A->u = u; A->r = r; A->lp = l + u; A->w = A->lp + r; A->nf = A->lp + 1 + r; A->nc = 2 * A->lp + 2 * r + 2;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
@@ -1142,7 +1172,19 @@ int ssm_abc_create(ssm_ctx *c, int64_t n, int l, int u, int r, ssm_abc **out) {
     *out = A;
     return 0;
 }
-int ssm_abc_destroy(ssm_abc *A) { if (A) { cudaStreamSynchronize(A->ctx->stream); delete A; } return 0; }
+int ssm_abc_destroy(ssm_abc *A) {
+    if (!A) return 0;
+    ssm_ctx *c = A->ctx;
+    cudaStreamSynchronize(c->stream);
+    if (A->n <= ABC_CACHE_MAX_N) {
+        A->tmp.reset();
+        if (c->abc_cache[0]) { delete static_cast<ssm_abc *>(c->abc_cache[1]); c->abc_cache[1] = c->abc_cache[0]; }
+        c->abc_cache[0] = A;
+        return 0;
+    }
+    delete A;
+    return 0;
+}
 
 int ssm_abc_generate(ssm_abc *A, uint64_t seed, int dist) {
     SSM_CHECK_ARG(A, "null argument");
@@ -1160,13 +1202,12 @@ int ssm_abc_set(ssm_abc *A, const double *bands, const double *U, const double *
     SSM_CHECK_ARG(A && bands && (A->r == 0 || (U && V)), "null argument");
     ssm_ctx *c = A->ctx;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
-    DevBufPtr hb, hu, hv;
-    const double *db, *du, *dv;
-    int rc = to_device(c, bands, (size_t)(A->lp + 1) * A->n, hb, &db);
-    if (!rc) rc = to_device(c, A->r ? U : nullptr, (size_t)A->n * A->r, hu, &du);
-    if (!rc) rc = to_device(c, A->r ? V : nullptr, (size_t)A->n * A->r, hv, &dv);
+    Staged st;
+    const int kb = st.add(bands, (size_t)(A->lp + 1) * A->n, true), ku = st.add(A->r ? U : nullptr, (size_t)A->n * A->r, true),
+              kv = st.add(A->r ? V : nullptr, (size_t)A->n * A->r, true);
+    int rc = stage_arrays(c, st);
     if (!rc) {
-        abc_pack_kernel<<<(unsigned)((A->n + ABC_PAD + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, db, du, dv, A->n, A->l, A->u, A->r);
+        abc_pack_kernel<<<(unsigned)((A->n + ABC_PAD + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, st.dev[kb], st.dev[ku], st.dev[kv], A->n, A->l, A->u, A->r);
         c->launches++;
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "abc_pack_kernel", __FILE__, __LINE__);
@@ -1210,14 +1251,11 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
         A->P = P;
     }
     A->m0 = m0; A->jx = jx; A->tiled = tiled; A->npf = npf;
-    DevBufPtr hb, hx;
-    const double *db = nullptr; double *dx = nullptr;
-    if (!rc) rc = to_device(c, b, (size_t)A->n, hb, &db);
-    const bool xhost = !is_device_ptr(x);
-    if (!rc) {
-        if (xhost) { rc = dev_alloc(c->device, (size_t)A->n, false, c->stream, hx); dx = hx ? hx->p : nullptr; }
-        else dx = x;
-    }
+    Staged st;
+    const int kb = st.add(b, (size_t)A->n, true), kx = st.add(x, (size_t)A->n, false);
+    if (!rc) rc = stage_arrays(c, st);
+    const double *db = st.dev[kb]; double *dx = st.dev[kx];
+    const bool xhost = st.staged[kx];
     if (!rc) {
         rc = SSM_E_UNSUPPORTED;
 #define X(LP_, R_) if (A->lp == LP_ && A->r == R_) rc = abc_solve_inst<LP_, R_>(A, db, dx, P);
@@ -1228,7 +1266,7 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
         cudaError_t e = cudaMemcpyAsync(x, dx, (size_t)A->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "D2H x", __FILE__, __LINE__);
     }
-    if (!rc && (xhost || hb)) {
+    if (!rc && (xhost || st.staged[kb])) {
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
     }
@@ -1241,10 +1279,10 @@ int ssm_abc_residual(ssm_abc *A, const double *x, const double *b, double *relre
     SSM_CHECK_ARG(A && x && b && relres, "null argument");
     ssm_ctx *c = A->ctx;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
-    DevBufPtr hx, hb;
-    const double *dx, *db;
-    int rc = to_device(c, x, (size_t)A->n, hx, &dx);
-    if (!rc) rc = to_device(c, b, (size_t)A->n, hb, &db);
+    Staged st;
+    const int kx = st.add(x, (size_t)A->n, true), kb = st.add(b, (size_t)A->n, true);
+    int rc = stage_arrays(c, st);
+    const double *dx = st.dev[kx], *db = st.dev[kb];
     const int nseg = (int)((A->n + RSEG - 1) / RSEG);
     if (!rc) rc = dev_alloc(c->device, (size_t)nseg * SSM_MAX_RANK + 2, true, c->stream, A->tmp);
     if (!rc) {

@@ -130,6 +130,7 @@ int ssm_ctx_destroy(ssm_ctx *c) {
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
     hostpipe_free(c);
+    abc_cache_free(c);
     if (c->stg.dev) cudaFree(c->stg.dev);
     if (c->stg.pin) cudaFreeHost(c->stg.pin);
     for (auto &s : c->aux) if (s) cudaStreamDestroy(s);

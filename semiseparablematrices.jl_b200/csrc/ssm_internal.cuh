@@ -55,7 +55,7 @@ struct Staging {        // lazily grown scratch: device staging in reference lay
 }  // namespace ssm
 
 struct ssm_ctx;
-namespace ssm { int staging_dev(ssm_ctx *c, size_t count, double **out); void hostpipe_free(ssm_ctx *c); }
+namespace ssm { int staging_dev(ssm_ctx *c, size_t count, double **out); void hostpipe_free(ssm_ctx *c); void abc_cache_free(ssm_ctx *c); }
 
 struct ssm_ctx {
     int          device = 0;
@@ -75,6 +75,7 @@ struct ssm_ctx {
     // extra streams / events for the chunk-pipelined host path
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
     void        *hostpipe = nullptr;   // ssm::HostPipe of ssm_ab_solve_host (host_path.cu)
+    void        *abc_cache[2] = {nullptr, nullptr};   // recently destroyed ssm_abc objects kept for reuse (abc_kernels.cu)
 };
 
 struct ssm_vec {
