@@ -387,6 +387,31 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
 //   Ein  : level blocks [W][2W+1] = [F | G | h];  merge i combines blocks 2i, 2i+1
 //   TOP  : [W][3W+1] = [Rhat | Fhat | Ghat | hhat]  (z_M = Rhat^-1 (hhat - Fhat z_L - Ghat z_R))
 // ---------------------------------------------------------------------------------------------------------------
+// Reflector of the column x[j..N-1] (LinearAlgebra.reflector! convention: nu = copysign(||x||, x_j), v = (1, x_s / (x_j + nu)),
+// tau = (x_j + nu) / nu) with the branch-free rsqrt / rcp of fastmath.cuh and three-way split sums, as in stage 1; returns the
+// projection sum_{s>j} x_s m_s of this lane's column on the RAW pivot column (it does not wait for the scalars).
+template <int N>
+__device__ __forceinline__ double abc_reflector(const double (&x)[N], const double (&m)[N], const int j, double &inv, double &tau, double &nu, bool &nz) {
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, d0 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+        if (s < j) continue;
+        if (s % 3 == 0) q0 = fma(x[s], x[s], q0); else if (s % 3 == 1) q1 = fma(x[s], x[s], q1); else q2 = fma(x[s], x[s], q2);
+        if (s == j) continue;
+        if (s % 3 == 0) d0 = fma(x[s], m[s], d0); else if (s % 3 == 1) d1 = fma(x[s], m[s], d1); else d2 = fma(x[s], m[s], d2);
+    }
+    const double ssq = (q0 + q1) + q2;
+    nz = ssq != 0.0;
+    const double rs = fast_rsqrt(ssq);
+    double nrm = ssq * rs;
+    nrm = fma(fma(-nrm, nrm, ssq), 0.5 * rs, nrm);            // one correction step: sqrt to ~1 ulp
+    nu = copysign(nrm, x[j]);
+    const double xi = x[j] + nu;
+    inv = nz ? fast_rcp(xi) : 0.0;
+    tau = nz ? xi * copysign(rs, x[j]) : 0.0;
+    return (d0 + d1) + d2;
+}
+
 template <int W>
 __device__ __forceinline__ void abc_merge_one(const double *Ein, double *Eout, double *TOP, const int nin, const int i, const int lane) {
     constexpr int EW = 2 * W + 1, TW = 3 * W + 1;
@@ -409,22 +434,16 @@ __device__ __forceinline__ void abc_merge_one(const double *Ein, double *Eout, d
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         double x[2 * W];
-        double ssq = 0.0;
 #pragma unroll
-        for (int s = j; s < 2 * W; ++s) { x[s] = __shfl_sync(FULL, M[s], j); ssq = fma(x[s], x[s], ssq); }
+        for (int s = j; s < 2 * W; ++s) x[s] = __shfl_sync(FULL, M[s], j);
+        double inv, tau, nu; bool nz;
         const double xp = x[j];
-        const double nu = copysign(sqrt(ssq), xp);
-        const double xi = xp + nu;
-        const bool nz = ssq != 0.0;
-        const double inv = nz ? 1.0 / xi : 0.0;
-        const double tau = nz ? xi / nu : 0.0;
-        double dot = M[j];
-#pragma unroll
-        for (int s = j + 1; s < 2 * W; ++s) { x[s] *= inv; dot = fma(x[s], M[s], dot); }
-        dot *= tau;
+        const double raw = abc_reflector<2 * W>(x, M, j, inv, tau, nu, nz);
+        const double dot = fma(inv, raw, M[j]) * tau;          // tau * v'm, v = (1, x_s * inv)
+        const double cf = dot * inv;
         M[j] -= dot;
 #pragma unroll
-        for (int s = j + 1; s < 2 * W; ++s) M[s] = fma(-x[s], dot, M[s]);
+        for (int s = j + 1; s < 2 * W; ++s) M[s] = fma(-x[s], cf, M[s]);
         if (lane == j) {
             M[j] = nz ? -nu : xp;
 #pragma unroll
@@ -468,22 +487,16 @@ __device__ __forceinline__ void abc_root_one(const double *E, double *Z, const i
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         double x[W];
-        double ssq = 0.0;
 #pragma unroll
-        for (int s = j; s < W; ++s) { x[s] = __shfl_sync(FULL, M[s], j); ssq = fma(x[s], x[s], ssq); }
+        for (int s = j; s < W; ++s) x[s] = __shfl_sync(FULL, M[s], j);
+        double inv, tau, nu; bool nz;
         const double xp = x[j];
-        const double nu = copysign(sqrt(ssq), xp);
-        const double xi = xp + nu;
-        const bool nz = ssq != 0.0;
-        const double inv = nz ? 1.0 / xi : 0.0;
-        const double tau = nz ? xi / nu : 0.0;
-        double dot = M[j];
-#pragma unroll
-        for (int s = j + 1; s < W; ++s) { x[s] *= inv; dot = fma(x[s], M[s], dot); }
-        dot *= tau;
+        const double raw = abc_reflector<W>(x, M, j, inv, tau, nu, nz);
+        const double dot = fma(inv, raw, M[j]) * tau;
+        const double cf = dot * inv;
         M[j] -= dot;
 #pragma unroll
-        for (int s = j + 1; s < W; ++s) M[s] = fma(-x[s], dot, M[s]);
+        for (int s = j + 1; s < W; ++s) M[s] = fma(-x[s], cf, M[s]);
         if (lane == j) {
             M[j] = nz ? -nu : xp;
 #pragma unroll
@@ -527,14 +540,19 @@ __device__ __forceinline__ void abc_expand_one(const double *TOP, double *Z, con
     if (lane >= W && lane < 2 * W) mult = Z[iL * W + (lane - W)];
     else if (lane >= 2 * W && lane < 3 * W) mult = Z[iR * W + (lane - 2 * W)];
     else if (lane == 3 * W) mult = -1.0;
+    // rows and the reciprocals of their diagonal entries first (independent of the recurrence), then the recurrence itself:
+    // one product, one butterfly sum and one multiply per row
+    double v[W], nrinv[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) v[j] = lane < TW ? T[j * TW + lane] : 0.0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) nrinv[j] = -fast_rcp(__shfl_sync(FULL, v[j], j));
 #pragma unroll
     for (int j = W - 1; j >= 0; --j) {
-        const double v = lane < TW ? T[j * TW + lane] : 0.0;
-        double p = v * mult;                                  // lanes <= j of the z_M part still hold 0
+        double p = v[j] * mult;                               // lanes <= j of the z_M part still hold 0
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
-        const double rjj = __shfl_sync(FULL, v, j);
-        if (lane == j) mult = -p / rjj;
+        if (lane == j) mult = p * nrinv[j];
     }
     if (lane < W) Z[iM * W + lane] = mult;
 }
