@@ -68,6 +68,13 @@ int  ssm_ctx_set_option(ssm_ctx *ctx, const char *key, int value);
 int  ssm_ctx_get_option(ssm_ctx *ctx, const char *key, int *value);
 /* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */
 int64_t ssm_ctx_launch_count(ssm_ctx *ctx);
+/* Device blocks of destroyed objects (<= 64 MiB each, <= 512 MiB per device) are kept on a per-device free list and handed to the
+   next ssm_*_create of a similar size, so that a caller who builds, factorises and destroys one matrix per call — what Julia's
+   qr(A) / A \ b do (AlmostBandedMatrix.jl:126-133 allocates its factors per call as well) — pays no cudaMalloc / cudaFree.
+   ssm_pool_trim returns the listed blocks of `device` to the driver (bytes freed); ssm_pool_stats reports the list
+   (any output pointer may be null).  SSM_POOL=0 in the environment disables the list. */
+int64_t ssm_pool_trim(int device);
+int  ssm_pool_stats(int device, int64_t *bytes, int64_t *blocks, int64_t *hits, int64_t *misses);
 
 /* ---- vectors ------------------------------------------------------------------------------------ */
 int  ssm_vec_create(ssm_ctx *ctx, int n, int64_t nb, ssm_vec **v);

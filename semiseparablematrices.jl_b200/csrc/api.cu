@@ -2,6 +2,8 @@
 // the AlmostBanded entry points.  BPS entry points live in bps_api.cu.
 #include <cstdarg>
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 #include "ssm_internal.cuh"
 
 namespace ssm {
@@ -22,15 +24,96 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return (int)e;
 }
 
+// ---- per-device free list of small device blocks ---------------------------------------------------------------
+// A caller that factorises one matrix per call (the Julia glue: qr(A) creates an operand batch, a factor object and a vector and
+// destroys them again) paid a cudaMalloc + cudaFree per buffer, several times the kernels' own time at n ~ 1,000.  Blocks of at
+// most POOL_BLOCK_MAX bytes therefore go back to a per-device list (at most POOL_TOTAL_MAX bytes, oldest evicted first) and
+// dev_alloc takes the smallest listed block of at least — and at most twice — the requested size.  A block is only listed when
+// the stream it was allocated for is idle (every ssm_*_destroy synchronises its context's stream first), so it can be handed to any
+// other stream; otherwise it is cudaFree'd as before.  Large batches never pass through the list: their allocation cost is
+// invisible beside their kernels and holding them back would only take memory from the next batch.
+// SSM_POOL=0 in the environment switches the list off; ssm_pool_trim() gives the listed blocks back to the driver.
+namespace {
+constexpr size_t POOL_BLOCK_MAX = 64ull << 20;
+constexpr size_t POOL_TOTAL_MAX = 512ull << 20;
+constexpr int    POOL_MAX_DEV   = 64;
+struct PoolEntry { double *p; size_t cap; };
+struct DevPool { std::mutex mu; std::vector<PoolEntry> blocks; size_t bytes = 0; int64_t hits = 0, misses = 0; };
+DevPool *pool_of(int device) {
+    static DevPool *pools = new DevPool[POOL_MAX_DEV];      // never destroyed: no cudaFree after the runtime has shut down
+    static const bool on = [] { const char *e = getenv("SSM_POOL"); return !(e && e[0] == '0'); }();
+    return (on && device >= 0 && device < POOL_MAX_DEV) ? &pools[device] : nullptr;
+}
+void raw_free(int device, double *p) {
+    int cur = 0; cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    cudaFree(p);
+    if (cur != device) cudaSetDevice(cur);
+}
+double *pool_take(int device, size_t count, size_t *cap) {
+    DevPool *P = pool_of(device);
+    if (!P || count * sizeof(double) > POOL_BLOCK_MAX) return nullptr;
+    std::lock_guard<std::mutex> g(P->mu);
+    int best = -1;
+    for (int i = 0; i < (int)P->blocks.size(); i++) {
+        const size_t c = P->blocks[i].cap;
+        if (c >= count && c <= 2 * count + 512 && (best < 0 || c < P->blocks[best].cap)) best = i;
+    }
+    if (best < 0) { P->misses++; return nullptr; }
+    PoolEntry e = P->blocks[best];
+    P->blocks.erase(P->blocks.begin() + best);
+    P->bytes -= e.cap * sizeof(double);
+    P->hits++;
+    *cap = e.cap;
+    return e.p;
+}
+bool pool_give(int device, double *p, size_t cap) {
+    DevPool *P = pool_of(device);
+    const size_t bytes = cap * sizeof(double);
+    if (!P || bytes > POOL_BLOCK_MAX) return false;
+    std::vector<PoolEntry> evict;
+    {
+        std::lock_guard<std::mutex> g(P->mu);
+        while (P->bytes + bytes > POOL_TOTAL_MAX && !P->blocks.empty()) {
+            evict.push_back(P->blocks.front());
+            P->bytes -= P->blocks.front().cap * sizeof(double);
+            P->blocks.erase(P->blocks.begin());
+        }
+        P->blocks.push_back({p, cap});
+        P->bytes += bytes;
+    }
+    for (auto &e : evict) raw_free(device, e.p);
+    return true;
+}
+int64_t pool_trim_dev(int device) {
+    DevPool *P = pool_of(device);
+    if (!P) return 0;
+    std::vector<PoolEntry> all;
+    { std::lock_guard<std::mutex> g(P->mu); all.swap(P->blocks); P->bytes = 0; }
+    int64_t freed = 0;
+    for (auto &e : all) { raw_free(device, e.p); freed += (int64_t)(e.cap * sizeof(double)); }
+    return freed;
+}
+}  // namespace
+
 DevBuf::~DevBuf() {
-    if (p) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(device); cudaFree(p); cudaSetDevice(cur); }
+    if (!p) return;
+    // listed only when nothing can still be using it (see above); cudaFree waits for the device, the list does not
+    if (cudaStreamQuery(st) == cudaSuccess && pool_give(device, p, cap)) return;
+    cudaGetLastError();
+    raw_free(device, p);
 }
 int dev_alloc(int device, size_t count, bool zero, cudaStream_t st, DevBufPtr &out) {
     auto b = std::make_shared<DevBuf>();
-    b->device = device; b->count = count;
+    b->device = device; b->count = count; b->st = st;
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc(&b->p, count * sizeof(double));
-    if (e != cudaSuccess) { b->p = nullptr; set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(double), cudaGetErrorString(e)); cudaGetLastError(); return SSM_E_NOMEM; }
+    b->cap = count;
+    b->p = pool_take(device, count, &b->cap);
+    if (!b->p) {
+        cudaError_t e = cudaMalloc(&b->p, count * sizeof(double));
+        if (e != cudaSuccess && pool_trim_dev(device) > 0) { cudaGetLastError(); e = cudaMalloc(&b->p, count * sizeof(double)); }
+        if (e != cudaSuccess) { b->p = nullptr; set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(double), cudaGetErrorString(e)); cudaGetLastError(); return SSM_E_NOMEM; }
+    }
     if (zero) SSM_CUDA(cudaMemsetAsync(b->p, 0, count * sizeof(double), st));
     out = b;
     return 0;
@@ -169,6 +252,17 @@ int ssm_ctx_get_option(ssm_ctx *c, const char *key, int *value) {
     return 0;
 }
 int64_t ssm_ctx_launch_count(ssm_ctx *c) { return c ? c->launches : 0; }
+int64_t ssm_pool_trim(int device) { return pool_trim_dev(device); }
+int ssm_pool_stats(int device, int64_t *bytes, int64_t *blocks, int64_t *hits, int64_t *misses) {
+    DevPool *P = pool_of(device);
+    int64_t v[4] = {0, 0, 0, 0};
+    if (P) { std::lock_guard<std::mutex> g(P->mu); v[0] = (int64_t)P->bytes; v[1] = (int64_t)P->blocks.size(); v[2] = P->hits; v[3] = P->misses; }
+    if (bytes) *bytes = v[0];
+    if (blocks) *blocks = v[1];
+    if (hits) *hits = v[2];
+    if (misses) *misses = v[3];
+    return P ? 0 : SSM_E_UNSUPPORTED;
+}
 
 
 // ---- vectors ----------------------------------------------------------------------------------------------

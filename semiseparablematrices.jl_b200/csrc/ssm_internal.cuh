@@ -25,8 +25,10 @@ inline int64_t ntiles_of(int64_t nb) { return (nb + TILE - 1) / TILE; }
 
 struct DevBuf {
     double *p = nullptr;
-    size_t  count = 0;
+    size_t  count = 0;          // doubles asked for
+    size_t  cap = 0;            // doubles the block holds (>= count when it came off the free list, api.cu)
     int     device = 0;
+    cudaStream_t st = nullptr;  // stream of the context it was allocated for
     ~DevBuf();
 };
 using DevBufPtr = std::shared_ptr<DevBuf>;

@@ -63,6 +63,10 @@ function context()
     CTX[]
 end
 
+# Device blocks of destroyed handles (<= 64 MiB each) stay on the library's per-device free list, so qr(A) / ldiv! on one matrix per
+# call cost no cudaMalloc / cudaFree; trim_pool() hands them back to the driver (e.g. before another library needs the memory).
+trim_pool() = ccall((:ssm_pool_trim, libssm), Int64, (Cint,), DEVICE[])
+
 # ---- thin RAII wrappers around the opaque handles -------------------------------------------------------------------
 mutable struct Handle
     p::Ptr{Cvoid}

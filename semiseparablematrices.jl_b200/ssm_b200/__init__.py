@@ -3,5 +3,5 @@ reference's operator names.  Thin host layer over libssmb200.so (C ABI in includ
 from ._lib import DimensionMismatch, SSMError, SSM_DIST_BC, SSM_DIST_DD, exported_symbols, lib  # noqa: F401
 from .almostbanded import (AlmostBandedMatrix, AlmostBandedQR, Context, LowerTriangular,  # noqa: F401
                            UnitLowerTriangular, UnitUpperTriangular, UpperTriangular, Vec, almostbandedrank,
-                           almostbandwidths, bandpart, default_context, factorize, fillpart, ldiv, qr, solve,
+                           almostbandwidths, bandpart, default_context, factorize, fillpart, ldiv, pool_stats, pool_trim, qr, solve,
                            solve_host)

@@ -93,6 +93,18 @@ def default_context(device: int = 0) -> Context:
     return _default_ctx[device]
 
 
+def pool_stats(device: int = 0) -> dict:
+    """The per-device free list of small device blocks (``ssm_pool_stats``): bytes and blocks listed, hits and misses so far."""
+    v = [C.c_int64() for _ in range(4)]
+    check(_lib.lib().ssm_pool_stats(int(device), *[C.byref(x) for x in v]), "ssm_pool_stats")
+    return dict(zip(("bytes", "blocks", "hits", "misses"), (int(x.value) for x in v)))
+
+
+def pool_trim(device: int = 0) -> int:
+    """Give the listed blocks of ``device`` back to the driver; returns the bytes freed (``ssm_pool_trim``)."""
+    return int(_lib.lib().ssm_pool_trim(int(device)))
+
+
 class Vec:
     """Batch of length-n vectors in the device layout (``ssm_vec``)."""
 

@@ -48,3 +48,58 @@ def test_chunked_path_tiny_systems(ctx, l, u, r):
                 assert np.linalg.norm(x - x0) <= 1e-12 * np.linalg.norm(x0), (n, A.chunks, min_chunks)
         finally:
             ctx.set_option("abc_tiled_min_chunks", default)
+
+
+def _one_qr_solve(ssm, ctx, bands, U, V, b, l, u):
+    """what the Julia glue does for qr(A) \\ b on one matrix: operand batch, factor object and vector made and destroyed per call"""
+    A = ssm.AlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
+    F = ssm.qr(A)
+    x = F.ldiv(b.copy())
+    fac, Uf, tau = F.get()
+    del F, A
+    return x, fac, tau
+
+
+def test_recycled_device_blocks_give_identical_results(ctx):
+    """Per-device free list (ssm_pool_*, api.cu): the second and later calls take their device blocks off the list (hits grow),
+    results stay bit-identical to the first call's, and stale contents of a recycled block (here: NaN) never reach a result."""
+    import gc
+    import ssm_b200 as ssm
+    n, l, u, r = 1000, 2, 2, 2
+    bands, U, V, b = oracle.ab_generate(n, l, u, r, 1, seed=11)
+    ssm.pool_trim(0)
+    x0, fac0, tau0 = _one_qr_solve(ssm, ctx, bands, U, V, b, l, u)
+    gc.collect()
+    s0 = ssm.pool_stats(0)
+    assert s0["blocks"] > 0 and 0 < s0["bytes"] <= 512 << 20
+    for _ in range(3):
+        x, fac, tau = _one_qr_solve(ssm, ctx, bands, U, V, b, l, u)
+        assert np.array_equal(x, x0) and np.array_equal(fac, fac0) and np.array_equal(tau, tau0)
+    gc.collect()
+    s1 = ssm.pool_stats(0)
+    assert s1["hits"] >= s0["hits"] + 9, (s0, s1)       # operands (2) + factors (2) + vector per call, at least
+    # poison every listed block size with NaN through vectors of the same footprint, then solve again
+    sizes = sorted({(n + 48) * f for f in (1, r, l + 1, l + u + 1 + r)})
+    for rep in range(2):
+        vs = [ssm.Vec(ctx, cnt - 48, 32, data=np.full((32, cnt - 48), np.nan)) for cnt in sizes for _ in range(2)]
+        del vs
+        gc.collect()
+    x, fac, tau = _one_qr_solve(ssm, ctx, bands, U, V, b, l, u)
+    assert np.array_equal(x, x0) and np.array_equal(fac, fac0) and np.array_equal(tau, tau0)
+    xd = np.linalg.solve(dense(bands[0], U[0], V[0], l, u), b[0])
+    assert np.linalg.norm(x[0] - xd) <= 1e-12 * np.linalg.norm(xd)
+    # a different context (another stream) may take the same blocks; large batches never enter the list
+    ctx2 = ssm.Context(0)
+    x2, _, _ = _one_qr_solve(ssm, ctx2, bands, U, V, b, l, u)
+    assert np.array_equal(x2, x0)
+    big = ssm.Vec(ctx2, 1024, 16384)                     # 140 MB > the 64 MiB block limit
+    before = ssm.pool_stats(0)["bytes"]
+    del big
+    gc.collect()
+    assert ssm.pool_stats(0)["bytes"] == before
+    ctx2.close()
+    assert ssm.pool_trim(0) > 0
+    s2 = ssm.pool_stats(0)
+    assert s2["bytes"] == 0 and s2["blocks"] == 0
+    x, _, _ = _one_qr_solve(ssm, ctx, bands, U, V, b, l, u)
+    assert np.array_equal(x, x0)
