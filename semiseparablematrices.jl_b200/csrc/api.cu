@@ -320,6 +320,8 @@ int ssm_vec_copy(ssm_vec *dst, const ssm_vec *src) {
     if (dst->n != src->n || dst->nb != src->nb) { set_error("ssm_vec_copy: shape mismatch"); return SSM_E_SHAPE; }
     DeviceGuard g(dst->ctx->device);
     SSM_CUDA(cudaMemcpyAsync(dst->d->p, src->d->p, src->d->count * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    // a copy between contexts reads src on dst's stream: finish it here, so that src's own stream still orders everything that touches src
+    if (dst->ctx->stream != src->ctx->stream) SSM_CUDA(cudaStreamSynchronize(dst->ctx->stream));
     return 0;
 }
 int ssm_vec_generate(ssm_vec *v, uint64_t seed, int array_id) {
