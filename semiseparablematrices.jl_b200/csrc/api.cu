@@ -261,7 +261,7 @@ int ssm_pool_stats(int device, int64_t *bytes, int64_t *blocks, int64_t *hits, i
     if (blocks) *blocks = v[1];
     if (hits) *hits = v[2];
     if (misses) *misses = v[3];
-    return P ? 0 : SSM_E_UNSUPPORTED;
+    return 0;                         // list switched off (SSM_POOL=0): all zero
 }
 
 
