@@ -93,6 +93,10 @@ int  ssm_ab_set(ssm_ab *A, const double *bands, int64_t bands_stride, const doub
 int  ssm_ab_get(const ssm_ab *A, double *bands, int64_t bands_stride, double *U, int64_t U_stride,
                 double *V, int64_t V_stride);
 int  ssm_ab_generate(ssm_ab *A, uint64_t seed, int dist);       /* device-side synthetic operands        */
+/* resize(A, n_new, n_new) (AlmostBandedMatrix.jl:338-348, the step resizedata! :368-371 takes when a cached operand outgrows its
+ * storage): a new batch of n_new x n_new matrices holding the same bands and fill; the new band entries, the new rows of U and the
+ * new columns of V are zero.  n_new < n is a DimensionMismatch (SSM_E_SHAPE), as Zeros(m - size(U,1), r) is in the reference. */
+int  ssm_ab_resize(const ssm_ab *A, int n_new, ssm_ab **out);
 /* Vcat(a, Bd) front end (AlmostBandedMatrix.jl:298-305 bandwidth rule, :316-337 copyto!): the boundary-row form spectral-method
  * callers produce.  a: r x n dense rows (column-major), Bd: (lb+ub+1) x n band storage of the (n-r) x n banded block.  Builds
  * U = [I_r; 0], V = a and the bands directly in the device layout.  A must have been created with r rows of fill and bandwidths

@@ -347,6 +347,32 @@ int ssm_ab_create(ssm_ctx *c, int n, int l, int u, int r, int64_t nb, ssm_ab **o
 }
 int ssm_ab_destroy(ssm_ab *A) { if (A) { cudaStreamSynchronize(A->ctx->stream); delete A; } return 0; }
 
+// resize(A, n_new, n_new) (AlmostBandedMatrix.jl:338-348): the same bands and fill in a larger matrix, new band rows / columns, new rows of U
+// and new columns of V zero.  A tile's rows are contiguous ([tile][np][nf][32]), so the old rows of every tile move in one strided copy into
+// the zero-initialised larger batch; nothing is repacked.
+static int copy_tile_rows(ssm_ctx *c, double *dst, int64_t np_dst, const double *src, int64_t np_src, int64_t rows, int nf, int64_t ntiles) {
+    const size_t rec = (size_t)nf * TILE * sizeof(double);
+    if ((size_t)np_dst * rec < (size_t)0x7fffffff)
+        SSM_CUDA(cudaMemcpy2DAsync(dst, (size_t)np_dst * rec, src, (size_t)np_src * rec, (size_t)rows * rec, (size_t)ntiles, cudaMemcpyDeviceToDevice, c->stream));
+    else
+        for (int64_t t = 0; t < ntiles; t++)
+            SSM_CUDA(cudaMemcpyAsync(dst + t * np_dst * nf * TILE, src + t * np_src * nf * TILE, (size_t)rows * rec, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+int ssm_ab_resize(const ssm_ab *A, int n_new, ssm_ab **out) {
+    SSM_CHECK_ARG(A && out, "null argument");
+    if (n_new < A->n) { set_error("ssm_ab_resize: DimensionMismatch: cannot shrink a %d x %d matrix to %d x %d", A->n, A->n, n_new, n_new); return SSM_E_SHAPE; }
+    ssm_ctx *c = A->ctx;
+    ssm_ab *B = nullptr;
+    SSM_TRY(ssm_ab_create(c, n_new, A->l, A->u, A->r, A->nb, &B));
+    DeviceGuard g(c->device);
+    int rc = copy_tile_rows(c, B->AU->p, B->np, A->AU->p, A->np, A->n, A->l + A->u + 1 + A->r, A->ntiles);
+    if (!rc && A->r > 0) rc = copy_tile_rows(c, B->V->p, B->np, A->V->p, A->np, A->n, A->r, A->ntiles);
+    if (rc) { ssm_ab_destroy(B); return rc; }
+    *out = B;
+    return 0;
+}
+
 int ssm_ab_set(ssm_ab *A, const double *bands, int64_t sb, const double *U, int64_t su, const double *V, int64_t sv) {
     SSM_CHECK_ARG(A && bands && (A->r == 0 || (U && V)), "null argument");
     ssm_ctx *c = A->ctx;

@@ -221,6 +221,14 @@ class AlmostBandedMatrix:
         check(_lib.lib().ssm_ab_set_vcat(self._h, c_vp(a.ctypes.data), 0, c_vp(Bd.ctypes.data), 0, lb, ub), "ssm_ab_set_vcat")
         return self
 
+    def resize(self, n: int) -> "AlmostBandedMatrix":
+        """``resize(A, n, n)`` (AlmostBandedMatrix.jl:338-348): the same bands and fill in a larger matrix, everything new zero; on the device."""
+        new = type(self).__new__(type(self))
+        new.ctx, new.n, new.l, new.u, new.r, new.nb, new.single = self.ctx, int(n), self.l, self.u, self.r, self.nb, self.single
+        new._h = c_vp()
+        check(_lib.lib().ssm_ab_resize(self._h, int(n), C.byref(new._h)), "ssm_ab_resize")
+        return new
+
     # -- reference accessors ----------------------------------------------------------------------
     @property
     def shape(self):

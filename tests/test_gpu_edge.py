@@ -103,3 +103,27 @@ def test_recycled_device_blocks_give_identical_results(ctx):
     assert s2["bytes"] == 0 and s2["blocks"] == 0
     x, _, _ = _one_qr_solve(ssm, ctx, bands, U, V, b, l, u)
     assert np.array_equal(x, x0)
+
+
+@pytest.mark.parametrize("l,u,r", [(2, 1, 2), (1, 0, 1), (4, 4, 2)])
+def test_resize_keeps_bands_and_fill_and_zero_pads(ctx, l, u, r):
+    """resize(A, m, m) (AlmostBandedMatrix.jl:338-348) on the device: same bands and fill, new band entries / U rows / V columns zero,
+    the dense matrix is [A 0; 0 0]; shrinking is a DimensionMismatch."""
+    import ssm_b200 as ssm
+    n, m, nb = 50, 83, 37                                   # two tiles, the second partly filled
+    bands, U, V, b = oracle.ab_generate(n, l, u, r, nb, seed=5)
+    A = ssm.AlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
+    B = A.resize(m)
+    assert B.shape == (m, m) and B.almostbandwidths() == (l, u) and B.almostbandedrank() == r
+    b2, (U2, V2) = B.bandpart(), B.fillpart()
+    assert np.array_equal(b2[:, :n], bands) and not b2[:, n:].any()
+    assert np.array_equal(U2[:, :, :n], U) and not U2[:, :, n:].any()
+    assert np.array_equal(V2[:, :n], V) and not V2[:, n:].any()
+    for s in (0, nb - 1):
+        D = dense(b2[s], U2[s], V2[s], l, u)
+        assert np.array_equal(D[:n, :n], dense(bands[s], U[s], V[s], l, u)) and not D[n:].any() and not D[:, n:].any()
+    b0, (U0, V0) = A.bandpart(), A.fillpart()               # the operand itself is untouched
+    assert np.array_equal(b0, bands) and np.array_equal(U0, U) and np.array_equal(V0, V)
+    assert np.array_equal(A.resize(n).bandpart(), bands)    # same size: a copy
+    with pytest.raises(ssm.DimensionMismatch):
+        A.resize(n - 1)
