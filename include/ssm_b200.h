@@ -97,6 +97,11 @@ int  ssm_ab_generate(ssm_ab *A, uint64_t seed, int dist);       /* device-side s
  * storage): a new batch of n_new x n_new matrices holding the same bands and fill; the new band entries, the new rows of U and the
  * new columns of V are zero.  n_new < n is a DimensionMismatch (SSM_E_SHAPE), as Zeros(m - size(U,1), r) is in the reference. */
 int  ssm_ab_resize(const ssm_ab *A, int n_new, ssm_ab **out);
+/* The copy resizedata! makes after growing (:373-389): rows [k0, k1) (0-based, half open) of every matrix — the band entries
+ * A[i, i-l .. i+u], U[i, :] and V[:, i] — are taken from full reference-layout arrays of A's size (same arguments as ssm_ab_set);
+ * all other rows keep their contents.  Host arrays: only the windows that hold those rows are copied to the device.          */
+int  ssm_ab_set_rows(ssm_ab *A, int k0, int k1, const double *bands, int64_t bands_stride, const double *U, int64_t U_stride,
+                     const double *V, int64_t V_stride);
 /* Vcat(a, Bd) front end (AlmostBandedMatrix.jl:298-305 bandwidth rule, :316-337 copyto!): the boundary-row form spectral-method
  * callers produce.  a: r x n dense rows (column-major), Bd: (lb+ub+1) x n band storage of the (n-r) x n banded block.  Builds
  * U = [I_r; 0], V = a and the bands directly in the device layout.  A must have been created with r rows of fill and bandwidths

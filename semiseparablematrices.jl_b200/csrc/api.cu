@@ -398,6 +398,43 @@ int ssm_ab_set(ssm_ab *A, const double *bands, int64_t sb, const double *U, int6
     return 0;
 }
 
+// Rows [k0, k1) of every matrix from full reference-layout arrays: the band entries A[i, i-l .. i+u], U[i, :] and V[:, i] for k0 <= i < k1;
+// every other row keeps what it holds.  This is the copy resizedata! makes after it has grown the storage (AlmostBandedMatrix.jl:373-389:
+// the new columns of V, the new rows of U, the new part of the band).  Host arrays: only the band columns [k0-l, k1+u), the rows
+// k0..k1-1 of U and the columns k0..k1-1 of V cross the bus.
+int ssm_ab_set_rows(ssm_ab *A, int k0, int k1, const double *bands, int64_t sb, const double *U, int64_t su, const double *V, int64_t sv) {
+    SSM_CHECK_ARG(A && bands && (A->r == 0 || (U && V)), "null argument");
+    if (k0 < 0 || k1 > A->n || k0 > k1) { set_error("ssm_ab_set_rows: BoundsError: rows [%d, %d) of a %d x %d matrix", k0, k1, A->n, A->n); return SSM_E_SHAPE; }
+    if (k0 == k1) return 0;
+    ssm_ctx *c = A->ctx;
+    DeviceGuard g(c->device);
+    const int n = A->n, l = A->l, u = A->u, r = A->r, nd = l + u + 1;
+    const size_t eb = (size_t)nd * n, eu = (size_t)n * r;
+    if (sb == 0) sb = (int64_t)eb;
+    if (su == 0) su = (int64_t)eu;
+    if (sv == 0) sv = (int64_t)eu;
+    if ((size_t)sb < eb || (size_t)su < eu || (size_t)sv < eu) { set_error("ssm_ab_set_rows: Data and fill must be compatible size (stride smaller than one system)"); return SSM_E_SHAPE; }
+    const bool db = is_device_ptr(bands), du = r == 0 || is_device_ptr(U), dv = r == 0 || is_device_ptr(V);
+    if (db && du && dv) return launch_ab_pack_rows(c, A, bands, sb, 0, U, su, n, V, sv, 0, 0, A->nb, k0, k1);
+    const int64_t jlo = std::max(k0 - l, 0), jhi = std::min(k1 + u, n), rows = k1 - k0;
+    const size_t wb = (size_t)nd * (jhi - jlo), wu = (size_t)rows * r;            // window sizes per system
+    const int64_t ch = chunk_systems(wb + 2 * wu, A->nb);
+    for (int64_t s0 = 0; s0 < A->nb; s0 += ch) {
+        const int64_t cnt = std::min(ch, A->nb - s0);
+        double *stg;
+        SSM_TRY(staging_dev(c, (size_t)cnt * (wb + 2 * wu), &stg));
+        double *sB = stg, *sU = sB + (size_t)cnt * wb, *sV = sU + (size_t)cnt * wu;
+        SSM_TRY(h2d_block(c, sB, bands + s0 * sb + (int64_t)nd * jlo, sb, wb, cnt));
+        for (int q = 0; q < r; q++)                                                // rows k0..k1-1 of column q of U: [system][q][row] in the window
+            SSM_CUDA(cudaMemcpy2DAsync(sU + (size_t)q * rows, wu * sizeof(double), U + s0 * su + (int64_t)q * n + k0, (size_t)su * sizeof(double),
+                                       (size_t)rows * sizeof(double), (size_t)cnt, cudaMemcpyDefault, c->stream));
+        if (r > 0) SSM_TRY(h2d_block(c, sV, V + s0 * sv + (int64_t)r * k0, sv, wu, cnt));
+        SSM_TRY(launch_ab_pack_rows(c, A, sB, (int64_t)wb, jlo, sU, (int64_t)wu, rows, sV, (int64_t)wu, k0, s0, cnt, k0, k1));
+    }
+    SSM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // almostbandwidths(Vcat(a, Bd)) (AlmostBandedMatrix.jl:298-303): (max(lb + r, r - 1), ub - r); the device batch needs u >= 0, a
 // negative upper bandwidth is widened to 0 (the diagonal then holds the fill values it would otherwise have been read from).
 int ssm_ab_vcat_bandwidths(int r, int lb, int ub, int *l, int *u) {

@@ -161,6 +161,8 @@ int launch_ab_tri(ssm_ctx *c, const ssm_ab *A, double *rhs, bool upper, bool uni
 // util_kernels.cu
 int launch_ab_pack(ssm_ctx *c, ssm_ab *A, const double *bands, int64_t sb, const double *U, int64_t su,
                    const double *V, int64_t sv, int64_t s0, int64_t count);
+int launch_ab_pack_rows(ssm_ctx *c, ssm_ab *A, const double *bands, int64_t sb, int64_t jlo, const double *U, int64_t su, int64_t ldu,
+                        const double *V, int64_t sv, int64_t i0u, int64_t s0, int64_t count, int64_t i0, int64_t i1);
 int launch_ab_pack_vcat(ssm_ctx *c, ssm_ab *A, const double *a, int64_t sa, const double *Bd, int64_t sbd, int lb, int ub);
 int launch_ab_unpack(ssm_ctx *c, const ssm_ab *A, double *bands, int64_t sb, double *U, int64_t su, double *V,
                      int64_t sv);

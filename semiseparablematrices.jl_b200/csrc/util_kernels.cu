@@ -34,6 +34,33 @@ __global__ void ab_pack_kernel(double *AU, double *Vd, const double *bands, int6
     for (int q = 0; q < r; ++q) vrec[q * 32] = live ? V[(s - s0) * sv + q + (int64_t)r * i] : 0.0;
 }
 
+// rows [i0, i1) of the records only (ssm_ab_set_rows).  The source arrays may be windows of the reference-layout arrays: band columns
+// from jlo on (sb = doubles per system of the window), rows of U from i0u on with leading dimension ldu, columns of V from i0u on.
+__global__ void ab_pack_rows_kernel(double *AU, double *Vd, const double *bands, int64_t sb, int64_t jlo, const double *U, int64_t su,
+                                    int64_t ldu, const double *V, int64_t sv, int64_t i0u, int n, int l, int u, int r, int64_t nb,
+                                    int64_t np, int64_t s0, int64_t count, int64_t i0, int64_t i1) {
+    const int lane = threadIdx.x;
+    const int64_t i = i0 + (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    const int64_t tile = (int64_t)blockIdx.y + s0 / TILE;
+    const int64_t s = tile * TILE + lane;
+    if (i >= i1) return;
+    const bool live = s < nb && s >= s0 && s < s0 + count;
+    if (!live && s < nb) return;                           // another chunk owns this lane; lanes past the batch hold identity rows
+    const int nfa = l + u + 1 + r;
+    double *rec = AU + ((tile * np + i) * nfa) * 32 + lane;
+    const double *bs = bands + (s - s0) * sb;
+    for (int d = 0; d <= l + u; ++d) {
+        const int64_t j = i - l + d;
+        double val = 0.0;
+        if (live) { if (j >= 0 && j < n) val = bs[(int64_t)(l + u - d) + (int64_t)(l + u + 1) * (j - jlo)]; }
+        else val = (d == l) ? 1.0 : 0.0;
+        rec[d * 32] = val;
+    }
+    for (int q = 0; q < r; ++q) rec[(l + u + 1 + q) * 32] = live ? U[(s - s0) * su + (i - i0u) + ldu * q] : 0.0;
+    double *vrec = Vd + ((tile * np + i) * (r > 0 ? r : 1)) * 32 + lane;
+    for (int q = 0; q < r; ++q) vrec[q * 32] = live ? V[(s - s0) * sv + q + (int64_t)r * (i - i0u)] : 0.0;
+}
+
 __global__ void ab_unpack_kernel(const double *AU, const double *Vd, double *bands, int64_t sb, double *U, int64_t su,
                                  double *V, int64_t sv, int n, int l, int u, int r, int64_t nb, int64_t np) {
     const int lane = threadIdx.x;
@@ -216,6 +243,17 @@ int launch_ab_pack(ssm_ctx *c, ssm_ab *A, const double *bands, int64_t sb, const
     int64_t tiles = (send + TILE - 1) / TILE - s0 / TILE;
     ab_pack_kernel<<<rec_grid(A->n, tiles), dim3(32, 8), 0, c->stream>>>(A->AU->p, A->V->p, bands, sb, U, su, V, sv, A->n, A->l, A->u,
                                                                           A->r, A->nb, A->np, s0, count);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_ab_pack_rows(ssm_ctx *c, ssm_ab *A, const double *bands, int64_t sb, int64_t jlo, const double *U, int64_t su, int64_t ldu,
+                        const double *V, int64_t sv, int64_t i0u, int64_t s0, int64_t count, int64_t i0, int64_t i1) {
+    if (count <= 0 || i1 <= i0) return 0;
+    if (s0 % TILE != 0) { set_error("pack chunk must start on a tile boundary"); return SSM_E_ARG; }
+    const int64_t tiles = (s0 + count + TILE - 1) / TILE - s0 / TILE;
+    ab_pack_rows_kernel<<<rec_grid((int)(i1 - i0), tiles), dim3(32, 8), 0, c->stream>>>(A->AU->p, A->V->p, bands, sb, jlo, U, su, ldu, V, sv, i0u, A->n, A->l,
+                                                                                         A->u, A->r, A->nb, A->np, s0, count, i0, i1);
     c->launches++;
     SSM_CUDA(cudaGetLastError());
     return 0;

@@ -54,6 +54,7 @@ _SIGS = {
     "ssm_ab_get": (C.c_int, [c_vp, c_vp, i64, c_vp, i64, c_vp, i64]),
     "ssm_ab_generate": (C.c_int, [c_vp, u64, C.c_int]),
     "ssm_ab_resize": (C.c_int, [c_vp, C.c_int, C.POINTER(c_vp)]),
+    "ssm_ab_set_rows": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp, i64, c_vp, i64, c_vp, i64]),
     "ssm_ab_vcat_bandwidths": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssm_ab_set_vcat": (C.c_int, [c_vp, c_vp, i64, c_vp, i64, C.c_int, C.c_int]),
     "ssm_ab_qr": (C.c_int, [c_vp, C.POINTER(c_vp)]),

@@ -229,6 +229,21 @@ class AlmostBandedMatrix:
         check(_lib.lib().ssm_ab_resize(self._h, int(n), C.byref(new._h)), "ssm_ab_resize")
         return new
 
+    def set_rows(self, k0: int, k1: int, bands, fill):
+        """Rows ``k0 <= i < k1`` (0-based) of every matrix — ``A[i, i-l..i+u]``, ``U[i,:]``, ``V[:,i]`` — from full arrays in the constructor's
+        layout; the other rows keep their contents.  The copy ``resizedata!`` makes after ``resize`` (AlmostBandedMatrix.jl:373-389)."""
+        U, V = fill
+        if self.single and ((np.ndim(bands) == 2) if not _is_torch(bands) else (bands.dim() == 2)):
+            bands, U, V = bands[None], U[None], V[None]
+        nb, n, w, r = self.nb, self.n, self.l + self.u + 1, self.r
+        if tuple(bands.shape) != (nb, n, w) or tuple(U.shape) != (nb, r, n) or tuple(V.shape) != (nb, n, r):
+            raise DimensionMismatch("Data and fill must be compatible size")
+        pb, kb = _as_ptr(bands, (nb, n, w), "bands")
+        pu, ku = _as_ptr(U, (nb, r, n), "U")
+        pv, kv = _as_ptr(V, (nb, n, r), "V")
+        check(_lib.lib().ssm_ab_set_rows(self._h, int(k0), int(k1), c_vp(pb), 0, c_vp(pu), 0, c_vp(pv), 0), "ssm_ab_set_rows")
+        return self
+
     # -- reference accessors ----------------------------------------------------------------------
     @property
     def shape(self):

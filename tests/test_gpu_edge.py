@@ -127,3 +127,46 @@ def test_resize_keeps_bands_and_fill_and_zero_pads(ctx, l, u, r):
     assert np.array_equal(A.resize(n).bandpart(), bands)    # same size: a copy
     with pytest.raises(ssm.DimensionMismatch):
         A.resize(n - 1)
+
+
+@pytest.mark.parametrize("l,u,r", [(2, 2, 2), (1, 0, 1), (3, 1, 3)])
+@pytest.mark.parametrize("on_device", [False, True])
+def test_grow_then_set_rows_equals_fresh_upload(ctx, l, u, r, on_device):
+    """The resizedata! flow (AlmostBandedMatrix.jl:350-394) on the device: the leading n x n part is uploaded, the batch is grown to
+    m x m (ssm_ab_resize) and only the rows from n-u on are sent (ssm_ab_set_rows).  Operands, factors and solutions are then
+    bit-identical to those of a batch built from the full arrays; rows outside the range keep their contents."""
+    import torch
+    import ssm_b200 as ssm
+    n, m, nb = 40, 97, 35
+    bands, U, V, b = oracle.ab_generate(m, l, u, r, nb, seed=8)
+    full = ssm.AlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
+    lead_b = np.ascontiguousarray(bands[:, :n]); lead_U = np.ascontiguousarray(U[:, :, :n]); lead_V = np.ascontiguousarray(V[:, :n])
+    for j in range(n):                                     # band entries of the leading part that lie outside the n x n matrix
+        for d in range(l + u + 1):
+            if not 0 <= j + d - u < n:
+                lead_b[:, j, d] = 0.0
+    A = ssm.AlmostBandedMatrix(lead_b, (lead_U, lead_V), (l, u), ctx=ctx).resize(m)
+    k0 = max(n - u, 0)                                     # rows n-u..n-1 gain entries in the new columns
+    if on_device:
+        dev = [torch.from_numpy(a).cuda() for a in (bands, U, V)]
+        A.set_rows(k0, m, dev[0], (dev[1], dev[2]))
+    else:
+        A.set_rows(k0, m, bands, (U, V))
+    b1, (U1, V1) = A.bandpart(), A.fillpart()
+    b0, (U0, V0) = full.bandpart(), full.fillpart()
+    assert np.array_equal(b1, b0) and np.array_equal(U1, U0) and np.array_equal(V1, V0)
+    x0 = ssm.qr(full).ldiv(b.copy()); x1 = ssm.qr(A).ldiv(b.copy())
+    assert np.array_equal(x0, x1)
+    xd = np.linalg.solve(dense(bands[3], U[3], V[3], l, u), b[3])
+    assert np.linalg.norm(x1[3] - xd) <= 1e-12 * np.linalg.norm(xd)
+    # a range in the middle leaves the rest alone
+    junk = np.full_like(bands, 7.0), (np.full_like(U, 7.0), np.full_like(V, 7.0))
+    A.set_rows(10, 13, junk[0], junk[1])
+    b2, (U2, V2) = A.bandpart(), A.fillpart()
+    rows = np.r_[0:10, 13:m]
+    assert np.array_equal(U2[:, :, rows], U0[:, :, rows]) and np.array_equal(V2[:, rows], V0[:, rows]) and (U2[:, :, 10:13] == 7.0).all()
+    for i in rows:                                         # band row i = entries (i, j), stored at bands[j, u + i - j]
+        for j in range(max(i - l, 0), min(i + u, m - 1) + 1):
+            assert np.array_equal(b2[:, j, u + i - j], b0[:, j, u + i - j])
+    with pytest.raises(ssm.DimensionMismatch):
+        A.set_rows(5, m + 1, bands, (U, V))
