@@ -158,8 +158,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"batched AlmostBandedMatrix qr+ldiv! fp64, n={n}, l=u={l}, r={r}", "systems_per_step": sample,
-                   "note": "CPU reference arm: rank 0 only, host cores; one step = a bounded sample of the workload"},
+        "config": {"workload": f"BASELINE.json configs[1]: batched AlmostBandedMatrix qr + ldiv! fp64, n={n}, l=u={l}, r={r}, "
+                               f"{NB_PER_GPU} systems per GPU", "n": n, "l": l, "u": u, "r": r, "systems_per_gpu": NB_PER_GPU,
+                   "systems_per_step": sample, "seed": SEED,
+                   "note": "CPU reference arm: rank 0 only, host cores; one step = a bounded sample of the workload "
+                           f"({sample} of its {NB_PER_GPU} systems)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} systems per step; oracle port (Julia unavailable in this image)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
