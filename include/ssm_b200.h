@@ -68,7 +68,7 @@ int  ssm_ctx_set_option(ssm_ctx *ctx, const char *key, int value);
 int  ssm_ctx_get_option(ssm_ctx *ctx, const char *key, int *value);
 /* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */
 int64_t ssm_ctx_launch_count(ssm_ctx *ctx);
-/* Device blocks of destroyed objects (<= 64 MiB each, <= 512 MiB per device) are kept on a per-device free list and handed to the
+/* Device blocks of destroyed objects (<= 64 MiB each, <= 512 MiB and 256 blocks per device) are kept on a per-device free list and handed to the
    next ssm_*_create of a similar size, so that a caller who builds, factorises and destroys one matrix per call — what Julia's
    qr(A) / A \ b do (AlmostBandedMatrix.jl:126-133 allocates its factors per call as well) — pays no cudaMalloc / cudaFree.
    ssm_pool_trim returns the listed blocks of `device` to the driver (bytes freed); ssm_pool_stats reports the list

@@ -27,7 +27,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 // ---- per-device free list of small device blocks ---------------------------------------------------------------
 // A caller that factorises one matrix per call (the Julia glue: qr(A) creates an operand batch, a factor object and a vector and
 // destroys them again) paid a cudaMalloc + cudaFree per buffer, several times the kernels' own time at n ~ 1,000.  Blocks of at
-// most POOL_BLOCK_MAX bytes therefore go back to a per-device list (at most POOL_TOTAL_MAX bytes, oldest evicted first) and
+// most POOL_BLOCK_MAX bytes therefore go back to a per-device list (at most POOL_TOTAL_MAX bytes and POOL_MAX_BLOCKS blocks, oldest evicted first) and
 // dev_alloc takes the smallest listed block of at least — and at most twice — the requested size.  A block is only listed when
 // the stream it was allocated for is idle (every ssm_*_destroy synchronises its context's stream first), so it can be handed to any
 // other stream; otherwise it is cudaFree'd as before.  Large batches never pass through the list: their allocation cost is
@@ -37,6 +37,7 @@ namespace {
 constexpr size_t POOL_BLOCK_MAX = 64ull << 20;
 constexpr size_t POOL_TOTAL_MAX = 512ull << 20;
 constexpr int    POOL_MAX_DEV   = 64;
+constexpr size_t POOL_MAX_BLOCKS = 256;          // the list is searched linearly
 struct PoolEntry { double *p; size_t cap; };
 struct DevPool { std::mutex mu; std::vector<PoolEntry> blocks; size_t bytes = 0; int64_t hits = 0, misses = 0; };
 DevPool *pool_of(int device) {
@@ -74,7 +75,7 @@ bool pool_give(int device, double *p, size_t cap) {
     std::vector<PoolEntry> evict;
     {
         std::lock_guard<std::mutex> g(P->mu);
-        while (P->bytes + bytes > POOL_TOTAL_MAX && !P->blocks.empty()) {
+        while ((P->bytes + bytes > POOL_TOTAL_MAX || P->blocks.size() >= POOL_MAX_BLOCKS) && !P->blocks.empty()) {
             evict.push_back(P->blocks.front());
             P->bytes -= P->blocks.front().cap * sizeof(double);
             P->blocks.erase(P->blocks.begin());

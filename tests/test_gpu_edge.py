@@ -170,3 +170,17 @@ def test_grow_then_set_rows_equals_fresh_upload(ctx, l, u, r, on_device):
             assert np.array_equal(b2[:, j, u + i - j], b0[:, j, u + i - j])
     with pytest.raises(ssm.DimensionMismatch):
         A.set_rows(5, m + 1, bands, (U, V))
+
+
+def test_free_list_is_bounded(ctx):
+    """the per-device free list keeps at most 256 blocks (oldest evicted first), however many small objects are destroyed at once"""
+    import gc
+    import ssm_b200 as ssm
+    ssm.pool_trim(0)
+    vs = [ssm.Vec(ctx, 8 + i, 1) for i in range(300)]
+    del vs
+    gc.collect()
+    s = ssm.pool_stats(0)
+    assert 0 < s["blocks"] <= 256 and s["bytes"] <= 512 << 20, s
+    assert ssm.pool_trim(0) == s["bytes"]
+    assert ssm.pool_stats(0)["blocks"] == 0
