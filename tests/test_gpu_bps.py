@@ -154,3 +154,26 @@ def test_rq_mul_errors(bps, ctx):
     F = bps.qr(bps.BandedPlusSemiseparableMatrix(B, (U, V), (W, S), (2, 3), ctx=ctx))
     with pytest.raises(ssm_b200.DimensionMismatch):
         F.rq_mul()
+
+
+def test_random_shapes_match_oracle(bps, ctx):
+    """Sweep of 40 drawn shapes (l <= 4, m <= 5, r, p <= 3: everything the compiled instances cover by zero padding) through the
+    default kernel selection: factors, tau, Q'b and solutions against the oracle."""
+    ctx.set_option("ab_variant", 0)
+    rng = np.random.default_rng(2027)
+    for it in range(40):
+        l, m, r, p = int(rng.integers(0, 5)), int(rng.integers(0, 6)), int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        n = max(1, int(rng.choice([1, 2, 3, l + m, l + m + 1, l + m + 2, 17, 64, 150])))
+        nb = int(rng.choice([1, 5, 32, 33, 70]))
+        B, U, V, W, S, b = oracle.bps_generate(n, l, m, r, p, nb, seed=2000 + it)
+        A = bps.BandedPlusSemiseparableMatrix(B, (U, V), (W, S), (l, m), ctx=ctx)
+        F = bps.qr(A)
+        gB, gU, gV, gW, gS, gt = F.get()
+        oB, oV, oW, oS, ot = oracle.bps_qr_batch(B, U, V, W, S, l, m)
+        e = lambda a, r_: np.abs(a - r_).max() / max(1.0, np.abs(r_).max()) if a.size else 0.0
+        tag = (it, n, l, m, r, p, nb)
+        assert e(gB, oB) <= 1e-13 and e(gV, oV) <= 1e-13 and e(gW, oW) <= 1e-13 and e(gS, oS) <= 1e-13, tag
+        assert np.abs(gt - ot).max() <= 1e-13, tag
+        x = F.R.solve(F.Q.T.lmul(b))
+        ox = oracle.bps_solve_batch(oB, U, oV, oW, oS, ot, b, l, l + m)
+        assert max(relerr(x[s], ox[s]) for s in range(nb)) <= 1e-12, tag

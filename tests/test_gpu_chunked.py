@@ -142,3 +142,30 @@ def test_config4_full_size(chunked, ctx):
     # a different chunking gives the same solution to rounding
     x2 = A.solve(b, nchunks=1000).cpu().numpy()
     assert np.linalg.norm(x2 - ox) / np.linalg.norm(ox) <= 1e-12
+
+
+def test_random_shapes_and_chunk_counts_match_oracle(ctx):
+    """Sweep of 40 drawn single systems over every compiled (l+u, r) of the chunked path, sizes from 1 row to a few thousand and chunk
+    counts from 1 to n/8, both stage-3 variants: the solution against the oracle's sequential sweep and the structured residual."""
+    from ssm_b200 import chunked
+    shapes = [(1, 0), (2, 0), (4, 0), (1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (6, 2), (8, 2)]
+    rng = np.random.default_rng(2028)
+    default = ctx.get_option("abc_tiled_min_chunks")
+    try:
+        for it in range(40):
+            lp, r = shapes[int(rng.integers(0, len(shapes)))]
+            l = int(rng.integers(0, lp + 1)); u = lp - l
+            n = int(rng.choice([1, 2, lp + 1, 2 * lp + 3, 100, 1000, 4097, 20000]))
+            dist = int(rng.integers(0, 2)) if r > 0 and n > r else 0
+            bands, U, V, b = oracle.ab_generate(n, l, u, r, 1, seed=3000 + it, dist=dist)
+            A = chunked.LargeAlmostBandedMatrix(bands[0], (U[0], V[0]), (l, u), ctx=ctx)
+            ox = oracle.ab_solve(bands[0], U[0], V[0], b[0], l, u)
+            for min_chunks in (default, 1):
+                ctx.set_option("abc_tiled_min_chunks", min_chunks)
+                for nchunks in sorted({0, 1, int(rng.integers(1, max(2, n // 8 + 1)))}):
+                    x = A.solve(b[0], nchunks=nchunks)
+                    tag = (it, n, l, u, r, dist, min_chunks, nchunks)
+                    assert np.linalg.norm(x - ox) <= 1e-12 * np.linalg.norm(ox), tag
+                    assert A.residual(x, b[0]) <= 1e-13, tag
+    finally:
+        ctx.set_option("abc_tiled_min_chunks", default)
