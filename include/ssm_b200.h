@@ -117,6 +117,9 @@ int  ssm_ab_qr(const ssm_ab *A, ssm_abqr **F);
  * past ncols of F.factors hold the partially updated trailing matrix (widened band + updated fill U), tau[ncols+1:] = 0 —
  * what adaptive / incremental callers continue from.  ssm_ab_qr(A, F) == ssm_ab_qr_cols(A, n - 1, F) (:137).            */
 int  ssm_ab_qr_cols(const ssm_ab *A, int ncols, ssm_abqr **F);
+/* Continue a partial factorisation in place: F = ssm_ab_qr_cols(A, n0) holds n0 reflectors; afterwards it holds ncols >= n0 of them and equals
+ * ssm_ab_qr_cols(A, ncols) (the same A).  The step adaptive QR repeats as it needs more columns (:139-172 run on the trailing view). */
+int  ssm_abqr_continue(ssm_abqr *F, const ssm_ab *A, int ncols);
 int  ssm_abqr_destroy(ssm_abqr *F);
 /* F.factors (widened band storage (2l+u+1) x n), F.factors.fill U (n x r), F.tau (n) (:174-185)           */
 int  ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t f_stride, double *U, int64_t U_stride,

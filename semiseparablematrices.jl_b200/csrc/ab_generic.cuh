@@ -7,7 +7,9 @@
 
 namespace ssm {
 
-__device__ inline void generic_ab_qr(const AbArgs &a, int l, int u, int r, bool with_rhs, bool store_q, int64_t tile, int lane) {
+// kstart > 0 continues a partial factorisation in place (ssm_abqr_continue): reflectors 0 .. kstart-1 exist, the partially updated rows
+// kstart .. kstart+l-1 come back out of the factor records (RU: diagonal and right of it, U row; QT of columns kstart ..: the entries below).
+__device__ inline void generic_ab_qr(const AbArgs &a, int l, int u, int r, bool with_rhs, bool store_q, int64_t tile, int lane, int kstart = 0) {
     constexpr int MB = SSM_MAX_BW, MR = SSM_MAX_RANK;
     const int ub = l + u, nfa = l + u + 1 + r, nfr = nfa, nfq = l + 1, n = a.n;
     const double *au = a.AU + tile * a.np * nfa * 32 + lane;
@@ -18,6 +20,7 @@ __device__ inline void generic_ab_qr(const AbArgs &a, int l, int u, int r, bool 
     double *qt = store_q ? a.QT + tile * a.np * nfq * 32 + lane : nullptr;
     double W[MB + 1][2 * MB + 1], UC[MB + 1][MR], RH[MB + 1], v[MB];
     for (int i = 0; i <= l; ++i) { for (int t = 0; t <= ub; ++t) W[i][t] = 0.0; for (int q = 0; q < MR; ++q) UC[i][q] = 0.0; RH[i] = 0.0; }
+    if (kstart == 0) {
     for (int rho = 0; rho < l; ++rho) {       // rows resident before step 0 (AlmostBandedMatrix.jl:30-38 for their fill part)
         for (int q = 0; q < r; ++q) UC[rho][q] = au[((int64_t)rho * nfa + l + u + 1 + q) * 32];
         RH[rho] = with_rhs ? rin[(int64_t)rho * 32] : 0.0;
@@ -26,7 +29,15 @@ __device__ inline void generic_ab_qr(const AbArgs &a, int l, int u, int r, bool 
             else { double s = 0.0; for (int q = 0; q < r; ++q) s = fma(UC[rho][q], vv[((int64_t)t * r + q) * 32], s); W[rho][t] = s; }
         }
     }
-    for (int k = 0; k < n; ++k) {
+    } else {
+    for (int i = 0; i < l; ++i) {             // window row i = matrix row kstart + i, window column t = matrix column kstart + t
+        const int64_t rho = (int64_t)kstart + i;
+        for (int q = 0; q < r; ++q) UC[i][q] = ru[(rho * nfr + ub + 1 + q) * 32];
+        for (int t = 0; t <= ub; ++t)
+            W[i][t] = (t >= i) ? ru[(rho * nfr + (t - i)) * 32] : qt[(((int64_t)kstart + t) * nfq + (i - t - 1)) * 32];
+    }
+    }
+    for (int k = kstart; k < n; ++k) {
         const int64_t e = k + l;                 // entering row
         for (int t = 0; t <= ub; ++t) W[l][t] = (t <= l + u) ? au[(e * nfa + t) * 32] : 0.0;
         for (int q = 0; q < r; ++q) UC[l][q] = au[(e * nfa + l + u + 1 + q) * 32];

@@ -508,6 +508,18 @@ int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &
     return 0;
 }
 
+__global__ void __launch_bounds__(32) ab_qr_continue_kernel(const AbArgs a, int l, int u, int r, int kstart) {
+    generic_ab_qr(a, l, u, r, false, true, (int64_t)blockIdx.x, (int)threadIdx.x, kstart);
+}
+// continue a partial factorisation in place from column kstart (a.RU / a.QT hold it) to a.ncols reflectors; runtime-shape kernel for every (l,u,r)
+int launch_ab_qr_continue(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, int kstart) {
+    if (ntiles <= 0) return 0;
+    ab_qr_continue_kernel<<<(unsigned)ntiles, 32, 0, c->stream>>>(a, l, u, r, kstart);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a, bool transpose) {
     (void)u; (void)r;
     if (ntiles <= 0) return 0;

@@ -533,6 +533,23 @@ int ssm_ab_qr_cols(const ssm_ab *A, int ncols, ssm_abqr **out) {
     *out = F;
     return 0;
 }
+// _almostbanded_qr!(A, tau, ncols) continued: F holds the first F->ncols reflectors of A (ssm_ab_qr_cols); form reflectors F->ncols .. ncols-1 in
+// place.  The result is what ssm_ab_qr_cols(A, ncols) returns.  What adaptive QR does when it needs more columns of an operand it has already
+// begun to factor (the reference runs :139-172 on the trailing view; here the sweep re-enters at column F->ncols from the factor records).
+int ssm_abqr_continue(ssm_abqr *F, const ssm_ab *A, int ncols) {
+    SSM_CHECK_ARG(F && A, "null argument");
+    if (F->n != A->n || F->l != A->l || F->u != A->u || F->r != A->r || F->nb != A->nb) { set_error("ssm_abqr_continue: DimensionMismatch: factor object and operand have different shapes"); return SSM_E_SHAPE; }
+    if (ncols < F->ncols || ncols > A->n) { set_error("ssm_abqr_continue: ncols = %d outside %d..n = %d", ncols, F->ncols, A->n); return SSM_E_ARG; }
+    if (!F->QT) { set_error("ssm_abqr_continue: factor object keeps no reflectors"); return SSM_E_STATE; }
+    if (ncols == F->ncols) return 0;
+    ssm_ctx *c = F->ctx;
+    DeviceGuard g(c->device);
+    AbArgs a{A->AU->p, A->V->p, F->RU->p, F->QT->p, nullptr, nullptr, A->n, A->np, ncols};
+    SSM_TRY(F->ncols == 0 ? launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, false, true) : launch_ab_qr_continue(c, A->l, A->u, A->r, A->ntiles, a, F->ncols));
+    F->V = A->V;
+    F->ncols = ncols;
+    return 0;
+}
 int ssm_ab_qr(const ssm_ab *A, ssm_abqr **out) {
     SSM_CHECK_ARG(A && out, "null argument");
     return ssm_ab_qr_cols(A, A->n - 1, out);     // min(m - 1, n) for a real square matrix (:137)

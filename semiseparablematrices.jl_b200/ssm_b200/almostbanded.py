@@ -368,6 +368,12 @@ class AlmostBandedQR:
         self._A = A
         return self
 
+    def continue_to(self, ncols: int):
+        """Form reflectors ``self.ncols .. ncols-1`` in place (``ssm_abqr_continue``); afterwards equal to ``qr(A, ncols=ncols)``."""
+        check(_lib.lib().ssm_abqr_continue(self._h, self._A._h, int(ncols)), "ssm_abqr_continue")
+        self.ncols = int(ncols)
+        return self
+
     def get(self):
         n, l, u, r, nb = self.n, self.l, self.u, self.r, self.nb
         F = np.zeros((nb, n, 2 * l + u + 1)); U = np.empty((nb, r, n)); tau = np.empty((nb, n))
