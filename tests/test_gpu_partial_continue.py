@@ -9,6 +9,12 @@ from helpers import randn_system, relerr
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture()
+def ssm():
+    import ssm_b200
+    return ssm_b200
+
+
 @pytest.fixture(autouse=True)
 def _reset_variant(ctx):
     yield
