@@ -57,6 +57,18 @@ def lib() -> C.CDLL:
     return _LIB
 
 
+def threads(want: int = 0) -> int:
+    """OpenMP team size of the batched drivers; ``want`` > 0 sets it first (overrides an inherited OMP_NUM_THREADS)."""
+    return int(lib().ssm_oracle_threads(int(want)))
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
 def _p(a: np.ndarray):
     assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"]
     return a.ctypes.data_as(c_dp)

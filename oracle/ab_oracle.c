@@ -379,3 +379,24 @@ int ssm_oracle_ab_ldiv_batch(int n, int l, int ub, int r, int64_t nb, const doub
                            tau + (size_t)n * (size_t)s, b + (size_t)n * (size_t)s);
     return 0;
 }
+
+/* ---- OpenMP team size of the batched drivers (bench.py's cpu_baseline / --impl reference legs) ----
+ * want > 0: omp_set_num_threads(want) first — torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would
+ * silently turn the "all host cores" baseline into a single-thread one.  Returns the team size a parallel region really gets. */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+int ssm_oracle_threads(int want) {
+    int got = 1;
+#ifdef _OPENMP
+    if (want > 0) { omp_set_dynamic(0); omp_set_num_threads(want); }
+#pragma omp parallel
+    {
+#pragma omp single
+        got = omp_get_num_threads();
+    }
+#else
+    (void)want;
+#endif
+    return got;
+}
