@@ -68,6 +68,9 @@ int  ssm_ctx_set_option(ssm_ctx *ctx, const char *key, int value);
 int  ssm_ctx_get_option(ssm_ctx *ctx, const char *key, int *value);
 /* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */
 int64_t ssm_ctx_launch_count(ssm_ctx *ctx);
+/* the cudaStream_t this context enqueues on, for callers that order their own device work against it (calls that take DEVICE pointers only
+   enqueue: the caller's producer kernels must be ordered before, its consumers after — the Python twin does this for torch tensors) */
+void *ssm_ctx_stream(ssm_ctx *ctx);
 /* Device blocks of destroyed objects (<= 64 MiB each, <= 512 MiB and 256 blocks per device) are kept on a per-device free list and handed to the
    next ssm_*_create of a similar size, so that a caller who builds, factorises and destroys one matrix per call — what Julia's
    qr(A) / A \ b do (AlmostBandedMatrix.jl:126-133 allocates its factors per call as well) — pays no cudaMalloc / cudaFree.
@@ -118,7 +121,11 @@ int  ssm_ab_qr(const ssm_ab *A, ssm_abqr **F);
  * what adaptive / incremental callers continue from.  ssm_ab_qr(A, F) == ssm_ab_qr_cols(A, n - 1, F) (:137).            */
 int  ssm_ab_qr_cols(const ssm_ab *A, int ncols, ssm_abqr **F);
 /* Continue a partial factorisation in place: F = ssm_ab_qr_cols(A, n0) holds n0 reflectors; afterwards it holds ncols >= n0 of them and equals
- * ssm_ab_qr_cols(A, ncols) (the same A).  The step adaptive QR repeats as it needs more columns (:139-172 run on the trailing view). */
+ * ssm_ab_qr_cols(A, ncols) (the same A) to rounding (bit for bit when both run the same kernel family).  The step adaptive QR repeats as it
+ * needs more columns (:139-172 run on the trailing view).  ssm_abqr_ldiv / _solve / _upper_ldiv / _ldiv_mat need the complete factorisation
+ * (ncols >= n - 1) and return SSM_E_STATE before that; ssm_abqr_lmul_q / _qt apply the reflectors formed so far.
+ * A factor object shares V with the operand batch it was made from; writing to that batch afterwards (ssm_ab_set, _set_rows, _set_vcat,
+ * _generate) first gives the batch a V of its own, so live factor objects keep the matrix they factored (qr(A) copies, :129-133). */
 int  ssm_abqr_continue(ssm_abqr *F, const ssm_ab *A, int ncols);
 int  ssm_abqr_destroy(ssm_abqr *F);
 /* F.factors (widened band storage (2l+u+1) x n), F.factors.fill U (n x r), F.tau (n) (:174-185)           */

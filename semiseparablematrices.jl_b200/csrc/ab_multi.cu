@@ -12,7 +12,7 @@
 #include "stream_loader.cuh"
 
 struct ssm_mat {
-    ssm_ctx *ctx; int n, nrhs, w, ng; int64_t nb, ntiles, np;
+    ssm_ctx *ctx; ssm::CtxRef ref; int n, nrhs, w, ng; int64_t nb, ntiles, np;
     ssm::DevBufPtr d;           // [ntiles][ng][np][w][32]
 };
 
@@ -168,17 +168,17 @@ int ssm_mat_create(ssm_ctx *c, int n, int nrhs, int64_t nb, ssm_mat **out) {
     SSM_CHECK_ARG(c && out, "null argument");
     SSM_CHECK_ARG(n >= 1 && nrhs >= 1 && nb >= 1, "sizes must be positive");
     auto *B = new ssm_mat();
-    B->ctx = c; B->n = n; B->nrhs = nrhs; B->nb = nb; B->ntiles = ntiles_of(nb); B->np = (int64_t)n + PAD;
+    B->ctx = c; B->ref.bind(c); B->n = n; B->nrhs = nrhs; B->nb = nb; B->ntiles = ntiles_of(nb); B->np = (int64_t)n + PAD;
     B->w = nrhs <= 4 ? 4 : 8;
     B->ng = (nrhs + B->w - 1) / B->w;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
-    int rc = dev_alloc(c->device, (size_t)(B->ntiles * B->ng * B->np * B->w * 32), true, c->stream, B->d);
+    int rc = dev_alloc(c, (size_t)(B->ntiles * B->ng * B->np * B->w * 32), true, B->d);
     cudaSetDevice(prev);
     if (rc) { delete B; return rc; }
     *out = B;
     return 0;
 }
-int ssm_mat_destroy(ssm_mat *B) { if (B) { cudaStreamSynchronize(B->ctx->stream); delete B; } return 0; }
+int ssm_mat_destroy(ssm_mat *B) { if (B) { obj_sync(B->ctx); delete B; } return 0; }
 
 static int mat_xfer(ssm_mat *B, double *host_or_dev, int64_t stride, bool set) {
     ssm_ctx *c = B->ctx;
@@ -231,7 +231,9 @@ int ssm_abqr_ldiv_mat(const ssm_abqr *F, ssm_mat *B) {
     SSM_CHECK_ARG(F && B, "null argument");
     if (B->n != F->n || B->nb != F->nb) { set_error("ssm_abqr_ldiv_mat: DimensionMismatch: matrix batch is %lld x (%d x %d), factor batch is %lld x %d", (long long)B->nb, B->n, B->nrhs, (long long)F->nb, F->n); return SSM_E_SHAPE; }
     if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
+    if (F->ncols < F->n - 1) { set_error("ssm_abqr_ldiv_mat: the factor object holds %d of %d reflectors: finish it first (ssm_abqr_continue)", F->ncols, F->n - 1); return SSM_E_STATE; }
     ssm_ctx *c = F->ctx;
+    uses(B->d, c); uses(F->V, c); uses(F->RU, c); uses(F->QT, c);
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     int rc = SSM_E_UNSUPPORTED;
     if (c->ab_variant != 9) {

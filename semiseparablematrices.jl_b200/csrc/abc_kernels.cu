@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(256) abc_res_kernel(const double *REC, const d
 using namespace ssm;
 
 struct ssm_abc {
-    ssm_ctx *ctx; int64_t n; int l, u, r, lp, w, nf, nc;
+    ssm_ctx *ctx; ssm::CtxRef ref; int64_t n; int l, u, r, lp, w, nf, nc;
     DevBufPtr REC, V;                 // operands
     DevBufPtr FR, E, TOP, Z, tmp;     // workspace of the last solve (allocated on first use)
     int P = 0, m0 = 0, jx = 0;
@@ -1181,10 +1181,10 @@ int ssm_abc_create(ssm_ctx *c, int64_t n, int l, int u, int r, ssm_abc **out) {
         if (C && C->n == n && C->l == l && C->u == u && C->r == r) { slot = nullptr; *out = C; return 0; }
     }
     auto *A = new ssm_abc();
-    A->ctx = c; A->n = n; A->l = l; A->u = u; A->r = r; A->lp = l + u; A->w = A->lp + r; A->nf = A->lp + 1 + r; A->nc = 2 * A->lp + 2 * r + 2;
+    A->ctx = c; A->ref.bind(c); A->n = n; A->l = l; A->u = u; A->r = r; A->lp = l + u; A->w = A->lp + r; A->nf = A->lp + 1 + r; A->nc = 2 * A->lp + 2 * r + 2;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
-    int rc = dev_alloc(c->device, (size_t)(n + ABC_PAD) * A->nf, true, c->stream, A->REC);
-    if (!rc) rc = dev_alloc(c->device, (size_t)(n + ABC_PAD) * (r > 0 ? r : 1), true, c->stream, A->V);
+    int rc = dev_alloc(c, (size_t)(n + ABC_PAD) * A->nf, true, A->REC);
+    if (!rc) rc = dev_alloc(c, (size_t)(n + ABC_PAD) * (r > 0 ? r : 1), true, A->V);
     cudaSetDevice(prev);
     if (rc) { delete A; return rc; }
     *out = A;
@@ -1193,8 +1193,8 @@ int ssm_abc_create(ssm_ctx *c, int64_t n, int l, int u, int r, ssm_abc **out) {
 int ssm_abc_destroy(ssm_abc *A) {
     if (!A) return 0;
     ssm_ctx *c = A->ctx;
-    cudaStreamSynchronize(c->stream);
-    if (A->n <= ABC_CACHE_MAX_N) {
+    obj_sync(c);
+    if (A->n <= ABC_CACHE_MAX_N && !c->retired.load()) {
         A->tmp.reset();
         if (c->abc_cache[0]) { delete static_cast<ssm_abc *>(c->abc_cache[1]); c->abc_cache[1] = c->abc_cache[0]; }
         c->abc_cache[0] = A;
@@ -1262,10 +1262,10 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
     if (!rc && (!A->FR || A->P != P || A->tiled != tiled || A->npf != npf)) {
         A->FR.reset(); A->E.reset(); A->TOP.reset(); A->Z.reset();
         const size_t frcount = tiled ? (size_t)((P + 31) / 32) * (size_t)npf * (size_t)A->nc * 32 : (size_t)(A->n + ABC_PAD + 40) * A->nc;
-        rc = dev_alloc(c->device, frcount, tiled, c->stream, A->FR);   // tiled: spare lanes of the last tile are read, so they are defined
-        if (!rc) rc = dev_alloc(c->device, (size_t)(2 * (int64_t)P + 64) * W * (2 * W + 1), true, c->stream, A->E);
-        if (!rc) rc = dev_alloc(c->device, (size_t)((int64_t)P + 64) * W * (3 * W + 1), true, c->stream, A->TOP);
-        if (!rc) rc = dev_alloc(c->device, (size_t)((int64_t)P + 2) * W, true, c->stream, A->Z);
+        rc = dev_alloc(c, frcount, tiled, A->FR);   // tiled: spare lanes of the last tile are read, so they are defined
+        if (!rc) rc = dev_alloc(c, (size_t)(2 * (int64_t)P + 64) * W * (2 * W + 1), true, A->E);
+        if (!rc) rc = dev_alloc(c, (size_t)((int64_t)P + 64) * W * (3 * W + 1), true, A->TOP);
+        if (!rc) rc = dev_alloc(c, (size_t)((int64_t)P + 2) * W, true, A->Z);
         A->P = P;
     }
     A->m0 = m0; A->jx = jx; A->tiled = tiled; A->npf = npf;
@@ -1302,7 +1302,7 @@ int ssm_abc_residual(ssm_abc *A, const double *x, const double *b, double *relre
     int rc = stage_arrays(c, st);
     const double *dx = st.dev[kx], *db = st.dev[kb];
     const int nseg = (int)((A->n + RSEG - 1) / RSEG);
-    if (!rc) rc = dev_alloc(c->device, (size_t)nseg * SSM_MAX_RANK + 2, true, c->stream, A->tmp);
+    if (!rc) rc = dev_alloc(c, (size_t)nseg * SSM_MAX_RANK + 2, true, A->tmp);
     if (!rc) {
         double *part = A->tmp->p, *acc2 = part + (size_t)nseg * SSM_MAX_RANK;
         abc_res_partial_kernel<<<nseg, 256, 0, c->stream>>>(A->V->p, dx, part, A->n, A->r);

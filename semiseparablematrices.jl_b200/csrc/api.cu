@@ -99,14 +99,22 @@ int64_t pool_trim_dev(int device) {
 
 DevBuf::~DevBuf() {
     if (!p) return;
-    // listed only when nothing can still be using it (see above); cudaFree waits for the device, the list does not
-    if (cudaStreamQuery(st) == cudaSuccess && pool_give(device, p, cap)) return;
+    // listed only when nothing can still be using it (see above); cudaFree waits for the device, the list does not.
+    // A retired context synchronised its stream when it was destroyed and nothing can have been enqueued since.
+    const bool idle = !foreign.load() && (!tok || !tok->alive.load() || cudaStreamQuery(tok->st) == cudaSuccess);
+    if (idle && pool_give(device, p, cap)) return;
     cudaGetLastError();
     raw_free(device, p);
 }
-int dev_alloc(int device, size_t count, bool zero, cudaStream_t st, DevBufPtr &out) {
+void ctx_retain(ssm_ctx *c) { c->live.fetch_add(1); }
+void ctx_release(ssm_ctx *c) {
+    if (c->live.fetch_sub(1) == 1 && c->retired.load()) delete c;
+}
+int dev_alloc(ssm_ctx *c, size_t count, bool zero, DevBufPtr &out) {
+    const int device = c->device;
+    cudaStream_t st = c->stream;
     auto b = std::make_shared<DevBuf>();
-    b->device = device; b->count = count; b->st = st;
+    b->device = device; b->count = count; b->tok = c->tok;
     if (count == 0) count = 1;
     b->cap = count;
     b->p = pool_take(device, count, &b->cap);
@@ -196,6 +204,7 @@ int ssm_ctx_create(int device, ssm_ctx **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     c->own_stream = true;
+    c->tok = std::make_shared<StreamToken>(); c->tok->st = c->stream;
     *out = c;
     return 0;
 }
@@ -206,20 +215,25 @@ int ssm_ctx_create_on_stream(int device, void *cuda_stream, ssm_ctx **out) {
     if (rc) { delete c; return rc; }
     c->stream = (cudaStream_t)cuda_stream;
     c->own_stream = false;
+    c->tok = std::make_shared<StreamToken>(); c->tok->st = c->stream;
     *out = c;
     return 0;
 }
 int ssm_ctx_destroy(ssm_ctx *c) {
-    if (!c) return 0;
+    if (!c || c->retired.load()) return 0;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
     hostpipe_free(c);
     abc_cache_free(c);
-    if (c->stg.dev) cudaFree(c->stg.dev);
-    if (c->stg.pin) cudaFreeHost(c->stg.pin);
-    for (auto &s : c->aux) if (s) cudaStreamDestroy(s);
+    if (c->stg.dev) { cudaFree(c->stg.dev); c->stg.dev = nullptr; c->stg.dev_count = 0; }
+    if (c->stg.pin) { cudaFreeHost(c->stg.pin); c->stg.pin = nullptr; c->stg.pin_count = 0; }
+    for (auto &s : c->aux) if (s) { cudaStreamDestroy(s); s = nullptr; }
+    if (c->tok) c->tok->alive.store(false);          // blocks that outlive the context must not query its stream any more
     if (c->own_stream) cudaStreamDestroy(c->stream);
-    delete c;
+    // objects still alive (destroyed out of order by the host runtime): the struct stays until the last of them is gone
+    ctx_retain(c);
+    c->retired.store(true);
+    ctx_release(c);
     return 0;
 }
 int ssm_ctx_sync(ssm_ctx *c) {
@@ -253,6 +267,7 @@ int ssm_ctx_get_option(ssm_ctx *c, const char *key, int *value) {
     return 0;
 }
 int64_t ssm_ctx_launch_count(ssm_ctx *c) { return c ? c->launches : 0; }
+void *ssm_ctx_stream(ssm_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int64_t ssm_pool_trim(int device) { return pool_trim_dev(device); }
 int ssm_pool_stats(int device, int64_t *bytes, int64_t *blocks, int64_t *hits, int64_t *misses) {
     DevPool *P = pool_of(device);
@@ -272,13 +287,13 @@ int ssm_vec_create(ssm_ctx *c, int n, int64_t nb, ssm_vec **out) {
     SSM_CHECK_ARG(n >= 1 && nb >= 1, "n and nb must be positive");
     DeviceGuard g(c->device);
     auto *v = new ssm_vec();
-    v->ctx = c; v->n = n; v->nb = nb; v->ntiles = ntiles_of(nb); v->np = (int64_t)n + PAD;
-    int rc = dev_alloc(c->device, (size_t)(v->ntiles * v->np * 32), true, c->stream, v->d);
+    v->ctx = c; v->ref.bind(c); v->n = n; v->nb = nb; v->ntiles = ntiles_of(nb); v->np = (int64_t)n + PAD;
+    int rc = dev_alloc(c, (size_t)(v->ntiles * v->np * 32), true, v->d);
     if (rc) { delete v; return rc; }
     *out = v;
     return 0;
 }
-int ssm_vec_destroy(ssm_vec *v) { if (v) { cudaStreamSynchronize(v->ctx->stream); delete v; } return 0; }
+int ssm_vec_destroy(ssm_vec *v) { if (v) { obj_sync(v->ctx); delete v; } return 0; }
 
 int ssm_vec_set(ssm_vec *v, const double *b, int64_t stride) {
     SSM_CHECK_ARG(v && b, "null argument");
@@ -339,14 +354,14 @@ int ssm_ab_create(ssm_ctx *c, int n, int l, int u, int r, int64_t nb, ssm_ab **o
     if (l > SSM_MAX_BW || u > SSM_MAX_BW || r > SSM_MAX_RANK) { set_error("(l,u,r)=(%d,%d,%d) exceeds compiled limits (%d,%d,%d)", l, u, r, SSM_MAX_BW, SSM_MAX_BW, SSM_MAX_RANK); return SSM_E_UNSUPPORTED; }
     DeviceGuard g(c->device);
     auto *A = new ssm_ab();
-    A->ctx = c; A->n = n; A->l = l; A->u = u; A->r = r; A->nb = nb; A->ntiles = ntiles_of(nb); A->np = (int64_t)n + PAD;
-    int rc = dev_alloc(c->device, (size_t)(A->ntiles * A->np * (l + u + 1 + r) * 32), true, c->stream, A->AU);
-    if (!rc) rc = dev_alloc(c->device, (size_t)(A->ntiles * A->np * (r > 0 ? r : 1) * 32), true, c->stream, A->V);
+    A->ctx = c; A->ref.bind(c); A->n = n; A->l = l; A->u = u; A->r = r; A->nb = nb; A->ntiles = ntiles_of(nb); A->np = (int64_t)n + PAD;
+    int rc = dev_alloc(c, (size_t)(A->ntiles * A->np * (l + u + 1 + r) * 32), true, A->AU);
+    if (!rc) rc = dev_alloc(c, (size_t)(A->ntiles * A->np * (r > 0 ? r : 1) * 32), true, A->V);
     if (rc) { delete A; return rc; }
     *out = A;
     return 0;
 }
-int ssm_ab_destroy(ssm_ab *A) { if (A) { cudaStreamSynchronize(A->ctx->stream); delete A; } return 0; }
+int ssm_ab_destroy(ssm_ab *A) { if (A) { obj_sync(A->ctx); delete A; } return 0; }
 
 // resize(A, n_new, n_new) (AlmostBandedMatrix.jl:338-348): the same bands and fill in a larger matrix, new band rows / columns, new rows of U
 // and new columns of V zero.  A tile's rows are contiguous ([tile][np][nf][32]), so the old rows of every tile move in one strided copy into
@@ -374,6 +389,19 @@ int ssm_ab_resize(const ssm_ab *A, int n_new, ssm_ab **out) {
     return 0;
 }
 
+// A factor object made from A shares A's V block (it is never written by the path).  Before anything rewrites A's V the batch takes a block of
+// its own — with the old contents when only some rows are about to change — so that live factor objects keep the matrix they factored.
+static int ab_own_v(ssm_ab *A, bool keep) {
+    if (!A->V || A->V.use_count() <= 1) return 0;
+    ssm_ctx *c = A->ctx;
+    DevBufPtr nv;
+    SSM_TRY(dev_alloc(c, A->V->count, !keep, nv));
+    if (keep) SSM_CUDA(cudaMemcpyAsync(nv->p, A->V->p, A->V->count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    uses(A->V, c);
+    A->V = nv;
+    return 0;
+}
+
 int ssm_ab_set(ssm_ab *A, const double *bands, int64_t sb, const double *U, int64_t su, const double *V, int64_t sv) {
     SSM_CHECK_ARG(A && bands && (A->r == 0 || (U && V)), "null argument");
     ssm_ctx *c = A->ctx;
@@ -383,6 +411,7 @@ int ssm_ab_set(ssm_ab *A, const double *bands, int64_t sb, const double *U, int6
     if (su == 0) su = (int64_t)eu;
     if (sv == 0) sv = (int64_t)eu;
     if ((size_t)sb < eb || (size_t)su < eu || (size_t)sv < eu) { set_error("ssm_ab_set: Data and fill must be compatible size (stride smaller than one system)"); return SSM_E_SHAPE; }
+    SSM_TRY(ab_own_v(A, false));
     const bool db = is_device_ptr(bands), du = A->r == 0 || is_device_ptr(U), dv = A->r == 0 || is_device_ptr(V);
     if (db && du && dv) return launch_ab_pack(c, A, bands, sb, U, su, V, sv, 0, A->nb);
     const int64_t ch = chunk_systems(eb + 2 * eu, A->nb);
@@ -415,6 +444,7 @@ int ssm_ab_set_rows(ssm_ab *A, int k0, int k1, const double *bands, int64_t sb, 
     if (su == 0) su = (int64_t)eu;
     if (sv == 0) sv = (int64_t)eu;
     if ((size_t)sb < eb || (size_t)su < eu || (size_t)sv < eu) { set_error("ssm_ab_set_rows: Data and fill must be compatible size (stride smaller than one system)"); return SSM_E_SHAPE; }
+    SSM_TRY(ab_own_v(A, true));
     const bool db = is_device_ptr(bands), du = r == 0 || is_device_ptr(U), dv = r == 0 || is_device_ptr(V);
     if (db && du && dv) return launch_ab_pack_rows(c, A, bands, sb, 0, U, su, n, V, sv, 0, 0, A->nb, k0, k1);
     const int64_t jlo = std::max(k0 - l, 0), jhi = std::min(k1 + u, n), rows = k1 - k0;
@@ -462,6 +492,7 @@ int ssm_ab_set_vcat(ssm_ab *A, const double *a, int64_t a_stride, const double *
     if (a_stride == 0) a_stride = (int64_t)ea;
     if (b_stride == 0) b_stride = (int64_t)eb;
     if ((size_t)a_stride < ea || (size_t)b_stride < eb) { set_error("ssm_ab_set_vcat: stride smaller than one system"); return SSM_E_SHAPE; }
+    SSM_TRY(ab_own_v(A, false));
     if (is_device_ptr(a) && is_device_ptr(Bd)) return launch_ab_pack_vcat(c, A, a, a_stride, Bd, b_stride, lb, ub);
     double *stg;
     SSM_TRY(staging_dev(c, (size_t)A->nb * (ea + eb), &stg));
@@ -499,15 +530,16 @@ int ssm_ab_generate(ssm_ab *A, uint64_t seed, int dist) {
     SSM_CHECK_ARG(A, "null argument");
     SSM_CHECK_ARG(dist == SSM_DIST_DD || dist == SSM_DIST_BC, "unknown distribution");
     DeviceGuard g(A->ctx->device);
+    SSM_TRY(ab_own_v(A, false));
     return launch_ab_generate(A->ctx, A, seed, dist);
 }
 
 static int abqr_alloc(const ssm_ab *A, bool with_q, ssm_abqr **out) {
     ssm_ctx *c = A->ctx;
     auto *F = new ssm_abqr();
-    F->ctx = c; F->n = A->n; F->l = A->l; F->u = A->u; F->r = A->r; F->nb = A->nb; F->ntiles = A->ntiles; F->np = A->np;
-    int rc = dev_alloc(c->device, (size_t)(F->ntiles * F->np * (F->l + F->u + 1 + F->r) * 32), true, c->stream, F->RU);
-    if (!rc && with_q) rc = dev_alloc(c->device, (size_t)(F->ntiles * F->np * (F->l + 1) * 32), true, c->stream, F->QT);
+    F->ctx = c; F->ref.bind(c); F->n = A->n; F->l = A->l; F->u = A->u; F->r = A->r; F->nb = A->nb; F->ntiles = A->ntiles; F->np = A->np;
+    int rc = dev_alloc(c, (size_t)(F->ntiles * F->np * (F->l + F->u + 1 + F->r) * 32), true, F->RU);
+    if (!rc && with_q) rc = dev_alloc(c, (size_t)(F->ntiles * F->np * (F->l + 1) * 32), true, F->QT);
     if (rc) { delete F; return rc; }
     F->V = A->V;
     *out = F;
@@ -523,6 +555,7 @@ int ssm_ab_qr_cols(const ssm_ab *A, int ncols, ssm_abqr **out) {
     if (F) {   // refactor into an existing object of the same shape (steady-state benchmarking, no allocation)
         if (F->n != A->n || F->l != A->l || F->u != A->u || F->r != A->r || F->nb != A->nb) { set_error("ssm_ab_qr: factor object has a different shape"); return SSM_E_SHAPE; }
         F->V = A->V;
+        uses(F->RU, c); uses(F->QT, c);          // a factor object of another context is rewritten on A's stream
     } else {
         SSM_TRY(abqr_alloc(A, true, &F));
     }
@@ -543,6 +576,7 @@ int ssm_abqr_continue(ssm_abqr *F, const ssm_ab *A, int ncols) {
     if (!F->QT) { set_error("ssm_abqr_continue: factor object keeps no reflectors"); return SSM_E_STATE; }
     if (ncols == F->ncols) return 0;
     ssm_ctx *c = F->ctx;
+    uses(A->AU, c); uses(A->V, c);
     DeviceGuard g(c->device);
     AbArgs a{A->AU->p, A->V->p, F->RU->p, F->QT->p, nullptr, nullptr, A->n, A->np, ncols};
     SSM_TRY(F->ncols == 0 ? launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, false, true) : launch_ab_qr_continue(c, A->l, A->u, A->r, A->ntiles, a, F->ncols));
@@ -554,7 +588,7 @@ int ssm_ab_qr(const ssm_ab *A, ssm_abqr **out) {
     SSM_CHECK_ARG(A && out, "null argument");
     return ssm_ab_qr_cols(A, A->n - 1, out);     // min(m - 1, n) for a real square matrix (:137)
 }
-int ssm_abqr_destroy(ssm_abqr *F) { if (F) { cudaStreamSynchronize(F->ctx->stream); delete F; } return 0; }
+int ssm_abqr_destroy(ssm_abqr *F) { if (F) { obj_sync(F->ctx); delete F; } return 0; }
 
 int ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t sf, double *U, int64_t su, double *tau, int64_t st) {
     SSM_CHECK_ARG(F, "null argument");
@@ -581,6 +615,14 @@ static int check_vec(const char *fn, int n, int64_t nb, const ssm_ctx *c, const 
     if (!b) { set_error("%s: null vector", fn); return SSM_E_ARG; }
     if (b->n != n || b->nb != nb) { set_error("%s: DimensionMismatch: vector batch is %lld x %d, matrix batch is %lld x %d", fn, (long long)b->nb, b->n, (long long)nb, n); return SSM_E_SHAPE; }
     if (b->ctx->device != c->device) { set_error("%s: operands live on different devices", fn); return SSM_E_ARG; }
+    uses(b->d, c);              // a vector of another context is used on this one's stream: its block leaves the free-list protocol
+    return 0;
+}
+// F's kernels run on F->ctx; its V (and, after a refactorisation from another context, its own records) may belong elsewhere
+static void abqr_uses(const ssm_abqr *F) { uses(F->V, F->ctx); uses(F->RU, F->ctx); uses(F->QT, F->ctx); }
+// The solve / apply entry points need the COMPLETE factorisation (n - 1 reflectors, AlmostBandedMatrix.jl:137): with fewer, "R" is not triangular.
+static int abqr_complete(const char *fn, const ssm_abqr *F) {
+    if (F->ncols < F->n - 1) { set_error("%s: the factor object holds %d of %d reflectors (ssm_ab_qr_cols / ssm_abqr_continue): finish it first", fn, F->ncols, F->n - 1); return SSM_E_STATE; }
     return 0;
 }
 
@@ -588,6 +630,7 @@ int ssm_abqr_lmul_qt(const ssm_abqr *F, ssm_vec *b) {
     SSM_CHECK_ARG(F, "null argument");
     SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, b));
     if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
+    abqr_uses(F);                  // a partial factorisation is fine here: the reflectors not yet formed have tau = 0
     DeviceGuard g(F->ctx->device);
     AbSolveArgs a{F->RU->p, F->QT->p, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
     return launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, a, true);
@@ -596,6 +639,7 @@ int ssm_abqr_lmul_q(const ssm_abqr *F, ssm_vec *b) {
     SSM_CHECK_ARG(F, "null argument");
     SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, b));
     if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
+    abqr_uses(F);                  // a partial factorisation is fine here: the reflectors not yet formed have tau = 0
     DeviceGuard g(F->ctx->device);
     AbSolveArgs a{F->RU->p, F->QT->p, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
     return launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, a, false);
@@ -603,6 +647,8 @@ int ssm_abqr_lmul_q(const ssm_abqr *F, ssm_vec *b) {
 int ssm_abqr_upper_ldiv(const ssm_abqr *F, ssm_vec *b) {
     SSM_CHECK_ARG(F, "null argument");
     SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, b));
+    SSM_TRY(abqr_complete(__func__, F));
+    abqr_uses(F);
     DeviceGuard g(F->ctx->device);
     AbSolveArgs a{F->RU->p, F->QT ? F->QT->p : nullptr, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
     return launch_ab_backsolve(F->ctx, F->l, F->u, F->r, F->ntiles, a);
@@ -612,6 +658,8 @@ int ssm_abqr_solve(const ssm_abqr *F, const ssm_vec *b, ssm_vec *x) {
     SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, b));
     SSM_TRY(check_vec(__func__, F->n, F->nb, F->ctx, x));
     if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
+    SSM_TRY(abqr_complete(__func__, F));
+    abqr_uses(F);
     DeviceGuard g(F->ctx->device);
     AbSolveArgs q{F->RU->p, F->QT->p, F->V->p, b->d->p, x->d->p, F->n, F->np, 0};        // x <- Q'b
     SSM_TRY(launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, q, true));
@@ -627,7 +675,7 @@ int ssm_ab_solve(const ssm_ab *A, const ssm_vec *b, ssm_vec *x) {
     ssm_ctx *c = A->ctx;
     DeviceGuard g(c->device);
     // R round-trips through HBM (the back-substitution runs against the sweep); reflectors are not kept.
-    if (!A->scratch) SSM_TRY(dev_alloc(c->device, (size_t)(A->ntiles * A->np * (A->l + A->u + 1 + A->r) * 32), true, c->stream, A->scratch));
+    if (!A->scratch) SSM_TRY(dev_alloc(c, (size_t)(A->ntiles * A->np * (A->l + A->u + 1 + A->r) * 32), true, A->scratch));
     DevBufPtr RU = A->scratch;
     AbArgs a{A->AU->p, A->V->p, RU->p, nullptr, b->d->p, x->d->p, A->n, A->np, A->n - 1};
     SSM_TRY(launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, true, false));

@@ -14,8 +14,10 @@ int chk_vec(const char *fn, int n, int64_t nb, const ssm_ctx *c, const ssm_vec *
     if (!b) { set_error("%s: null vector", fn); return SSM_E_ARG; }
     if (b->n != n || b->nb != nb) { set_error("%s: DimensionMismatch: vector batch is %lld x %d, matrix batch is %lld x %d", fn, (long long)b->nb, b->n, (long long)nb, n); return SSM_E_SHAPE; }
     if (b->ctx->device != c->device) { set_error("%s: operands live on different devices", fn); return SSM_E_ARG; }
+    uses(b->d, c);              // a vector of another context is used on this one's stream: its block leaves the free-list protocol
     return 0;
 }
+void bpsqr_uses(const ssm_bpsqr *F) { uses(F->REC, F->ctx); uses(F->OUT, F->ctx); uses(F->GT, F->ctx); uses(F->TT, F->ctx); }
 // stage `count` doubles from a host or device pointer into the ctx staging area at offset `off`
 int stage_in(ssm_ctx *c, double *stg, size_t off, const double *src, int64_t stride, size_t elems, int64_t nb, const double **out) {
     if (!src) { *out = nullptr; return 0; }
@@ -40,14 +42,25 @@ int ssm_bps_create(ssm_ctx *c, int n, int l, int m, int r, int p, int64_t nb, ss
     if (!bps_pick_shape(l, m, r, p, &tl, &tm, &tr, &tp)) { set_error("BPS shape (l,m,r,p)=(%d,%d,%d,%d) exceeds the compiled kernel shapes (max (4,5,3,3))", l, m, r, p); return SSM_E_UNSUPPORTED; }
     DevGuard g(c->device);
     auto *A = new ssm_bps();
-    A->ctx = c; A->n = n; A->l = l; A->m = m; A->r = r; A->p = p; A->tl = tl; A->tm = tm; A->tr = tr; A->tp = tp;
+    A->ctx = c; A->ref.bind(c); A->n = n; A->l = l; A->m = m; A->r = r; A->p = p; A->tl = tl; A->tm = tm; A->tr = tr; A->tp = tp;
     A->nb = nb; A->ntiles = ntiles_of(nb); A->np = (int64_t)BPS_FRONT + n + PAD;
-    int rc = dev_alloc(c->device, (size_t)(A->ntiles * A->np * bps_nfa(tl, tm, tr, tp) * 32), true, c->stream, A->REC);
+    int rc = dev_alloc(c, (size_t)(A->ntiles * A->np * bps_nfa(tl, tm, tr, tp) * 32), true, A->REC);
     if (rc) { delete A; return rc; }
     *out = A;
     return 0;
 }
-int ssm_bps_destroy(ssm_bps *A) { if (A) { cudaStreamSynchronize(A->ctx->stream); delete A; } return 0; }
+int ssm_bps_destroy(ssm_bps *A) { if (A) { obj_sync(A->ctx); delete A; } return 0; }
+
+// A factor object shares the operand records (U and S[:, 1:p] are part of the factorisation): rewriting the operands of a batch that has
+// live factor objects first gives the batch records of its own.
+static int bps_own_rec(ssm_bps *A) {
+    if (!A->REC || A->REC.use_count() <= 1) return 0;
+    DevBufPtr nr;
+    SSM_TRY(dev_alloc(A->ctx, A->REC->count, true, nr));
+    uses(A->REC, A->ctx);
+    A->REC = nr;
+    return 0;
+}
 
 int ssm_bps_set(ssm_bps *A, const double *B, int64_t sb, const double *U, const double *V, int64_t suv, const double *W, const double *S, int64_t sws) {
     SSM_CHECK_ARG(A && B, "null argument");
@@ -60,6 +73,7 @@ int ssm_bps_set(ssm_bps *A, const double *B, int64_t sb, const double *U, const 
     if (suv == 0) suv = (int64_t)eu;
     if (sws == 0) sws = (int64_t)ew;
     if ((size_t)sb < eb || (size_t)suv < eu || (size_t)sws < ew) { set_error("ssm_bps_set: Dimensions are not compatible."); return SSM_E_SHAPE; }
+    SSM_TRY(bps_own_rec(A));
     double *stg;
     SSM_TRY(staging_dev(c, (size_t)A->nb * (eb + 2 * eu + 2 * ew) + 8, &stg));
     const double *dB, *dU, *dV, *dW, *dS;
@@ -77,6 +91,7 @@ int ssm_bps_set(ssm_bps *A, const double *B, int64_t sb, const double *U, const 
 int ssm_bps_generate(ssm_bps *A, uint64_t seed) {
     SSM_CHECK_ARG(A, "null argument");
     DevGuard g(A->ctx->device);
+    SSM_TRY(bps_own_rec(A));
     return launch_bps_generate(A->ctx, A, seed);
 }
 
@@ -88,14 +103,15 @@ int ssm_bps_qr(const ssm_bps *A, ssm_bpsqr **out) {
     if (F) {
         if (F->n != A->n || F->l != A->l || F->m != A->m || F->r != A->r || F->p != A->p || F->nb != A->nb) { set_error("ssm_bps_qr: factor object has a different shape"); return SSM_E_SHAPE; }
         F->REC = A->REC;
+        uses(F->OUT, c); uses(F->GT, c); uses(F->TT, c);        // refactorisation of another context's factor object runs on A's stream
     } else {
         F = new ssm_bpsqr();
-        F->ctx = c; F->n = A->n; F->l = A->l; F->m = A->m; F->r = A->r; F->p = A->p; F->tl = A->tl; F->tm = A->tm; F->tr = A->tr; F->tp = A->tp;
+        F->ctx = c; F->ref.bind(c); F->n = A->n; F->l = A->l; F->m = A->m; F->r = A->r; F->p = A->p; F->tl = A->tl; F->tm = A->tm; F->tr = A->tr; F->tp = A->tp;
         F->nb = A->nb; F->ntiles = A->ntiles; F->np = A->np; F->npo = (int64_t)A->n + PAD;
         F->REC = A->REC;
-        int rc = dev_alloc(c->device, (size_t)(F->ntiles * F->npo * bps_nfo(F->tl, F->tm, F->tr, F->tp) * 32), true, c->stream, F->OUT);
-        if (!rc) rc = dev_alloc(c->device, (size_t)(F->ntiles * F->tr * F->tr * 32), true, c->stream, F->GT);
-        if (!rc) rc = dev_alloc(c->device, (size_t)(F->ntiles * F->tr * 32), true, c->stream, F->TT);
+        int rc = dev_alloc(c, (size_t)(F->ntiles * F->npo * bps_nfo(F->tl, F->tm, F->tr, F->tp) * 32), true, F->OUT);
+        if (!rc) rc = dev_alloc(c, (size_t)(F->ntiles * F->tr * F->tr * 32), true, F->GT);
+        if (!rc) rc = dev_alloc(c, (size_t)(F->ntiles * F->tr * 32), true, F->TT);
         if (rc) { delete F; return rc; }
     }
     int rc = launch_bps_qr(c, A, F);
@@ -103,7 +119,7 @@ int ssm_bps_qr(const ssm_bps *A, ssm_bpsqr **out) {
     *out = F;
     return 0;
 }
-int ssm_bpsqr_destroy(ssm_bpsqr *F) { if (F) { cudaStreamSynchronize(F->ctx->stream); delete F; } return 0; }
+int ssm_bpsqr_destroy(ssm_bpsqr *F) { if (F) { obj_sync(F->ctx); delete F; } return 0; }
 
 int ssm_bpsqr_get(const ssm_bpsqr *F, double *B, int64_t sb, double *U, double *V, int64_t suv, double *W, double *S, int64_t sws, double *tau, int64_t st) {
     SSM_CHECK_ARG(F, "null argument");
@@ -136,12 +152,14 @@ int ssm_bpsqr_get(const ssm_bpsqr *F, double *B, int64_t sb, double *U, double *
 int ssm_bpsqr_lmul_qt(const ssm_bpsqr *F, ssm_vec *b) {
     SSM_CHECK_ARG(F, "null argument");
     SSM_TRY(chk_vec(__func__, F->n, F->nb, F->ctx, b));
+    bpsqr_uses(F);
     DevGuard g(F->ctx->device);
     return launch_bps_qt(F->ctx, F, b->d->p, b->d->p);
 }
 int ssm_bpsqr_upper_ldiv(const ssm_bpsqr *F, ssm_vec *b) {
     SSM_CHECK_ARG(F, "null argument");
     SSM_TRY(chk_vec(__func__, F->n, F->nb, F->ctx, b));
+    bpsqr_uses(F);
     DevGuard g(F->ctx->device);
     return launch_bps_backsolve(F->ctx, F, b->d->p, b->d->p);
 }
@@ -149,6 +167,7 @@ int ssm_bpsqr_solve(const ssm_bpsqr *F, const ssm_vec *b, ssm_vec *x) {
     SSM_CHECK_ARG(F, "null argument");
     SSM_TRY(chk_vec(__func__, F->n, F->nb, F->ctx, b));
     SSM_TRY(chk_vec(__func__, F->n, F->nb, F->ctx, x));
+    bpsqr_uses(F);
     DevGuard g(F->ctx->device);
     SSM_TRY(launch_bps_qt(F->ctx, F, b->d->p, x->d->p));
     return launch_bps_backsolve(F->ctx, F, x->d->p, x->d->p);

@@ -407,7 +407,7 @@ int ssm_bpsqr_rq_mul(const ssm_bpsqr *F, ssm_bps **out) {
     if (!Q) SSM_TRY(ssm_bps_create(c, F->n, F->l, F->l, F->r, F->r, F->nb, &Q));
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     DevBufPtr flag;
-    int rc = dev_alloc(c->device, 1, true, c->stream, flag);
+    int rc = dev_alloc(c, 1, true, flag);
     if (!rc) {
         RqOut o{Q->REC->p, Q->np, bps_nfa(Q->tl, Q->tm, Q->tr, Q->tp), Q->tl, Q->tm, Q->tr, Q->tp};
         if (Q->tl != F->tl || Q->tm != F->tm || Q->tr != F->tr || Q->tp != F->tp) {

@@ -45,8 +45,8 @@ static HostPipe *get_pipe(ssm_ctx *c, int n, int l, int u, int r, int64_t nb, in
         hp->cx[s]->ab_variant = c->ab_variant; hp->cx[s]->pipeline_stages = c->pipeline_stages;
         if ((*rc = ssm_ab_create(hp->cx[s], n, l, u, r, hp->ch, &hp->A[s]))) break;
         if ((*rc = ssm_vec_create(hp->cx[s], n, hp->ch, &hp->v[s]))) break;
-        if ((*rc = dev_alloc(c->device, (size_t)hp->ch * (eb + 2 * eu + n), false, hp->cx[s]->stream, hp->stg[s]))) break;
-        if ((*rc = dev_alloc(c->device, (size_t)(hp->A[s]->ntiles * hp->A[s]->np * (l + u + 1 + r) * 32), true, hp->cx[s]->stream, hp->ru[s]))) break;
+        if ((*rc = dev_alloc(hp->cx[s], (size_t)hp->ch * (eb + 2 * eu + n), false, hp->stg[s]))) break;
+        if ((*rc = dev_alloc(hp->cx[s], (size_t)(hp->A[s]->ntiles * hp->A[s]->np * (l + u + 1 + r) * 32), true, hp->ru[s]))) break;
     }
     if (*rc) { hp->release(); delete hp; return nullptr; }
     c->hostpipe = hp;
@@ -97,6 +97,7 @@ extern "C" int ssm_ab_solve_host(ssm_ctx *c, int n, int l, int u, int r, int64_t
         launches += cx->launches - l0;
     }
     for (int s = 0; s < HostPipe::NSLOT; ++s) {
+        hp->A[s]->nb = hp->ch; hp->v[s]->nb = hp->ch;      // an error inside a short last chunk must not leave the cached pipeline truncated
         cudaError_t e = cudaStreamSynchronize(hp->cx[s]->stream);
         if (e != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
     }

@@ -1,6 +1,7 @@
 // ssm_internal.cuh — shared definitions of libssmb200.so (not installed; the public surface is include/ssm_b200.h)
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -8,6 +9,8 @@
 #include <string>
 #include <vector>
 #include "../../include/ssm_b200.h"
+
+struct ssm_ctx;
 
 namespace ssm {
 
@@ -23,16 +26,25 @@ constexpr int PAD  = 48;
 
 inline int64_t ntiles_of(int64_t nb) { return (nb + TILE - 1) / TILE; }
 
+// The stream a context enqueues on, with a flag that outlives the context: a block may only be asked "is your stream idle?" while that
+// stream still exists (cudaStreamQuery on a destroyed stream is undefined).  ssm_ctx_destroy synchronises, then clears `alive`.
+struct StreamToken {
+    cudaStream_t st = nullptr;
+    std::atomic<bool> alive{true};
+};
+using StreamTokenPtr = std::shared_ptr<StreamToken>;
+
 struct DevBuf {
     double *p = nullptr;
     size_t  count = 0;          // doubles asked for
     size_t  cap = 0;            // doubles the block holds (>= count when it came off the free list, api.cu)
     int     device = 0;
-    cudaStream_t st = nullptr;  // stream of the context it was allocated for
+    StreamTokenPtr tok;         // stream of the context it was allocated for
+    std::atomic<bool> foreign{false};   // some OTHER context's stream has read or written it (see uses()): never recycled, cudaFree waits for the device
     ~DevBuf();
 };
 using DevBufPtr = std::shared_ptr<DevBuf>;
-int dev_alloc(int device, size_t count, bool zero, cudaStream_t st, DevBufPtr &out);
+int dev_alloc(ssm_ctx *c, size_t count, bool zero, DevBufPtr &out);
 
 void set_error(const char *fmt, ...);
 bool is_device_ptr(const void *p);
@@ -56,13 +68,15 @@ struct Staging {        // lazily grown scratch: device staging in reference lay
 
 }  // namespace ssm
 
-struct ssm_ctx;
 namespace ssm { int staging_dev(ssm_ctx *c, size_t count, double **out); void hostpipe_free(ssm_ctx *c); void abc_cache_free(ssm_ctx *c); }
 
 struct ssm_ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;
     bool         own_stream = false;
+    ssm::StreamTokenPtr tok;           // {stream, alive}: what this context's device blocks ask before they go back to the free list
+    std::atomic<int64_t> live{0};      // objects created on this context and not yet destroyed (ssm::CtxRef)
+    std::atomic<bool>    retired{false};   // ssm_ctx_destroy was called while objects were alive: freed with the last of them
     int          ab_variant = 0;       // 0 auto, 1 direct-load kernels, 2 bulk-async (TMA) ring kernels, 4 GroupRing kernels (producer warp + grouped bulk copies), 9 generic
     int          carveout_all = 0;     // experiment: direct-load kernels also ask for the max-shared carveout
     int          group_smem_kb = 200;  // GroupRing: shared memory one CTA may take.  Alone on the GPU the deep ring is worth 3-8 % at <= 2 tiles per
@@ -80,20 +94,40 @@ struct ssm_ctx {
     void        *abc_cache[2] = {nullptr, nullptr};   // recently destroyed ssm_abc objects kept for reuse (abc_kernels.cu)
 };
 
+namespace ssm {
+// Every object counts against its context.  A context destroyed before its objects (a host runtime that runs finalizers in any order, e.g. Julia's
+// atexit hooks before its GC finalizers) is only retired — streams synchronised and released, caches freed — and its memory goes with the last object.
+void ctx_retain(ssm_ctx *c);
+void ctx_release(ssm_ctx *c);
+struct CtxRef {
+    ssm_ctx *c = nullptr;
+    CtxRef() = default;
+    CtxRef(const CtxRef &) = delete;
+    CtxRef &operator=(const CtxRef &) = delete;
+    void bind(ssm_ctx *ctx) { if (!c) { c = ctx; ctx_retain(ctx); } }
+    ~CtxRef() { if (c) ctx_release(c); }
+};
+// wait for the object's context before its buffers go away (nothing to wait for once the context is retired: it synchronised then)
+inline void obj_sync(const ssm_ctx *c) { if (c && !c->retired.load()) cudaStreamSynchronize(c->stream); }
+// `user` is about to enqueue work that touches block d.  If d belongs to another context, the owner's destroy-time synchronisation no longer
+// covers every use, so the block is barred from the free list for good (its destructor falls back to cudaFree, which waits for the device).
+inline void uses(const DevBufPtr &d, const ssm_ctx *user) { if (d && d->tok.get() != user->tok.get()) d->foreign.store(true); }
+}  // namespace ssm
+
 struct ssm_vec {
-    ssm_ctx *ctx; int n; int64_t nb, ntiles, np;
+    ssm_ctx *ctx; ssm::CtxRef ref; int n; int64_t nb, ntiles, np;
     ssm::DevBufPtr d;           // [ntiles][np][32]
 };
 
 struct ssm_ab {
-    ssm_ctx *ctx; int n, l, u, r; int64_t nb, ntiles, np;
+    ssm_ctx *ctx; ssm::CtxRef ref; int n, l, u, r; int64_t nb, ntiles, np;
     ssm::DevBufPtr AU;          // [ntiles][np][l+u+1+r][32]   row record: A[i, i-l .. i+u], U[i, :]
     ssm::DevBufPtr V;           // [ntiles][np][r][32]         V[:, c]
     mutable ssm::DevBufPtr scratch;  // R records of the fused A\\b path (kept between calls)
 };
 
 struct ssm_abqr {
-    ssm_ctx *ctx; int n, l, u, r; int64_t nb, ntiles, np;
+    ssm_ctx *ctx; ssm::CtxRef ref; int n, l, u, r; int64_t nb, ntiles, np;
     int ncols = 0;              // reflectors formed (n-1 for qr(A); fewer after ssm_ab_qr_cols)
     ssm::DevBufPtr RU;          // [ntiles][np][l+u+1+r][32]   R[k, k .. k+ub], Ufinal[k, :]
     ssm::DevBufPtr QT;          // [ntiles][np][l+1][32]       reflector tail of column k, tau_k
@@ -103,11 +137,11 @@ struct ssm_abqr {
 // BandedPlusSemiseparable operands.  (l,m,r,p) is the caller's shape; (tl,tm,tr,tp) >= it is the compiled kernel
 // shape the batch is zero-padded to (a BPS matrix with zero extra bands / generator columns is the same matrix).
 struct ssm_bps {
-    ssm_ctx *ctx; int n, l, m, r, p, tl, tm, tr, tp; int64_t nb, ntiles, np;
+    ssm_ctx *ctx; ssm::CtxRef ref; int n, l, m, r, p, tl, tm, tr, tp; int64_t nb, ntiles, np;
     ssm::DevBufPtr REC;         // [ntiles][np][nfa][32], record (FRONT + row): B0 row (tl+tm+1) | U (tr) | V (tr) | W (tp) | S (tp)
 };
 struct ssm_bpsqr {
-    ssm_ctx *ctx; int n, l, m, r, p, tl, tm, tr, tp; int64_t nb, ntiles, np, npo;
+    ssm_ctx *ctx; ssm::CtxRef ref; int n, l, m, r, p, tl, tm, tr, tp; int64_t nb, ntiles, np, npo;
     ssm::DevBufPtr REC;         // shared with the operand batch (U and S[:,1:p] are part of the factorisation)
     ssm::DevBufPtr OUT;         // [ntiles][npo][nfo][32], record row: tail (tl) | Vnew (tr) | tau || pivot,d (tl+tm+1) | alpha (tp) | beta (tr) | A'U (tr)
     ssm::DevBufPtr GT;          // [ntiles][tr*tr][32]  U'U of each system

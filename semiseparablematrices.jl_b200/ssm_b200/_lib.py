@@ -40,6 +40,7 @@ _SIGS = {
     "ssm_ctx_set_option": (C.c_int, [c_vp, C.c_char_p, C.c_int]),
     "ssm_ctx_get_option": (C.c_int, [c_vp, C.c_char_p, C.POINTER(C.c_int)]),
     "ssm_ctx_launch_count": (i64, [c_vp]),
+    "ssm_ctx_stream": (c_vp, [c_vp]),
     "ssm_pool_trim": (i64, [C.c_int]),
     "ssm_pool_stats": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "ssm_vec_create": (C.c_int, [c_vp, C.c_int, i64, C.POINTER(c_vp)]),

@@ -44,6 +44,38 @@ def _as_ptr(a, shape=None, name="array"):
     return arr.ctypes.data, arr
 
 
+class _TorchOrder:
+    """Stream ordering between torch and the library for calls that take torch CUDA tensors (the C ABI only ENQUEUES on its
+    context's stream when it is given device pointers).  On entry the context's stream waits for torch's current stream — the
+    tensors may still be being produced; on exit torch's current stream waits for the context's — the outputs are ready for
+    whatever torch enqueues next — and every tensor (temporaries from ``.contiguous()`` included) is recorded on the context's
+    stream so that torch's allocator does not hand its memory out again before the library has used it.  Nothing happens for
+    host arrays, nor when the context already runs on torch's current stream."""
+
+    def __init__(self, ctx, *arrays):
+        self.ctx = ctx
+        self.ts = [a for a in arrays if a is not None and _is_torch(a) and a.is_cuda]
+        self.ext = None
+
+    def __enter__(self):
+        if self.ts:
+            import torch
+            dev = self.ts[0].device
+            self.cur = torch.cuda.current_stream(dev)
+            sp = self.ctx.stream_ptr
+            if self.cur.cuda_stream != sp:
+                self.ext = torch.cuda.ExternalStream(sp, device=dev)
+                self.ext.wait_stream(self.cur)
+        return self
+
+    def __exit__(self, *exc):
+        if self.ext is not None:
+            for t in self.ts:
+                t.record_stream(self.ext)
+            self.cur.wait_stream(self.ext)
+        return False
+
+
 class Context:
     """Device + stream + staging workspace (``ssm_ctx``).  ``stream`` is a raw ``cudaStream_t`` (e.g.
     ``torch.cuda.current_stream().cuda_stream``) or None for a private non-blocking stream."""
@@ -71,6 +103,11 @@ class Context:
     @property
     def launches(self) -> int:
         return int(_lib.lib().ssm_ctx_launch_count(self._h))
+
+    @property
+    def stream_ptr(self) -> int:
+        """the raw ``cudaStream_t`` this context enqueues on"""
+        return int(_lib.lib().ssm_ctx_stream(self._h) or 0)
 
     def close(self):
         if self._h:
@@ -117,7 +154,8 @@ class Vec:
 
     def set(self, b):
         p, keep = _as_ptr(b, (self.nb, self.n), "b")
-        check(_lib.lib().ssm_vec_set(self._h, c_vp(p), 0), "ssm_vec_set")
+        with _TorchOrder(self.ctx, keep):
+            check(_lib.lib().ssm_vec_set(self._h, c_vp(p), 0), "ssm_vec_set")
         return self
 
     def get(self, out=None):
@@ -126,7 +164,8 @@ class Vec:
         p, keep = _as_ptr(out, (self.nb, self.n), "out")
         if keep is not out and not _is_torch(out):
             raise TypeError("out must be a contiguous float64 array")
-        check(_lib.lib().ssm_vec_get(self._h, c_vp(p), 0), "ssm_vec_get")
+        with _TorchOrder(self.ctx, keep):
+            check(_lib.lib().ssm_vec_get(self._h, c_vp(p), 0), "ssm_vec_get")
         return out
 
     def copy(self) -> "Vec":
@@ -184,7 +223,8 @@ class AlmostBandedMatrix:
         pb, kb = _as_ptr(bands, (nb, n, w), "bands")
         pu, ku = _as_ptr(U, (nb, r, n), "U")
         pv, kv = _as_ptr(V, (nb, n, r), "V")
-        check(_lib.lib().ssm_ab_set(self._h, c_vp(pb), 0, c_vp(pu), 0, c_vp(pv), 0), "ssm_ab_set")
+        with _TorchOrder(self.ctx, kb, ku, kv):
+            check(_lib.lib().ssm_ab_set(self._h, c_vp(pb), 0, c_vp(pu), 0, c_vp(pv), 0), "ssm_ab_set")
 
     @classmethod
     def _empty(cls, ctx, n, l, u, r, nb):
@@ -241,7 +281,8 @@ class AlmostBandedMatrix:
         pb, kb = _as_ptr(bands, (nb, n, w), "bands")
         pu, ku = _as_ptr(U, (nb, r, n), "U")
         pv, kv = _as_ptr(V, (nb, n, r), "V")
-        check(_lib.lib().ssm_ab_set_rows(self._h, int(k0), int(k1), c_vp(pb), 0, c_vp(pu), 0, c_vp(pv), 0), "ssm_ab_set_rows")
+        with _TorchOrder(self.ctx, kb, ku, kv):
+            check(_lib.lib().ssm_ab_set_rows(self._h, int(k0), int(k1), c_vp(pb), 0, c_vp(pu), 0, c_vp(pv), 0), "ssm_ab_set_rows")
         return self
 
     # -- reference accessors ----------------------------------------------------------------------

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import DimensionMismatch, check, c_vp
-from .almostbanded import Context, Vec, _as_ptr, _is_torch, _to_vec, default_context
+from .almostbanded import Context, Vec, _TorchOrder, _as_ptr, _is_torch, _to_vec, default_context
 
 
 class BandedPlusSemiseparableMatrix:
@@ -40,8 +40,9 @@ class BandedPlusSemiseparableMatrix:
         self._h = c_vp()
         check(_lib.lib().ssm_bps_create(self.ctx._h, n, l, m, r, p, nb, C.byref(self._h)), "ssm_bps_create")
         ptrs = [_as_ptr(a, None, nm) for a, nm in ((B, "B"), (U, "U"), (V, "V"), (W, "W"), (S, "S"))]
-        check(_lib.lib().ssm_bps_set(self._h, c_vp(ptrs[0][0]), 0, c_vp(ptrs[1][0]), c_vp(ptrs[2][0]), 0,
-                                     c_vp(ptrs[3][0]), c_vp(ptrs[4][0]), 0), "ssm_bps_set")
+        with _TorchOrder(self.ctx, *[k for _, k in ptrs]):
+            check(_lib.lib().ssm_bps_set(self._h, c_vp(ptrs[0][0]), 0, c_vp(ptrs[1][0]), c_vp(ptrs[2][0]), 0,
+                                         c_vp(ptrs[3][0]), c_vp(ptrs[4][0]), 0), "ssm_bps_set")
 
     @classmethod
     def generate(cls, n, l, m, r, p, nb, seed, ctx: Context | None = None):

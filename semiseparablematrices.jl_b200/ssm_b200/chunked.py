@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import DimensionMismatch, check, c_vp
-from .almostbanded import Context, _as_ptr, _is_torch, default_context
+from .almostbanded import Context, _TorchOrder, _as_ptr, _is_torch, default_context
 
 
 class LargeAlmostBandedMatrix:
@@ -27,7 +27,8 @@ class LargeAlmostBandedMatrix:
         pb, kb = _as_ptr(bands, (n, w), "bands")
         pu, ku = _as_ptr(U, (r, n), "U")
         pv, kv = _as_ptr(V, (n, r), "V")
-        check(_lib.lib().ssm_abc_set(self._h, c_vp(pb), c_vp(pu), c_vp(pv)), "ssm_abc_set")
+        with _TorchOrder(self.ctx, kb, ku, kv):
+            check(_lib.lib().ssm_abc_set(self._h, c_vp(pb), c_vp(pu), c_vp(pv)), "ssm_abc_set")
 
     def _init(self, ctx, n, l, u, r):
         self.ctx, self.n, self.l, self.u, self.r = ctx, int(n), l, u, r
@@ -43,7 +44,8 @@ class LargeAlmostBandedMatrix:
 
     def generate_rhs(self, b_dev, seed):
         """fill a torch CUDA float64 tensor of length n with the shared generator's b (array id 3)"""
-        check(_lib.lib().ssm_abc_vec_generate(self._h, c_vp(b_dev.data_ptr()), seed), "ssm_abc_vec_generate")
+        with _TorchOrder(self.ctx, b_dev):
+            check(_lib.lib().ssm_abc_vec_generate(self._h, c_vp(b_dev.data_ptr()), seed), "ssm_abc_vec_generate")
         self.ctx.sync()
         return b_dev
 
@@ -58,7 +60,8 @@ class LargeAlmostBandedMatrix:
             else:
                 out = np.empty(self.n)
         po, ko = _as_ptr(out, (self.n,), "out")
-        check(_lib.lib().ssm_abc_solve(self._h, c_vp(pb), c_vp(po), int(nchunks)), "ssm_abc_solve")
+        with _TorchOrder(self.ctx, kb, ko):
+            check(_lib.lib().ssm_abc_solve(self._h, c_vp(pb), c_vp(po), int(nchunks)), "ssm_abc_solve")
         if sync and _is_torch(out):
             self.ctx.sync()
         return out
@@ -67,7 +70,8 @@ class LargeAlmostBandedMatrix:
         px, kx = _as_ptr(x, (self.n,), "x")
         pb, kb = _as_ptr(b, (self.n,), "b")
         out = C.c_double()
-        check(_lib.lib().ssm_abc_residual(self._h, c_vp(px), c_vp(pb), C.byref(out)), "ssm_abc_residual")
+        with _TorchOrder(self.ctx, kx, kb):
+            check(_lib.lib().ssm_abc_residual(self._h, c_vp(px), c_vp(pb), C.byref(out)), "ssm_abc_residual")
         return out.value
 
     @property
