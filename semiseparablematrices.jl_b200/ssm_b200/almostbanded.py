@@ -48,9 +48,11 @@ class _TorchOrder:
     """Stream ordering between torch and the library for calls that take torch CUDA tensors (the C ABI only ENQUEUES on its
     context's stream when it is given device pointers).  On entry the context's stream waits for torch's current stream — the
     tensors may still be being produced; on exit torch's current stream waits for the context's — the outputs are ready for
-    whatever torch enqueues next — and every tensor (temporaries from ``.contiguous()`` included) is recorded on the context's
-    stream so that torch's allocator does not hand its memory out again before the library has used it.  Nothing happens for
-    host arrays, nor when the context already runs on torch's current stream."""
+    whatever torch enqueues next, and a temporary from ``.contiguous()`` that is freed afterwards can only be handed out again
+    to work that torch's stream orders behind the library's use of it (torch's allocator reuses a block on the stream it was
+    allocated on).  ``Tensor.record_stream`` is deliberately NOT used: the allocator would later record an event on the
+    context's stream, which may be gone by then.  Nothing happens for host arrays, nor when the context already runs on torch's
+    current stream."""
 
     def __init__(self, ctx, *arrays):
         self.ctx = ctx
@@ -70,8 +72,6 @@ class _TorchOrder:
 
     def __exit__(self, *exc):
         if self.ext is not None:
-            for t in self.ts:
-                t.record_stream(self.ext)
             self.cur.wait_stream(self.ext)
         return False
 
