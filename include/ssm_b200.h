@@ -127,6 +127,12 @@ int  ssm_ab_qr_cols(const ssm_ab *A, int ncols, ssm_abqr **F);
  * A factor object shares V with the operand batch it was made from; writing to that batch afterwards (ssm_ab_set, _set_rows, _set_vcat,
  * _generate) first gives the batch a V of its own, so live factor objects keep the matrix they factored (qr(A) copies, :129-133). */
 int  ssm_abqr_continue(ssm_abqr *F, const ssm_ab *A, int ncols);
+/* Grow a partial factorisation together with its operand — the step adaptive QR takes when the cached operand has outgrown its storage
+ * (resizedata!, :357-394) while a factorisation of its leading columns exists: F = ssm_ab_qr_cols(A_old, k0), A = the operand after
+ * ssm_ab_resize + ssm_ab_set_rows (its old n0 x n0 block unchanged).  Afterwards F has A's size and equals ssm_ab_qr_cols(A, k0) to
+ * rounding — the stored reflectors are applied to the new columns (materialize!(Lmul{AdjQRPackedQLayout}), :201-207, restricted to them) —
+ * and ssm_abqr_continue(F, A, ncols) goes on from there.  k0 + l > n0 is SSM_E_STATE: such reflectors saw columns cut off by the old size. */
+int  ssm_abqr_resize(ssm_abqr *F, const ssm_ab *A);
 int  ssm_abqr_destroy(ssm_abqr *F);
 /* F.factors (widened band storage (2l+u+1) x n), F.factors.fill U (n x r), F.tau (n) (:174-185)           */
 int  ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t f_stride, double *U, int64_t U_stride,

@@ -87,6 +87,89 @@ __device__ inline void generic_ab_qr(const AbArgs &a, int l, int u, int r, bool 
     }
 }
 
+// Growth fix-up of a partial factorisation (ssm_abqr_resize; what adaptive QR needs when the cached operand of AlmostBandedMatrix.jl:357-394
+// has grown under a factorisation in progress).  a.RU / a.QT hold k0 reflectors formed when the operand had n0 rows and columns; a.AU / a.V are
+// the GROWN operand (n = a.n >= n0, old part unchanged).  Explicit entries of the factor records in the NEW columns c >= n0 — they can occur in
+// rows j0 .. k0+l-1, j0 = max(0, n0 - 2l - u) — were formed when those columns did not exist.  They are re-derived by replaying steps
+// j0 .. k0-1 of the sweep with the STORED reflectors (lmul!(Q', .) restricted to the new columns, :201-207):
+//   (1) backwards over k = k0-1 .. j0, un-applying H_k (an involution) to the window of U rows: recovers the U rows as they were before step j0;
+//   (2) forwards, the sweep's own bookkeeping (entering rows from the grown operand, fill extension from the new V columns) with v, tau
+//       read from QT instead of being formed.  Columns are independent under H_k, so the old columns need not be carried: only entries
+//       in columns >= n0 are written.
+// Requires k0 + l <= n0 (every row a stored reflector touches existed; checked by the caller).
+__device__ inline void generic_ab_grow_fix(const AbArgs &a, int l, int u, int r, int n0, int k0, int64_t tile, int lane) {
+    constexpr int MB = SSM_MAX_BW, MR = SSM_MAX_RANK;
+    const int ub = l + u, nfa = l + u + 1 + r, nfr = nfa, nfq = l + 1;
+    const int j0 = n0 - 2 * l - u > 0 ? n0 - 2 * l - u : 0;
+    if (k0 <= j0) return;
+    const double *au = a.AU + tile * a.np * nfa * 32 + lane;
+    const double *vv = a.V + tile * a.np * (r > 0 ? r : 1) * 32 + lane;
+    double *ru = a.RU + tile * a.np * nfr * 32 + lane;
+    const double *qt = a.QT + tile * a.np * nfq * 32 + lane;
+    double W[MB + 1][2 * MB + 1], UC[MB + 1][MR], v[MB];
+    for (int i = 0; i <= l; ++i) { for (int t = 0; t <= ub; ++t) W[i][t] = 0.0; for (int q = 0; q < MR; ++q) UC[i][q] = 0.0; }
+    // (1) backwards: window rows k .. k+l
+    for (int i = 0; i <= l; ++i)
+        for (int q = 0; q < r; ++q) UC[i][q] = ru[(((int64_t)k0 - 1 + i) * nfr + ub + 1 + q) * 32];
+    for (int k = k0 - 1; k >= j0; --k) {
+        const double tau = qt[((int64_t)k * nfq + l) * 32];
+        if (tau != 0.0)
+            for (int q = 0; q < r; ++q) {
+                double s = UC[0][q];
+                for (int i = 1; i <= l; ++i) s = fma(qt[((int64_t)k * nfq + i - 1) * 32], UC[i][q], s);
+                s *= tau; UC[0][q] -= s;
+                for (int i = 1; i <= l; ++i) UC[i][q] = fma(-qt[((int64_t)k * nfq + i - 1) * 32], s, UC[i][q]);
+            }
+        if (k > j0) {
+            for (int i = l; i >= 1; --i) for (int q = 0; q < r; ++q) UC[i][q] = UC[i - 1][q];
+            for (int q = 0; q < r; ++q) UC[0][q] = ru[(((int64_t)k - 1) * nfr + ub + 1 + q) * 32];
+        }
+    }
+    // (2) forwards from step j0; at j0 = 0 the window starts from the operand's first rows (the sweep's prologue), otherwise the rows
+    // j0 .. j0+l-1 hold nothing in a column >= n0 yet (their last live column is j0 + ub = n0 - l)
+    if (j0 == 0)
+        for (int rho = 0; rho < l; ++rho)
+            for (int t = 0; t <= ub; ++t) {
+                if (t - rho <= u) W[rho][t] = t - rho + l >= 0 ? au[((int64_t)rho * nfa + (t - rho + l)) * 32] : 0.0;
+                else { double s = 0.0; for (int q = 0; q < r; ++q) s = fma(UC[rho][q], vv[((int64_t)t * r + q) * 32], s); W[rho][t] = s; }
+            }
+    for (int k = j0; k < k0; ++k) {
+        const int64_t e = (int64_t)k + l;
+        for (int t = 0; t <= ub; ++t) W[l][t] = (t <= l + u) ? au[(e * nfa + t) * 32] : 0.0;
+        for (int q = 0; q < r; ++q) UC[l][q] = au[(e * nfa + l + u + 1 + q) * 32];
+        const double tau = qt[((int64_t)k * nfq + l) * 32];
+        if (tau != 0.0) {
+            for (int i = 1; i <= l; ++i) v[i - 1] = qt[((int64_t)k * nfq + i - 1) * 32];
+            for (int t = 1; t <= ub; ++t) {
+                double s = W[0][t];
+                for (int i = 1; i <= l; ++i) s = fma(v[i - 1], W[i][t], s);
+                s *= tau; W[0][t] -= s;
+                for (int i = 1; i <= l; ++i) W[i][t] = fma(-v[i - 1], s, W[i][t]);
+            }
+            for (int q = 0; q < r; ++q) {
+                double s = UC[0][q];
+                for (int i = 1; i <= l; ++i) s = fma(v[i - 1], UC[i][q], s);
+                s *= tau; UC[0][q] -= s;
+                for (int i = 1; i <= l; ++i) UC[i][q] = fma(-v[i - 1], s, UC[i][q]);
+            }
+        }
+        for (int t = 1; t <= ub; ++t)
+            if (k + t >= n0) ru[((int64_t)k * nfr + t) * 32] = W[0][t];
+        const int64_t c = (int64_t)k + 1 + ub;
+        for (int i = 1; i <= l; ++i) {
+            for (int t = 1; t <= ub; ++t) W[i - 1][t - 1] = W[i][t];
+            double s = 0.0;
+            for (int q = 0; q < r; ++q) s = fma(UC[i][q], vv[(c * r + q) * 32], s);
+            W[i - 1][ub] = s;
+            for (int q = 0; q < r; ++q) UC[i - 1][q] = UC[i][q];
+        }
+    }
+    // the partially updated rows k0 .. k0+l-1: window row i = matrix row k0+i, window column t = matrix column k0+t
+    for (int i = 0; i < l; ++i)
+        for (int t = i; t <= ub; ++t)
+            if (k0 + t >= n0) ru[(((int64_t)k0 + i) * nfr + (t - i)) * 32] = W[i][t];
+}
+
 // transpose: b <- Q'b (reflectors 0..n-1 in order); else b <- Q b (reverse order).  AlmostBandedMatrix.jl:181,201-207
 __device__ inline void generic_ab_qt(const AbSolveArgs &a, int l, bool transpose, int64_t tile, int lane) {
     constexpr int MB = SSM_MAX_BW;

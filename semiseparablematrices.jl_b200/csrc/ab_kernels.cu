@@ -511,10 +511,81 @@ int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &
 __global__ void __launch_bounds__(32) ab_qr_continue_kernel(const AbArgs a, int l, int u, int r, int kstart) {
     generic_ab_qr(a, l, u, r, false, true, (int64_t)blockIdx.x, (int)threadIdx.x, kstart);
 }
-// continue a partial factorisation in place from column kstart (a.RU / a.QT hold it) to a.ncols reflectors; runtime-shape kernel for every (l,u,r)
+// Register-resident second entry of K1 for the compiled shapes: the sweep re-enters at column kstart.  Everything the sweep addresses is
+// relative to its first row, so the continuation is the SAME sweep on pointers moved down by kstart rows (row kstart plays row 0: it lives in
+// slot 0, the phases line up), with a prologue that takes the l partially updated rows out of the factor records — RU: the diagonal and what is
+// right of it plus the U row; QT of the columns kstart .. kstart+l-2: the entries below their diagonals — instead of out of the operand.
+template <int L, int U, int R>
+__global__ void __launch_bounds__(32) ab_qr_cont_kernel(const AbArgs a, const int kstart) {
+    using D = AbDims<L, U, R>;
+    constexpr int P = D::P, UB = D::UB, NFA = D::NFA, NFR = D::NFR, NFQ = D::NFQ;
+    const int64_t tile = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int n = a.n - kstart, ncols = a.ncols - kstart;
+    const double *au = a.AU + (tile * a.np + kstart) * NFA * 32 + lane;
+    const double *vv = a.V + (tile * a.np + kstart) * (R > 0 ? R : 1) * 32 + lane;
+    double *ru = a.RU + (tile * a.np + kstart) * NFR * 32 + lane;
+    double *qt = a.QT + (tile * a.np + kstart) * NFQ * 32 + lane;
+    AbState<L, U, R> st;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+#pragma unroll
+        for (int dd = 0; dd < D::ND; ++dd) st.A[i][dd] = 0.0;
+#pragma unroll
+        for (int t = 0; t <= UB; ++t)                 // entry (row i, column t) sits at diagonal index t - i + L
+            st.A[i][t - i + L] = (t >= i) ? ru[(i * NFR + (t - i)) * 32] : qt[(t * NFQ + (i - t - 1)) * 32];
+#pragma unroll
+        for (int q = 0; q < R; ++q) st.UC[i][q] = ru[(i * NFR + UB + 1 + q) * 32];
+        st.RH[i] = 0.0;
+    }
+    const int64_t nsteps = ((n + P - 1) / P) * P;
+    DirectLoaderD<NFA, R, 0, +1> ld;
+    ld.init(au + (int64_t)L * NFA * 32, vv + (int64_t)(UB + 1) * R * 32, nullptr, nullptr, 0, nsteps);
+    for (int kb = 0; kb < n; kb += P) {
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) {
+            const int k = kb + ph;
+            double rec[NFA], vc[R > 0 ? R : 1], bb[1];
+            ld.acquire(k, rec, vc, bb);
+            double out_r[NFR], out_q[NFQ], out_c;
+            ab_step<L, U, R, false>(st, ph, rec, vc, 0.0, k < ncols, out_r, out_q, out_c);
+            if (k < n) {
+#pragma unroll
+                for (int f = 0; f < NFR; ++f) ru[((int64_t)k * NFR + f) * 32] = out_r[f];
+#pragma unroll
+                for (int f = 0; f < NFQ; ++f) qt[((int64_t)k * NFQ + f) * 32] = out_q[f];
+            }
+        }
+    }
+}
+// continue a partial factorisation in place from column kstart (a.RU / a.QT hold it) to a.ncols reflectors
 int launch_ab_qr_continue(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, int kstart) {
     if (ntiles <= 0) return 0;
+    if (c->ab_variant != 9) {
+#define X(L_, U_, R_)                                                                              \
+    if (l == L_ && u == U_ && r == R_) {                                                           \
+        ab_qr_cont_kernel<L_, U_, R_><<<(unsigned)ntiles, 32, 0, c->stream>>>(a, kstart);          \
+        c->launches++;                                                                             \
+        SSM_CUDA(cudaGetLastError());                                                              \
+        return 0;                                                                                  \
+    }
+        SSM_AB_SHAPES(X)
+#undef X
+    }
     ab_qr_continue_kernel<<<(unsigned)ntiles, 32, 0, c->stream>>>(a, l, u, r, kstart);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+__global__ void __launch_bounds__(32) ab_grow_fix_kernel(const AbArgs a, int l, int u, int r, int n0, int k0) {
+    generic_ab_grow_fix(a, l, u, r, n0, k0, (int64_t)blockIdx.x, (int)threadIdx.x);
+}
+// ssm_abqr_resize: re-derive the factor entries that reach into the columns >= n0 of the grown operand (ab_generic.cuh).  At most 2l+u steps
+// of a runtime-shape replay per system: an edge computation, the same kernel for every shape.
+int launch_ab_grow_fix(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, int n0, int k0) {
+    if (ntiles <= 0) return 0;
+    ab_grow_fix_kernel<<<(unsigned)ntiles, 32, 0, c->stream>>>(a, l, u, r, n0, k0);
     c->launches++;
     SSM_CUDA(cudaGetLastError());
     return 0;

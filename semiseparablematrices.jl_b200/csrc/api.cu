@@ -584,6 +584,38 @@ int ssm_abqr_continue(ssm_abqr *F, const ssm_ab *A, int ncols) {
     F->ncols = ncols;
     return 0;
 }
+// Grow a partial factorisation with its operand (adaptive QR on a cached operand, AlmostBandedMatrix.jl:357-394 + :139-172 on the trailing view):
+// F = ssm_ab_qr_cols(A_old, k0), A = the operand after ssm_ab_resize + ssm_ab_set_rows (the old n0 x n0 part unchanged).  Afterwards F has A's
+// size and equals ssm_ab_qr_cols(A, k0) to rounding, so ssm_abqr_continue(F, A, ncols) goes on from it.  The records of the old rows move into
+// larger storage; the entries of rows >= n0 - 2l - u that reach into the new columns are re-derived by applying the stored reflectors to those
+// columns (launch_ab_grow_fix); the rows from k0 on pass through the sweep once more without new reflectors.
+int ssm_abqr_resize(ssm_abqr *F, const ssm_ab *A) {
+    SSM_CHECK_ARG(F && A, "null argument");
+    if (F->l != A->l || F->u != A->u || F->r != A->r || F->nb != A->nb) { set_error("ssm_abqr_resize: DimensionMismatch: factor object and operand have different bandwidths, rank or batch size"); return SSM_E_SHAPE; }
+    if (A->n < F->n) { set_error("ssm_abqr_resize: DimensionMismatch: cannot shrink a %d x %d factorisation to %d x %d", F->n, F->n, A->n, A->n); return SSM_E_SHAPE; }
+    if (!F->QT) { set_error("ssm_abqr_resize: factor object keeps no reflectors"); return SSM_E_STATE; }
+    if (A->n > F->n && F->ncols + F->l > F->n) {
+        set_error("ssm_abqr_resize: %d reflectors of a %d x %d matrix with lower bandwidth %d: the last of them saw columns cut off by the old size and do not "
+                  "belong to the grown matrix (factor at most n - l columns before growing, as adaptive QR does)", F->ncols, F->n, F->n, F->l);
+        return SSM_E_STATE;
+    }
+    ssm_ctx *c = F->ctx;
+    uses(A->AU, c); uses(A->V, c);
+    if (A->n == F->n) { F->V = A->V; return 0; }
+    DeviceGuard g(c->device);
+    const int n0 = F->n, k0 = F->ncols;
+    DevBufPtr RU, QT;
+    SSM_TRY(dev_alloc(c, (size_t)(A->ntiles * A->np * (F->l + F->u + 1 + F->r) * 32), true, RU));
+    SSM_TRY(dev_alloc(c, (size_t)(A->ntiles * A->np * (F->l + 1) * 32), true, QT));
+    SSM_TRY(copy_tile_rows(c, RU->p, A->np, F->RU->p, F->np, n0, F->l + F->u + 1 + F->r, F->ntiles));
+    SSM_TRY(copy_tile_rows(c, QT->p, A->np, F->QT->p, F->np, n0, F->l + 1, F->ntiles));
+    SSM_CUDA(cudaStreamSynchronize(c->stream));       // the old blocks are released below: nothing may still be reading them
+    F->RU = RU; F->QT = QT; F->V = A->V; F->n = A->n; F->np = A->np;
+    AbArgs a{A->AU->p, A->V->p, F->RU->p, F->QT->p, nullptr, nullptr, A->n, A->np, k0};
+    if (k0 == 0) return launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, false, true);
+    SSM_TRY(launch_ab_grow_fix(c, A->l, A->u, A->r, A->ntiles, a, n0, k0));
+    return launch_ab_qr_continue(c, A->l, A->u, A->r, A->ntiles, a, k0);
+}
 int ssm_ab_qr(const ssm_ab *A, ssm_abqr **out) {
     SSM_CHECK_ARG(A && out, "null argument");
     return ssm_ab_qr_cols(A, A->n - 1, out);     // min(m - 1, n) for a real square matrix (:137)

@@ -188,6 +188,7 @@ bool pick_group(const ssm_ctx *c, size_t block_bytes, int64_t ntiles, int *nstag
 // launchers implemented in ab_kernels.cu; return 0 or SSM_E_UNSUPPORTED when (l,u,r) has no fast instance
 int launch_ab_qr(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, bool with_rhs, bool store_q);
 int launch_ab_qr_continue(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, int kstart);
+int launch_ab_grow_fix(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbArgs &a, int n0, int k0);
 int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a, bool transpose);
 int launch_ab_backsolve(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a);
 // operand-level triangular solves (unfactored AlmostBandedMatrix), generic kernels only

@@ -61,6 +61,7 @@ _SIGS = {
     "ssm_ab_qr": (C.c_int, [c_vp, C.POINTER(c_vp)]),
     "ssm_ab_qr_cols": (C.c_int, [c_vp, C.c_int, C.POINTER(c_vp)]),
     "ssm_abqr_continue": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "ssm_abqr_resize": (C.c_int, [c_vp, c_vp]),
     "ssm_abqr_destroy": (C.c_int, [c_vp]),
     "ssm_abqr_get": (C.c_int, [c_vp, c_vp, i64, c_vp, i64, c_vp, i64]),
     "ssm_abqr_ldiv": (C.c_int, [c_vp, c_vp]),

@@ -415,6 +415,13 @@ class AlmostBandedQR:
         self.ncols = int(ncols)
         return self
 
+    def resize(self, A: AlmostBandedMatrix):
+        """Grow this partial factorisation to the size of ``A`` — the operand it was made from after ``A.resize(n)`` + ``set_rows`` (the
+        adaptive-QR growth step, AlmostBandedMatrix.jl:357-394); afterwards equal to ``qr(A, ncols=self.ncols)``; ``continue_to`` goes on."""
+        check(_lib.lib().ssm_abqr_resize(self._h, A._h), "ssm_abqr_resize")
+        self._A, self.n = A, A.n
+        return self
+
     def get(self):
         n, l, u, r, nb = self.n, self.l, self.u, self.r, self.nb
         F = np.zeros((nb, n, 2 * l + u + 1)); U = np.empty((nb, r, n)); tau = np.empty((nb, n))
