@@ -30,6 +30,18 @@ int stage_in(ssm_ctx *c, double *stg, size_t off, const double *src, int64_t str
 }
 }  // namespace
 
+// A factor object shares the operand records (U and S[:, 1:p] are part of the factorisation): rewriting the operands of a batch that has
+// live factor objects first gives the batch records of its own.
+int ssm::bps_own_rec(ssm_bps *A) {
+    if (!A->REC || A->REC.use_count() <= 1) return 0;
+    DevBufPtr nr;
+    SSM_TRY(dev_alloc(A->ctx, A->REC->count, true, nr));
+    uses(A->REC, A->ctx);
+    A->REC = nr;
+    A->GT.reset(); A->gt_valid = false;           // the factor objects keep the old one
+    return 0;
+}
+
 #define SSM_CHECK_ARG(cond, msg) do { if (!(cond)) { set_error("%s: %s", __func__, msg); return SSM_E_ARG; } } while (0)
 
 extern "C" {
@@ -50,17 +62,6 @@ int ssm_bps_create(ssm_ctx *c, int n, int l, int m, int r, int p, int64_t nb, ss
     return 0;
 }
 int ssm_bps_destroy(ssm_bps *A) { if (A) { obj_sync(A->ctx); delete A; } return 0; }
-
-// A factor object shares the operand records (U and S[:, 1:p] are part of the factorisation): rewriting the operands of a batch that has
-// live factor objects first gives the batch records of its own.
-static int bps_own_rec(ssm_bps *A) {
-    if (!A->REC || A->REC.use_count() <= 1) return 0;
-    DevBufPtr nr;
-    SSM_TRY(dev_alloc(A->ctx, A->REC->count, true, nr));
-    uses(A->REC, A->ctx);
-    A->REC = nr;
-    return 0;
-}
 
 int ssm_bps_set(ssm_bps *A, const double *B, int64_t sb, const double *U, const double *V, int64_t suv, const double *W, const double *S, int64_t sws) {
     SSM_CHECK_ARG(A && B, "null argument");
@@ -85,6 +86,7 @@ int ssm_bps_set(ssm_bps *A, const double *B, int64_t sb, const double *U, const 
     SSM_TRY(stage_in(c, stg, off, S, sws, ew, A->nb, &dS));
     // staged copies are dense; untouched device pointers keep the caller's stride (equal to dense by construction above)
     SSM_TRY(launch_bps_pack(c, A, dB, (int64_t)eb, dU, dV, (int64_t)eu, dW, dS, (int64_t)ew));
+    SSM_TRY(launch_bps_gram(c, A));               // U'U goes with the operands (qr then reads the records once)
     SSM_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -92,7 +94,8 @@ int ssm_bps_generate(ssm_bps *A, uint64_t seed) {
     SSM_CHECK_ARG(A, "null argument");
     DevGuard g(A->ctx->device);
     SSM_TRY(bps_own_rec(A));
-    return launch_bps_generate(A->ctx, A, seed);
+    SSM_TRY(launch_bps_generate(A->ctx, A, seed));
+    return launch_bps_gram(A->ctx, A);
 }
 
 int ssm_bps_qr(const ssm_bps *A, ssm_bpsqr **out) {
@@ -103,14 +106,13 @@ int ssm_bps_qr(const ssm_bps *A, ssm_bpsqr **out) {
     if (F) {
         if (F->n != A->n || F->l != A->l || F->m != A->m || F->r != A->r || F->p != A->p || F->nb != A->nb) { set_error("ssm_bps_qr: factor object has a different shape"); return SSM_E_SHAPE; }
         F->REC = A->REC;
-        uses(F->OUT, c); uses(F->GT, c); uses(F->TT, c);        // refactorisation of another context's factor object runs on A's stream
+        uses(F->OUT, c); uses(F->TT, c);        // refactorisation of another context's factor object runs on A's stream
     } else {
         F = new ssm_bpsqr();
         F->ctx = c; F->ref.bind(c); F->n = A->n; F->l = A->l; F->m = A->m; F->r = A->r; F->p = A->p; F->tl = A->tl; F->tm = A->tm; F->tr = A->tr; F->tp = A->tp;
         F->nb = A->nb; F->ntiles = A->ntiles; F->np = A->np; F->npo = (int64_t)A->n + PAD;
         F->REC = A->REC;
         int rc = dev_alloc(c, (size_t)(F->ntiles * F->npo * bps_nfo(F->tl, F->tm, F->tr, F->tp) * 32), true, F->OUT);
-        if (!rc) rc = dev_alloc(c, (size_t)(F->ntiles * F->tr * F->tr * 32), true, F->GT);
         if (!rc) rc = dev_alloc(c, (size_t)(F->ntiles * F->tr * 32), true, F->TT);
         if (rc) { delete F; return rc; }
     }

@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(64) bps_qr_pair_kernel(const double *REC, cons
 template <int L, int M, int R, int P>
 static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
     using D = BpsDims<L, M, R, P>;
-    bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)A->ntiles, 32 * BPS_RW, 0, c->stream>>>(A->REC->p, nullptr, F->GT->p, nullptr, A->n, A->np, 0);
-    c->launches++;
+    if (!A->gt_valid) SSM_TRY(launch_bps_gram(c, A));      // operands written by another kernel (rq_mul): form U'U now
+    F->GT = A->GT;
     // ab_variant: 0 auto, 1 one warp per tile, 2 two warps of 16 systems, 3 pair mode.  Measured on B200 (n = 4096, (3,3,2,2)):
     //   systems    4,096   8,192   12,288   16,384 (config 3)   32,768   65,536
     //   1 warp     4.28    4.29    4.33     4.45                6.65     13.7  ms
@@ -568,6 +568,23 @@ static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
     c->launches++;
     SSM_CUDA(cudaGetLastError());
     return 0;
+}
+template <int L, int M, int R, int P>
+static int gram_shape(ssm_ctx *c, const ssm_bps *A) {
+    using D = BpsDims<L, M, R, P>;
+    bps_reduce_kernel<D::NFA, D::FU, R><<<(unsigned)A->ntiles, 32 * BPS_RW, 0, c->stream>>>(A->REC->p, nullptr, A->GT->p, nullptr, A->n, A->np, 0);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    A->gt_valid = true;
+    return 0;
+}
+int launch_bps_gram(ssm_ctx *c, const ssm_bps *A) {
+    if (!A->GT) SSM_TRY(dev_alloc(c, (size_t)(A->ntiles * A->tr * A->tr * 32) + 32, true, A->GT));
+#define X(L_, M_, R_, P_) if (A->tl == L_ && A->tm == M_ && A->tr == R_ && A->tp == P_) return gram_shape<L_, M_, R_, P_>(c, A);
+    SSM_BPS_SHAPES(X)
+#undef X
+    set_error("no BPS kernel for padded shape (%d,%d,%d,%d)", A->tl, A->tm, A->tr, A->tp);
+    return SSM_E_UNSUPPORTED;
 }
 int launch_bps_qr(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
 #define X(L_, M_, R_, P_) if (A->tl == L_ && A->tm == M_ && A->tr == R_ && A->tp == P_) return qr_shape<L_, M_, R_, P_>(c, A, F);

@@ -405,6 +405,8 @@ int ssm_bpsqr_rq_mul(const ssm_bpsqr *F, ssm_bps **out) {
     const bool fresh = Q == nullptr;
     if (Q && (Q->n != F->n || Q->l != F->l || Q->m != F->l || Q->r != F->r || Q->p != F->r || Q->nb != F->nb)) { set_error("ssm_bpsqr_rq_mul: result batch has a different shape"); return SSM_E_SHAPE; }
     if (!Q) SSM_TRY(ssm_bps_create(c, F->n, F->l, F->l, F->r, F->r, F->nb, &Q));
+    else SSM_TRY(bps_own_rec(Q));                          // a reused result batch may be the operand of a live factor object (even of F itself)
+    Q->gt_valid = false;                                   // its U changes: qr(Q) forms U'U again
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     DevBufPtr flag;
     int rc = dev_alloc(c, 1, true, flag);

@@ -139,12 +139,17 @@ struct ssm_abqr {
 struct ssm_bps {
     ssm_ctx *ctx; ssm::CtxRef ref; int n, l, m, r, p, tl, tm, tr, tp; int64_t nb, ntiles, np;
     ssm::DevBufPtr REC;         // [ntiles][np][nfa][32], record (FRONT + row): B0 row (tl+tm+1) | U (tr) | V (tr) | W (tp) | S (tp)
+    // U'U of every system ([ntiles][tr*tr][32]), the one reduction the QR sweep needs before its first step (semiseparableqr.jl:36-48,573-640).
+    // It depends on the operands only, so it is formed when they are written (ssm_bps_set / _generate) and kept with them: qr(A) then makes
+    // ONE pass over the records.  gt_valid is false for a batch written by another kernel (rq_mul's result); qr forms it on demand then.
+    mutable ssm::DevBufPtr GT;
+    mutable bool gt_valid = false;
 };
 struct ssm_bpsqr {
     ssm_ctx *ctx; ssm::CtxRef ref; int n, l, m, r, p, tl, tm, tr, tp; int64_t nb, ntiles, np, npo;
     ssm::DevBufPtr REC;         // shared with the operand batch (U and S[:,1:p] are part of the factorisation)
     ssm::DevBufPtr OUT;         // [ntiles][npo][nfo][32], record row: tail (tl) | Vnew (tr) | tau || pivot,d (tl+tm+1) | alpha (tp) | beta (tr) | A'U (tr)
-    ssm::DevBufPtr GT;          // [ntiles][tr*tr][32]  U'U of each system
+    ssm::DevBufPtr GT;          // [ntiles][tr*tr][32]  U'U of each system (shared with the operand batch)
     ssm::DevBufPtr TT;          // [ntiles][tr][32]     U'b scratch of lmul!(Q', b)
 };
 
@@ -160,6 +165,8 @@ int launch_bps_pack(ssm_ctx *c, ssm_bps *A, const double *B, int64_t sb, const d
                     const double *W, const double *S, int64_t sws);
 int launch_bps_generate(ssm_ctx *c, ssm_bps *A, uint64_t seed);
 int launch_bps_qr(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F);
+int launch_bps_gram(ssm_ctx *c, const ssm_bps *A);       // A->GT <- U'U (K5), marks it valid
+int bps_own_rec(ssm_bps *A);                              // copy-on-write: records (and U'U) of its own before A's operands are rewritten
 int launch_bpsqr_unpack(ssm_ctx *c, const ssm_bpsqr *F, double *B, int64_t sb, double *U, double *V, int64_t suv, double *W,
                         double *S, int64_t sws, double *tau, int64_t st);
 int launch_bps_qt(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double *rhs);
