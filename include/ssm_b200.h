@@ -137,6 +137,11 @@ int  ssm_abqr_destroy(ssm_abqr *F);
 /* F.factors (widened band storage (2l+u+1) x n), F.factors.fill U (n x r), F.tau (n) (:174-185)           */
 int  ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t f_stride, double *U, int64_t U_stride,
                   double *tau, int64_t tau_stride);
+/* The inverse of ssm_abqr_get: a factor object made from the reference's own fields — F.factors (widened band storage (2l+u+1) x n, its
+ * fill U n x r and V r x n) and F.tau (:174-185) — for a QR{Float64,AlmostBandedMatrix} this library instance did not produce (a copy, a
+ * deserialised factorisation), so that ldiv!(F, b) works on any F.  ncols < 0 means the complete factorisation (n - 1 reflectors).        */
+int  ssm_abqr_set(ssm_ctx *ctx, int n, int l, int u, int r, int64_t nb, const double *factors, int64_t f_stride, const double *U,
+                  int64_t U_stride, const double *V, int64_t V_stride, const double *tau, int64_t tau_stride, int ncols, ssm_abqr **F);
 /* ldiv!(F, b) (:187-192): b <- R \ (Q'b), in place                                                        */
 int  ssm_abqr_ldiv(const ssm_abqr *F, ssm_vec *b);
 /* F \ b = ldiv!(F, copy(b)): x <- R \ (Q'b), b untouched (x may alias b)                                   */

@@ -643,6 +643,46 @@ int ssm_abqr_get(const ssm_abqr *F, double *factors, int64_t sf, double *U, int6
     return 0;
 }
 
+// A factor object from the reference's own fields (F.factors = widened bands + fill (U, V), F.tau; AlmostBandedMatrix.jl:174-185): the
+// inverse of ssm_abqr_get.  What the glue calls for a QR it did not make itself (a copy, a deserialised factorisation) before ldiv!.
+int ssm_abqr_set(ssm_ctx *c, int n, int l, int u, int r, int64_t nb, const double *factors, int64_t sf, const double *U, int64_t su,
+                 const double *V, int64_t sv, const double *tau, int64_t st, int ncols, ssm_abqr **out) {
+    SSM_CHECK_ARG(c && out && factors && tau && (r == 0 || (U && V)), "null argument");
+    SSM_CHECK_ARG(n >= 1 && nb >= 1 && l >= 0 && u >= 0 && r >= 0, "bad sizes");
+    if (l > SSM_MAX_BW || u > SSM_MAX_BW || r > SSM_MAX_RANK) { set_error("(l,u,r)=(%d,%d,%d) exceeds compiled limits (%d,%d,%d)", l, u, r, SSM_MAX_BW, SSM_MAX_BW, SSM_MAX_RANK); return SSM_E_UNSUPPORTED; }
+    if (ncols < 0) ncols = n - 1;
+    if (ncols > n) { set_error("ssm_abqr_set: ncols = %d outside 0..n = %d", ncols, n); return SSM_E_ARG; }
+    const size_t ef = (size_t)(2 * l + u + 1) * n, eu = (size_t)n * r, et = (size_t)n;
+    if (sf == 0) sf = (int64_t)ef;
+    if (su == 0) su = (int64_t)eu;
+    if (sv == 0) sv = (int64_t)eu;
+    if (st == 0) st = (int64_t)et;
+    if ((size_t)sf < ef || (size_t)su < eu || (size_t)sv < eu || (size_t)st < et) { set_error("ssm_abqr_set: stride smaller than one system"); return SSM_E_SHAPE; }
+    DeviceGuard g(c->device);
+    auto *F = new ssm_abqr();
+    F->ctx = c; F->ref.bind(c); F->n = n; F->l = l; F->u = u; F->r = r; F->nb = nb; F->ntiles = ntiles_of(nb); F->np = (int64_t)n + PAD; F->ncols = ncols;
+    int rc = dev_alloc(c, (size_t)(F->ntiles * F->np * (l + u + 1 + r) * 32), true, F->RU);
+    if (!rc) rc = dev_alloc(c, (size_t)(F->ntiles * F->np * (l + 1) * 32), true, F->QT);
+    if (!rc) rc = dev_alloc(c, (size_t)(F->ntiles * F->np * (r > 0 ? r : 1) * 32), true, F->V);
+    if (rc) { delete F; return rc; }
+    const bool dev = is_device_ptr(factors) && is_device_ptr(tau) && (r == 0 || (is_device_ptr(U) && is_device_ptr(V)));
+    if (dev) rc = launch_abqr_pack(c, F, factors, sf, U, su, V, sv, tau, st);
+    else {
+        double *stg;
+        rc = staging_dev(c, (size_t)nb * (ef + 2 * eu + et), &stg);
+        double *sF = stg, *sU = sF + (size_t)nb * ef, *sV = sU + (size_t)nb * eu, *sT = sV + (size_t)nb * eu;
+        if (!rc) rc = h2d_block(c, sF, factors, sf, ef, nb);
+        if (!rc && r > 0) rc = h2d_block(c, sU, U, su, eu, nb);
+        if (!rc && r > 0) rc = h2d_block(c, sV, V, sv, eu, nb);
+        if (!rc) rc = h2d_block(c, sT, tau, st, et, nb);
+        if (!rc) rc = launch_abqr_pack(c, F, sF, (int64_t)ef, sU, (int64_t)eu, sV, (int64_t)eu, sT, (int64_t)et);
+        if (!rc) { cudaError_t e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); }
+    }
+    if (rc) { delete F; return rc; }
+    *out = F;
+    return 0;
+}
+
 static int check_vec(const char *fn, int n, int64_t nb, const ssm_ctx *c, const ssm_vec *b) {
     if (!b) { set_error("%s: null vector", fn); return SSM_E_ARG; }
     if (b->n != n || b->nb != nb) { set_error("%s: DimensionMismatch: vector batch is %lld x %d, matrix batch is %lld x %d", fn, (long long)b->nb, b->n, (long long)nb, n); return SSM_E_SHAPE; }

@@ -211,6 +211,8 @@ int launch_ab_unpack(ssm_ctx *c, const ssm_ab *A, double *bands, int64_t sb, dou
                      int64_t sv);
 int launch_abqr_unpack(ssm_ctx *c, const ssm_abqr *F, double *factors, int64_t sf, double *U, int64_t su,
                        double *tau, int64_t st);
+int launch_abqr_pack(ssm_ctx *c, ssm_abqr *F, const double *factors, int64_t sf, const double *U, int64_t su, const double *V, int64_t sv,
+                     const double *tau, int64_t st);
 int launch_ab_generate(ssm_ctx *c, ssm_ab *A, uint64_t seed, int dist);
 int launch_vec_pack(ssm_ctx *c, ssm_vec *v, const double *b, int64_t stride, int64_t s0, int64_t count);
 int launch_vec_unpack(ssm_ctx *c, const ssm_vec *v, double *b, int64_t stride, int64_t s0, int64_t count);

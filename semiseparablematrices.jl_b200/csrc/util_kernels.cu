@@ -145,6 +145,28 @@ __global__ void abqr_unpack_kernel(const double *RU, const double *QT, double *f
     if (tau) tau[s * st + k] = qrec[l * 32];
 }
 
+// reference layout -> QR factor records (the inverse of abqr_unpack_kernel, plus the V records): what a factor object that was not made by this
+// library instance (a copy, a deserialised QR) is re-created from.  Entries outside the matrix stay zero (the buffers are zero-initialised).
+__global__ void abqr_pack_kernel(double *RU, double *QT, double *Vr, const double *factors, int64_t sf, const double *U, int64_t su, const double *V,
+                                 int64_t sv, const double *tau, int64_t st, int n, int l, int u, int r, int64_t nb, int64_t np) {
+    const int lane = threadIdx.x;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    const int64_t tile = blockIdx.y;
+    const int64_t s = tile * TILE + lane;
+    if (k >= n) return;
+    const bool live = s < nb;                       // spare lanes of the last tile hold identity rows: nothing divides by zero
+    const int ub = l + u, nfr = l + u + 1 + r, nfq = l + 1, nd = 2 * l + u + 1;
+    double *rrec = RU + ((tile * np + k) * nfr) * 32 + lane;
+    double *qrec = QT + ((tile * np + k) * nfq) * 32 + lane;
+    for (int t = 0; t <= ub; ++t) { const int64_t j = k + t; rrec[t * 32] = live ? (j < n ? factors[s * sf + (int64_t)(ub - t) + (int64_t)nd * j] : 0.0) : (t == 0 ? 1.0 : 0.0); }
+    for (int i = 1; i <= l; ++i) qrec[(i - 1) * 32] = (live && k + i < n) ? factors[s * sf + (int64_t)(ub + i) + (int64_t)nd * k] : 0.0;
+    for (int q = 0; q < r; ++q) {
+        rrec[(ub + 1 + q) * 32] = live ? U[s * su + k + (int64_t)n * q] : 0.0;
+        Vr[((tile * np + k) * r + q) * 32 + lane] = live ? V[s * sv + q + (int64_t)r * k] : 0.0;
+    }
+    qrec[l * 32] = live ? tau[s * st + k] : 0.0;
+}
+
 // ---- vectors: [nb][n] <-> [tile][rec][32] through a 32x32 shared-memory transpose -------------------------
 __global__ void vec_pack_kernel(double *d, const double *b, int64_t stride, int n, int64_t nb, int64_t np, int64_t s0, int64_t count) {
     __shared__ double t[32][33];
@@ -276,6 +298,14 @@ int launch_abqr_unpack(ssm_ctx *c, const ssm_abqr *F, double *factors, int64_t s
     if (factors) { band_corner_zero_kernel<<<(unsigned)F->nb, 64, 0, c->stream>>>(factors, sf, F->n, F->l, F->l + F->u, F->nb); c->launches++; }
     abqr_unpack_kernel<<<rec_grid(F->n, F->ntiles), dim3(32, 8), 0, c->stream>>>(F->RU->p, F->QT->p, factors, sf, U, su, tau, st, F->n,
                                                                                   F->l, F->u, F->r, F->nb, F->np);
+    c->launches++;
+    SSM_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_abqr_pack(ssm_ctx *c, ssm_abqr *F, const double *factors, int64_t sf, const double *U, int64_t su, const double *V, int64_t sv,
+                     const double *tau, int64_t st) {
+    abqr_pack_kernel<<<rec_grid(F->n, F->ntiles), dim3(32, 8), 0, c->stream>>>(F->RU->p, F->QT->p, F->V->p, factors, sf, U, su, V, sv, tau, st, F->n, F->l,
+                                                                                F->u, F->r, F->nb, F->np);
     c->launches++;
     SSM_CUDA(cudaGetLastError());
     return 0;

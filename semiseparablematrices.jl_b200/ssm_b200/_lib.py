@@ -64,6 +64,7 @@ _SIGS = {
     "ssm_abqr_resize": (C.c_int, [c_vp, c_vp]),
     "ssm_abqr_destroy": (C.c_int, [c_vp]),
     "ssm_abqr_get": (C.c_int, [c_vp, c_vp, i64, c_vp, i64, c_vp, i64]),
+    "ssm_abqr_set": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, c_vp, i64, c_vp, i64, c_vp, i64, c_vp, i64, C.c_int, C.POINTER(c_vp)]),
     "ssm_abqr_ldiv": (C.c_int, [c_vp, c_vp]),
     "ssm_abqr_solve": (C.c_int, [c_vp, c_vp, c_vp]),
     "ssm_mat_create": (C.c_int, [c_vp, C.c_int, C.c_int, i64, C.POINTER(c_vp)]),

@@ -403,6 +403,29 @@ class AlmostBandedQR:
         self.ncols = A.n - 1 if ncols is None else int(ncols)      # min(m - 1, n) for a real square matrix (:137)
         check(_lib.lib().ssm_ab_qr_cols(A._h, self.ncols, C.byref(self._h)), "ssm_ab_qr_cols")
 
+    @classmethod
+    def from_factors(cls, factors, U, V, tau, lu, ncols=None, ctx: Context | None = None):
+        """A factor object from the reference's own fields (``ssm_abqr_set``): ``factors`` (nb, n, 2l+u+1) widened band storage, ``U`` (nb, r, n),
+        ``V`` (nb, n, r), ``tau`` (nb, n) — what ``get()`` / ``factors`` / ``tau`` return.  For a QR that was not made by this library instance."""
+        l, u = (int(x) for x in lu)
+        factors = np.ascontiguousarray(factors, dtype=np.float64); U = np.ascontiguousarray(U, dtype=np.float64)
+        V = np.ascontiguousarray(V, dtype=np.float64); tau = np.ascontiguousarray(tau, dtype=np.float64)
+        single = factors.ndim == 2
+        if single:
+            factors, U, V, tau = factors[None], U[None], V[None], tau[None]
+        nb, n, w = factors.shape
+        r = int(U.shape[1])
+        if w != 2 * l + u + 1 or U.shape != (nb, r, n) or V.shape != (nb, n, r) or tau.shape != (nb, n):
+            raise DimensionMismatch("Data and fill must be compatible size")
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self.n, self.l, self.u, self.r, self.nb, self.single, self._A = n, l, u, r, nb, single, None
+        self.ncols = n - 1 if ncols is None else int(ncols)
+        self._h = c_vp()
+        P = lambda a: c_vp(a.ctypes.data)
+        check(_lib.lib().ssm_abqr_set(self.ctx._h, n, l, u, r, nb, P(factors), 0, P(U), 0, P(V), 0, P(tau), 0, self.ncols, C.byref(self._h)), "ssm_abqr_set")
+        return self
+
     def refactor(self, A: AlmostBandedMatrix):
         """qr into the existing factor storage (no allocation): steady-state use and benchmarking."""
         check(_lib.lib().ssm_ab_qr_cols(A._h, self.ncols, C.byref(self._h)), "ssm_ab_qr_cols")
