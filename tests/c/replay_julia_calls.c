@@ -29,22 +29,23 @@ static double rnd(void) {      /* xorshift, uniform in (-1, 1) */
 }
 
 /* dense n x n column-major helpers */
-static void dense_solve(int n, const double *A, const double *b, double *x) {   /* Gaussian elimination with partial pivoting */
-    double *M = malloc(sizeof(double) * n * (n + 1));
-    for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) M[i + (size_t)(n) * j] = A[i + (size_t)n * j];
+static void dense_solve(int n, const double *A, const double *b, double *x) {   /* Gaussian elimination with partial pivoting (row-major work copy) */
+    double *M = malloc(sizeof(double) * (size_t)n * n);
+    for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) M[(size_t)i * n + j] = A[i + (size_t)n * j];
     double *r = malloc(sizeof(double) * n);
     memcpy(r, b, sizeof(double) * n);
     for (int k = 0; k < n; ++k) {
         int p = k;
-        for (int i = k + 1; i < n; ++i) if (fabs(M[i + (size_t)n * k]) > fabs(M[p + (size_t)n * k])) p = i;
-        if (p != k) { for (int j = 0; j < n; ++j) { double t = M[k + (size_t)n * j]; M[k + (size_t)n * j] = M[p + (size_t)n * j]; M[p + (size_t)n * j] = t; } double t = r[k]; r[k] = r[p]; r[p] = t; }
+        for (int i = k + 1; i < n; ++i) if (fabs(M[(size_t)i * n + k]) > fabs(M[(size_t)p * n + k])) p = i;
+        if (p != k) { for (int j = 0; j < n; ++j) { double t = M[(size_t)k * n + j]; M[(size_t)k * n + j] = M[(size_t)p * n + j]; M[(size_t)p * n + j] = t; } double t = r[k]; r[k] = r[p]; r[p] = t; }
         for (int i = k + 1; i < n; ++i) {
-            double f = M[i + (size_t)n * k] / M[k + (size_t)n * k];
-            for (int j = k; j < n; ++j) M[i + (size_t)n * j] -= f * M[k + (size_t)n * j];
+            double f = M[(size_t)i * n + k] / M[(size_t)k * n + k];
+            if (f == 0.0) continue;
+            for (int j = k; j < n; ++j) M[(size_t)i * n + j] -= f * M[(size_t)k * n + j];
             r[i] -= f * r[k];
         }
     }
-    for (int i = n - 1; i >= 0; --i) { double s = r[i]; for (int j = i + 1; j < n; ++j) s -= M[i + (size_t)n * j] * x[j]; x[i] = s / M[i + (size_t)n * i]; }
+    for (int i = n - 1; i >= 0; --i) { double s = r[i]; for (int j = i + 1; j < n; ++j) s -= M[(size_t)i * n + j] * x[j]; x[i] = s / M[(size_t)i * n + i]; }
     free(M); free(r);
 }
 static double relerr(int n, const double *x, const double *ref) {
@@ -156,7 +157,7 @@ int main(void) {
 
     /* ---------------- A \ b for one larger system: chunked path (Base.:\) ---------------- */
     {
-        const int N = 3000;
+        const int N = 1500;
         AB L = ab_random(N, 1, 0, 1);
         double *DL = malloc(sizeof(double) * N * N), *bl = malloc(8 * N), *xl = malloc(8 * N), *xr = malloc(8 * N);
         ab_dense(&L, N, DL);
