@@ -222,6 +222,24 @@ def bps_qr(B, U, V, W, S, l, m):
     return Bf, Vf, Wf, Sf, tau
 
 
+def bps_qr_steps(B, U, V, W, S, l, m, nsteps):
+    """The sweep of ``bps_qr`` stopped after ``nsteps`` columns -> (Bf, Vf, Wf, Sf, tau, state) with ``state`` = dict of the perturbed-factor
+    matrices Q (r,p), K (r,r), E (r,lm), X (lx,p), Y (lx,r), Z (lx,lm)  [semiseparableqr.jl:14-48; invariant :1-12, test_getindex.jl:32-38]."""
+    n = B.shape[0]; r = U.shape[0]; p = W.shape[0]
+    lm, lx = min(l + m, n), min(l, n)
+    Bf = np.zeros((n, 2 * l + m + 1)); Vf = np.zeros((r, n)); Wf = np.zeros((p + r, n)); Sf = np.zeros((p + r, n)); tau = np.zeros(n)
+    sizes = [(r, p), (r, r), (r, lm), (lx, p), (lx, r), (lx, lm)]
+    st = np.zeros(sum(a * b for a, b in sizes) + 1)
+    rc = lib().ssm_oracle_bps_qr_steps(n, l, m, r, p, _p(_f64(B)), _p(_f64(U)), _p(_f64(V)), _p(_f64(W)), _p(_f64(S)), int(nsteps),
+                                       _p(Bf), _p(Vf), _p(Wf), _p(Sf), _p(tau), _p(st))
+    assert rc == 0
+    out, o = {}, 0
+    for name, (a, b) in zip("QKEXYZ", sizes):
+        out[name] = st[o:o + a * b].reshape((b, a)).T.copy()      # column-major (a x b)
+        o += a * b
+    return Bf, Vf, Wf, Sf, tau, out
+
+
 def bps_qr_batch(B, U, V, W, S, l, m):
     nb, n, _ = B.shape; r = U.shape[1]; p = W.shape[1]
     Bf = np.zeros((nb, n, 2 * l + m + 1)); Vf = np.zeros((nb, r, n)); Wf = np.zeros((nb, p + r, n)); Sf = np.zeros((nb, p + r, n)); tau = np.zeros((nb, n))

@@ -112,8 +112,23 @@ static void fast_UtA(const bps_t *A, int j, double *out) {
  * Inputs (not mutated): B (l+m+1) x n, U,V n x r, W,S n x p.
  * Outputs: Bf (2l+m+1) x n band storage with bandwidths (l, l+m); Vf n x r; Wf, Sf n x (p+r); tau n.  U unchanged.
  * ------------------------------------------------------------------------------------------------------- */
+static int bps_qr_core(int n, int l, int m, int r, int p, const double *B, const double *U, const double *V, const double *W,
+                       const double *S, double *Bf, double *Vf, double *Wf, double *Sf, double *tau, int nsteps, double *state);
 int ssm_oracle_bps_qr(int n, int l, int m, int r, int p, const double *B, const double *U, const double *V, const double *W,
                       const double *S, double *Bf, double *Vf, double *Wf, double *Sf, double *tau) {
+    return bps_qr_core(n, l, m, r, p, B, U, V, W, S, Bf, Vf, Wf, Sf, tau, n - 1, NULL);
+}
+/* The sweep stopped after `nsteps` columns, with the state of BandedPlusSemiseparableQRPerturbedFactors (src/semiseparableqr.jl:14-48) written to
+ * `state` = Q (r x p) | K (r x r) | Es (r x lm) | Xs (lx x p) | Ys (lx x r) | Zs (lx x lm), each column-major, lm = min(l+m, n), lx = min(l, n).
+ * For tests of the invariant the reference states at :1-12 and checks in test/test_getindex.jl:32-38: after j steps the trailing block is
+ *   A0 + U Q Sp' + U K U'A0 + U [Es 0] + [Xs;0] Sp' + [Ys;0] U'A0 + [Zs 0;0 0]. */
+int ssm_oracle_bps_qr_steps(int n, int l, int m, int r, int p, const double *B, const double *U, const double *V, const double *W,
+                            const double *S, int nsteps, double *Bf, double *Vf, double *Wf, double *Sf, double *tau, double *state) {
+    if (nsteps < 0 || nsteps > n - 1 || !state) return -1;
+    return bps_qr_core(n, l, m, r, p, B, U, V, W, S, Bf, Vf, Wf, Sf, tau, nsteps, state);
+}
+static int bps_qr_core(int n, int l, int m, int r, int p, const double *B, const double *U, const double *V, const double *W,
+                       const double *S, double *Bf, double *Vf, double *Wf, double *Sf, double *tau, int nsteps, double *state) {
     if (n < 1 || l < 0 || m < 0 || r < 0 || p < 0 || r > MAXR || p > MAXR || 2 * l + m + 1 > MAXB) return -1;
     const int pr = p + r, lm = imin(l + m, n), lx = imin(l, n);
     /* ---- constructor :36-48 ---- */
@@ -160,7 +175,7 @@ int ssm_oracle_bps_qr(int n, int l, int m, int r, int p, const double *B, const 
         }
     }
     /* ---- n-1 Householder steps :117-121, onestep_qr! :133-152 ---- */
-    for (int j = 0; j <= n - 2; ++j) {
+    for (int j = 0; j < nsteps; ++j) {
         const int q1 = j + 1;                         /* current column / row */
         const double *G = UTU(j + 2);
         /* == compute_Householder_vector :315-364 == */
@@ -401,8 +416,17 @@ int ssm_oracle_bps_qr(int n, int l, int m, int r, int p, const double *B, const 
         for (int s = 1; s <= lb; ++s) *Bp(&A, j + 1 + s, q1) = b[s - 1];
         for (int a = 1; a <= r; ++a) Vg(&A, q1, a) = kb[a - 1];
     }
+    if (state) {
+        double *o = state;
+        memcpy(o, Q, sizeof(double) * r * p); o += r * p;
+        memcpy(o, K, sizeof(double) * r * r); o += r * r;
+        memcpy(o, E, sizeof(double) * r * lm); o += r * lm;
+        memcpy(o, X, sizeof(double) * lx * p); o += lx * p;
+        memcpy(o, Y, sizeof(double) * lx * r); o += lx * r;
+        memcpy(o, Z, sizeof(double) * lx * lm);
+    }
     /* ---- A.B[n,n] = A[n,n] :123, through getindex :50-102 with j = n-1 (k == i branch :84-91) ---- */
-    if (n >= 1) {
+    if (nsteps == n - 1) {
         const int j = n - 1;
         bps_t Acur = { n, l, l + m, r, pr, Bf, (double *)U, Vf, Wf, Sf };
         double AtUn[MAXR];

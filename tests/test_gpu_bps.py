@@ -177,3 +177,66 @@ def test_random_shapes_match_oracle(bps, ctx):
         x = F.R.solve(F.Q.T.lmul(b))
         ox = oracle.bps_solve_batch(oB, U, oV, oW, oS, ot, b, l, l + m)
         assert max(relerr(x[s], ox[s]) for s in range(nb)) <= 1e-12, tag
+
+
+def _gpu_dense_factors(bps, ctx, B, U, V, W, S, l, m):
+    A = bps.BandedPlusSemiseparableMatrix(B, (U, V), (W, S), (l, m), ctx=ctx)
+    F = bps.qr(A)
+    gB, gU, gV, gW, gS, gt = F.get()
+    return A, F, oracle.bps_factors_dense(gB, gU, gV, gW, gS, l, l + m), gt
+
+
+def test_gpu_factors_against_high_precision_householder(bps, ctx):
+    """The device factors against references that owe nothing to the oracle: dense Householder QR in 50-digit arithmetic at the reference's test
+    shape (test_qr.jl:6-12) and in extended precision at n = 256 on randn data (tests/golden/make_bps_golden.py)."""
+    import json
+    from pathlib import Path
+    gold = Path(__file__).parent / "golden"
+    g = json.loads((gold / "bps_qr_mp_n20.json").read_text())
+    l, m = g["l"], g["m"]
+    B, U, V, W, S = (np.array(g[k]) for k in "BUVWS")
+    _, _, F, tau = _gpu_dense_factors(bps, ctx, B, U, V, W, S, l, m)
+    ref, t = np.array(g["factors"]), np.array(g["tau"])
+    cond = np.linalg.cond(oracle.bps_dense(B, U, V, W, S, l, m))
+    assert np.abs(F - ref).max() / np.abs(ref).max() <= 4e-15 * cond and np.abs(tau - t).max() <= 4e-15 * cond
+    g = np.load(gold / "bps_qr_ld_n256.npz")
+    n, l, m, r, p = (int(v) for v in g["shape"])
+    B, U, V, W, S, b = (g[k] for k in ("B", "U", "V", "W", "S", "b"))
+    Amat = oracle.bps_dense(B, U, V, W, S, l, m)
+    cond = np.linalg.cond(Amat)
+    A, Fq, F, tau = _gpu_dense_factors(bps, ctx, B, U, V, W, S, l, m)
+    err = np.abs(F - g["factors"]).max() / np.abs(g["factors"]).max()
+    assert err <= 1e-15 * cond and np.abs(tau - g["tau"]).max() <= 1e-15 * cond, (err, cond)
+    x = Fq.ldiv(b.copy())
+    assert relerr(x, np.linalg.solve(Amat, b)) <= 1e-15 * cond
+
+
+def test_randn_n4096_drift_scales_with_cond(bps, ctx, record_property):
+    """randn (ill-conditioned) BPS input at the config-3 size.  Device factors against the oracle and against LAPACK's dense QR, the
+    tolerance scaled by the measured condition number; the drift is recorded (printed with -rA / in the junit properties)."""
+    n, l, m, r, p, nb = 4096, 3, 3, 2, 2, 3
+    rng = np.random.default_rng(4096)
+    B, U, V, W, S, b = bps_randn(rng, n, l, m, r, p, nb)
+    A = bps.BandedPlusSemiseparableMatrix(B, (U, V), (W, S), (l, m), ctx=ctx)
+    F = bps.qr(A)
+    gB, gU, gV, gW, gS, gt = F.get()
+    x = F.ldiv(b.copy())
+    oB, oV, oW, oS, ot = oracle.bps_qr_batch(B, U, V, W, S, l, m)
+    ox = oracle.bps_solve_batch(oB, U, oV, oW, oS, ot, b, l, l + m)
+    s = 0
+    Amat = oracle.bps_dense(B[s], U[s], V[s], W[s], S[s], l, m)
+    cond = float(np.linalg.cond(Amat))
+    lap, tl = oracle.dense_qr_unblocked(Amat)
+    Fg = oracle.bps_factors_dense(gB[s], gU[s], gV[s], gW[s], gS[s], l, l + m)
+    Fo = oracle.bps_factors_dense(oB[s], U[s], oV[s], oW[s], oS[s], l, l + m)
+    d_gpu_lapack = float(np.abs(np.triu(Fg) - np.triu(lap)).max() / np.abs(lap).max())
+    d_oracle_lapack = float(np.abs(np.triu(Fo) - np.triu(lap)).max() / np.abs(lap).max())
+    d_gpu_oracle = float(max(np.abs(gB[k] - oB[k]).max() / np.abs(oB[k]).max() for k in range(nb)))
+    x0 = np.linalg.solve(Amat, b[s])
+    e_sol = float(relerr(x[s], x0)); e_sol_oracle = float(relerr(ox[s], x0))
+    for k, v in dict(cond=cond, gpu_vs_lapack=d_gpu_lapack, oracle_vs_lapack=d_oracle_lapack, gpu_vs_oracle=d_gpu_oracle, relerr_gpu=e_sol, relerr_oracle=e_sol_oracle).items():
+        record_property(k, v)
+    print(f"randn n=4096: cond {cond:.3e}; R factor drift vs LAPACK: gpu {d_gpu_lapack:.2e}, oracle {d_oracle_lapack:.2e}; gpu vs oracle {d_gpu_oracle:.2e}; "
+          f"solution relerr vs dense: gpu {e_sol:.2e}, oracle {e_sol_oracle:.2e}")
+    assert d_gpu_lapack <= 1e-14 * cond and d_gpu_oracle <= 1e-14 * cond
+    assert e_sol <= 1e-14 * cond and e_sol <= 10 * max(e_sol_oracle, 1e-15)
