@@ -182,7 +182,7 @@ def test_random_shapes_match_oracle(bps, ctx):
 def _gpu_dense_factors(bps, ctx, B, U, V, W, S, l, m):
     A = bps.BandedPlusSemiseparableMatrix(B, (U, V), (W, S), (l, m), ctx=ctx)
     F = bps.qr(A)
-    gB, gU, gV, gW, gS, gt = F.get()
+    gB, gU, gV, gW, gS, gt = (a[0] for a in F.get())           # a batch of one
     return A, F, oracle.bps_factors_dense(gB, gU, gV, gW, gS, l, l + m), gt
 
 
