@@ -89,6 +89,7 @@ constexpr int bps_nst(int l, int m, int look) { return l + m + 1 + look; }
 // shadow lanes 0-15 and do not store), both reading one shared window ring: the sweep is latency bound — a batch of 16,384 systems
 // is only 512 warps, fewer than the 592 warp schedulers of a B200 — so halving the systems per warp doubles the warps in flight at
 // the cost of idle lanes, not of HBM or TMA traffic.
+constexpr int BPS_LOOK_SMALL = 6;   // default look-ahead of the one-warp sweep at <= 4 tiles per SM (see qr_shape)
 constexpr int BPS_NST_SPLIT = 12;  // 46 KB per CTA: four CTAs (all 512 tiles of config 3) stay co-resident per SM
 template <int L, int M, int R, int P, int SPLIT, int LOOK = 1>
 __global__ void __launch_bounds__(32 * SPLIT) bps_qr_kernel(const double *REC, const double *GT, double *OUT, int n, int64_t np, int64_t npo) {
@@ -553,7 +554,20 @@ static int qr_shape(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
     } else {
         // one slot in flight keeps 7 CTAs per SM resident; a second one (6 CTAs per SM) removes most of the wait for the entering
         // row when the batch leaves room for it (config 3: 4.20 -> 3.87 ms; at 7 tiles per SM it would cost a second wave)
-        if (A->ntiles <= (int64_t)c->sm_count * 5) {
+        // pipeline_stages > 0 picks the look-ahead by hand (1, 2, 4 or 6 slots in flight): with one warp per scheduler the bytes in flight per SM
+        // are tiles/SM * look-ahead * 3.8 KB, and Little's law wants ~6.5 MB device-wide for the HBM rate
+        const int look = c->pipeline_stages > 0 ? c->pipeline_stages : (A->ntiles <= (int64_t)c->sm_count * 4 ? BPS_LOOK_SMALL : (A->ntiles <= (int64_t)c->sm_count * 5 ? 2 : 1));
+        if (look >= 6) {
+            const size_t smem = WindowRing<D::NFA, bps_nst(L, M, 6), 1>::smem_bytes();
+            auto kern = bps_qr_kernel<L, M, R, P, 1, 6>;
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+        } else if (look >= 4) {
+            const size_t smem = WindowRing<D::NFA, bps_nst(L, M, 4), 1>::smem_bytes();
+            auto kern = bps_qr_kernel<L, M, R, P, 1, 4>;
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)A->ntiles, 32, smem, c->stream>>>(A->REC->p, F->GT->p, F->OUT->p, A->n, A->np, F->npo);
+        } else if (look >= 2) {
             const size_t smem = WindowRing<D::NFA, bps_nst(L, M, 2), 1>::smem_bytes();
             auto kern = bps_qr_kernel<L, M, R, P, 1, 2>;
             SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
