@@ -319,9 +319,9 @@ static int pick_stages(const ssm_ctx *c, size_t stage_bytes, int64_t ntiles) {
     return s;
 }
 
+// shared-memory attributes of a ring kernel before its launch
 template <class K>
-static int launch1(ssm_ctx *c, K kern, int64_t ntiles, size_t smem, const char *name) {
-    (void)name;
+static int launch1(ssm_ctx *, K kern, int64_t, size_t smem, const char *) {
     if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (smem > 0) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;

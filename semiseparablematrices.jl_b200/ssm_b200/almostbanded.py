@@ -419,7 +419,7 @@ class AlmostBandedQR:
             raise DimensionMismatch("Data and fill must be compatible size")
         self = cls.__new__(cls)
         self.ctx = ctx or default_context()
-        self.n, self.l, self.u, self.r, self.nb, self.single, self._A = n, l, u, r, nb, single, None
+        self.n, self.l, self.u, self.r, self.nb, self.single, self._A, self._V = n, l, u, r, nb, single, None, V
         self.ncols = n - 1 if ncols is None else int(ncols)
         self._h = c_vp()
         P = lambda a: c_vp(a.ctypes.data)
@@ -455,7 +455,7 @@ class AlmostBandedQR:
     def factors(self):
         """(bands (nb,n,2l+u+1) with bandwidths (l, l+u), U (nb,r,n), V (nb,n,r))"""
         F, U, _ = self.get()
-        return F, U, self._A.fillpart()[1]
+        return F, U, (self._A.fillpart()[1] if self._A is not None else self._V)
 
     @property
     def tau(self):

@@ -22,6 +22,24 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1 and out["cpu_baseline"]["value"] == out["value"]
     assert out["e2e"] == {"value": out["value"], "unit": "systems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in out["config"] and "model" not in out["config"]
+    # the product arm prints the very same `config` object (the driver compares them) and the arm honours --steps / --warmup as given
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    assert out["config"] == mod.workload_config(1)
+    assert out["steps"] == 1 and out["warmup"] == 0
+
+
+def test_reference_arm_uses_all_cores_under_a_launcher_that_exports_one_thread():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every host core (round-1 finding)."""
+    import os
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = json.loads([ln for ln in p.stdout.splitlines() if ln.strip().startswith("{")][0])
+    cores = len(os.sched_getaffinity(0))
+    assert out["cpu_baseline"]["cores"] == cores, (out["cpu_baseline"]["cores"], cores)
 
 
 def test_product_arm_refuses_to_run_without_a_gpu():
