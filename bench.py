@@ -519,22 +519,26 @@ def leg_c5(args, job, dev, peak, with_cpu):
     return out
 
 
-def copy_ceiling(pins, xout, job, reps=3):
-    """What the box gives for this step's transfers with no kernel in the way: every rank copies its pinned inputs H2D and an
-    x-sized buffer D2H on two streams at the same time.  Returns aggregate GB/s over all ranks (H2D, D2H)."""
+def copy_ceiling(pins, xout, job, reps=3, chunk=8192, nstreams=3):
+    """What the box gives for this step's transfers with no kernel in the way: every rank moves the same bytes as one e2e step in the same
+    pattern — chunks of `chunk` systems round-robin over `nstreams` streams, the four input slices H2D then the x slice D2H per chunk (what
+    ssm_ab_solve_host's pipeline does between its kernels).  Returns aggregate GB/s over all ranks (H2D, D2H), best of `reps`."""
     import torch
-    dev_in = [torch.empty(p.shape, dtype=p.dtype, device="cuda") for p in pins]
-    dev_out = torch.empty(xout.shape, dtype=xout.dtype, device="cuda")
-    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    nb = xout.shape[0]
+    streams = [torch.cuda.Stream() for _ in range(nstreams)]
+    dev_in = [[torch.empty((chunk,) + tuple(p.shape[1:]), dtype=p.dtype, device="cuda") for p in pins] for _ in range(nstreams)]
+    dev_out = [torch.empty((chunk,) + tuple(xout.shape[1:]), dtype=xout.dtype, device="cuda") for _ in range(nstreams)]
     best = float("inf")
     for _ in range(reps):
         torch.cuda.synchronize(); job.barrier()
         t0 = time.perf_counter()
-        with torch.cuda.stream(s1):
-            for p, d in zip(pins, dev_in):
-                d.copy_(p, non_blocking=True)
-        with torch.cuda.stream(s2):
-            xout.copy_(dev_out, non_blocking=True)
+        for k, s0 in enumerate(range(0, nb, chunk)):
+            cnt = min(chunk, nb - s0)
+            sl = k % nstreams
+            with torch.cuda.stream(streams[sl]):
+                for p, d in zip(pins, dev_in[sl]):
+                    d[:cnt].copy_(p[s0:s0 + cnt], non_blocking=True)
+                xout[s0:s0 + cnt].copy_(dev_out[sl][:cnt], non_blocking=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         job.barrier()
@@ -715,7 +719,7 @@ def main():
                "matches_device_path": (bool(np.array_equal(xout.numpy(), x_host)) if (x_host is not None and nb_e == nb) else None)}
         ceil_h2d, ceil_d2h = copy_ceiling(pins, xout, job)
         e2e["copy_ceiling"] = {"h2d_GBps_aggregate": ceil_h2d, "d2h_GBps_aggregate": ceil_d2h,
-                               "how": "every rank copies the same pinned inputs H2D and an x-sized buffer D2H concurrently, no kernels; best of 3, max over ranks",
+                               "how": "every rank moves one step's bytes in the pipeline's own pattern (8192-system chunks round-robin over 3 streams, inputs H2D then x D2H), no kernels; best of 3, max over ranks",
                                "e2e_frac_of_ceiling": (world * h2d / dt / 1e9) / ceil_h2d}
         # the single-process sharder north_star describes (one process, one host thread + context per GPU; the host buffers are the gather)
         barrier()
