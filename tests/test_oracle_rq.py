@@ -49,3 +49,24 @@ def test_rq_oracle_refuses_unsymmetric_generators():
     Sf[0, 3] += 1.0
     with pytest.raises(AssertionError):
         rq_oracle.rq_mul(Bf, U, Vf, Wf, Sf, tau, 2, 4)
+
+
+def test_rq_steps_are_similarity_transforms():
+    """Independent of the QR oracle's factors: R*Q = Q'AQ, so three steps of the iteration A -> qr -> R*Q keep the spectrum of the symmetric
+    matrix (LAPACK eigvalsh of the dense matrices), the trace and the Frobenius norm, and the result stays symmetric."""
+    rng = np.random.default_rng(77)
+    n, l, r = 96, 3, 2
+    B, U, V, W, S = sym_bps(rng, n, l, r)
+    A0 = oracle.bps_dense(B, U, V, W, S, l, l)
+    ev0 = np.linalg.eigvalsh((A0 + A0.T) / 2)
+    assert np.abs(A0 - A0.T).max() == 0.0
+    for step in range(3):
+        Bf, Vf, Wf, Sf, tau = oracle.bps_qr(B, U, V, W, S, l, l)
+        B, Un, Vn = rq_oracle.rq_mul(Bf, U, Vf, Wf, Sf, tau, l, 2 * l)
+        U, V, W, S = Un, Vn, Vn.copy(), Un.copy()
+        A = rq_oracle.rq_dense(B, U, V, l)
+        assert np.abs(A - A.T).max() <= 1e-13 * np.abs(A).max()
+        ev = np.linalg.eigvalsh((A + A.T) / 2)
+        assert np.abs(ev - ev0).max() <= 1e-12 * np.abs(ev0).max(), (step, np.abs(ev - ev0).max())
+        assert abs(np.trace(A) - np.trace(A0)) <= 1e-12 * np.abs(ev0).sum()
+        assert abs(np.linalg.norm(A) - np.linalg.norm(A0)) <= 1e-12 * np.linalg.norm(A0)
