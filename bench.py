@@ -225,11 +225,14 @@ def run_reference(args, rank):
 # =================================================================================================================
 # GPU helpers
 # =================================================================================================================
-def timeit(fn, steps, stream, warm=3):
+def timeit(fn, steps, stream, warm=3, warm_seconds=0.25):
+    """mean device time of `steps` calls (CUDA events on the launching stream) after at least `warm` calls AND `warm_seconds` of work: a leg
+    that follows a CPU phase (oracle baseline, parity sample) finds the GPU at idle clocks, and three short calls do not bring them back."""
     import torch
-    for _ in range(warm):
-        fn()
-    torch.cuda.synchronize()
+    t0 = time.perf_counter(); k = 0
+    while k < warm or time.perf_counter() - t0 < warm_seconds:
+        fn(); k += 1
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
@@ -258,7 +261,10 @@ def timeit_streams(fns, streams, steps, warm=3):
         stop.record(main)
         torch.cuda.synchronize()
         return start.elapsed_time(stop) / k
+    t0 = time.perf_counter()
     run(warm)
+    while time.perf_counter() - t0 < 0.25:          # idle clocks after a CPU phase: see timeit
+        run(1)
     return run(steps)
 
 
