@@ -268,6 +268,14 @@ def timeit_streams(fns, streams, steps, warm=3):
     return run(steps)
 
 
+def timed_leg(fn, steps, stream, gpu_index):
+    """timeit + the SM clock / throttle reasons sampled while it ran (each leg reports its own `clocks`)"""
+    sampler = ClockSampler(gpu_index)
+    sampler.start()
+    t = timeit(fn, steps, stream)
+    return t, sampler.stop()
+
+
 def release():
     import torch
     import ssm_b200 as ssm
@@ -293,13 +301,13 @@ def leg_c3(args, ctx, stream, peak, with_cpu):
     l0 = ctx.launches
     F.refactor(A)
     launches_per_qr = ctx.launches - l0
-    t_qr = timeit(lambda: F.refactor(A), args.steps, stream)
+    t_qr, clk = timed_leg(lambda: F.refactor(A), args.steps, stream, args.gpu_index)
     t_sv = timeit(lambda: F.solve(b, out=x), args.steps, stream)
     rr = A.residual(x, b)
     qb, sb = bps_bytes(n, l, m, r, p)
     out = {"workload": f"BASELINE.json configs[2]: BandedPlusSemiseparableMatrix qr + solve fp64, n={n}, l=m={l}, r=p={r}, {nb} systems",
            "value": nb / (t_qr * 1e-3), "unit": "systems/s (qr)", "qr_ms": t_qr, "solve_ms": t_sv, "steps": args.steps,
-           "qr_plus_solve_systems_per_s": nb / ((t_qr + t_sv) * 1e-3), "launches_per_qr": int(launches_per_qr),
+           "qr_plus_solve_systems_per_s": nb / ((t_qr + t_sv) * 1e-3), "launches_per_qr": int(launches_per_qr), "clocks": clk,
            "roofline": {"bound": "hbm", "kernel": "bps_qr_kernel (K6) incl. its reduction pre-pass", "achieved": qb * nb / t_qr / 1e6, "peak": peak,
                         "unit": "GB/s", "frac": qb * nb / t_qr / 1e6 / peak, "traffic": traffic_of("bps_qr_dram_bytes_per_qr"),
                         "algorithmic_bytes_per_launch": qb * nb,
@@ -345,14 +353,14 @@ def leg_c4(args, ctx, stream, peak, with_cpu):
     l0 = ctx.launches
     A.solve(b, out=x, sync=True)
     launches = ctx.launches - l0
-    t = timeit(lambda: A.solve(b, out=x, sync=False), args.steps, stream)
+    t, clk = timed_leg(lambda: A.solve(b, out=x, sync=False), args.steps, stream, args.gpu_index)
     torch.cuda.synchronize()
     rr = A.residual(x, b)
     fused = ab_bytes(n, l, u, r)[2]
     qrldiv = sum(ab_bytes(n, l, u, r)[:2])
     out = {"workload": f"BASELINE.json configs[3]: one AlmostBandedMatrix system A \\ b fp64, n={n}, l=u={l}, r={r}, chunked n-axis sweep, 1 GPU",
            "value": 1e3 / t, "unit": "systems/s", "ms": t, "columns_per_s": n / (t * 1e-3), "chunks": A.chunks, "steps": args.steps,
-           "launches_per_solve": int(launches),
+           "launches_per_solve": int(launches), "clocks": clk,
            "roofline": {"bound": "hbm", "kernel": "abc_* (K10: chunk QR + separator tree + back-substitution)", "achieved": fused / t / 1e6,
                         "peak": peak, "unit": "GB/s", "frac": fused / t / 1e6 / peak, "traffic": traffic_of("abc_solve_dram_bytes_per_solve"),
                         "algorithmic_bytes_per_launch": fused, "byte_count": "fused A\\b, 8n(l+u+2r+3) (no factor output)",
@@ -596,6 +604,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    args.gpu_index = physical_gpu_index(local_rank)
     from ssm_b200 import sharder
     job = sharder.Job(backend="nccl", device=torch.device("cuda", local_rank))   # barrier + max-over-ranks only: no data-path collective
     barrier = job.barrier
