@@ -759,15 +759,29 @@ def main():
     # ---- the other BASELINE.json configs (bounded legs) ------------------------------------------------------------------
     del A, b, x, F
     release()
+    def guarded(name, fn, collective=False):
+        """a leg that fails must not take the headline line with it: its entry becomes {"error": ...}.  Legs every rank takes part in
+        (barriers inside) are not guarded against rank-local failures — a rank that dropped out would hang the others."""
+        try:
+            configs[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            if collective and world > 1:
+                raise
+            configs[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+            try:
+                release()
+            except Exception:
+                pass
+
     if world == 1:
         if "c3" in legs:
-            configs["c3"] = leg_c3(args, ctx, stream, peak, with_cpu)
+            guarded("c3", lambda: leg_c3(args, ctx, stream, peak, with_cpu))
         if "c4" in legs:
-            configs["c4"] = leg_c4(args, ctx, stream, peak, with_cpu)
+            guarded("c4", lambda: leg_c4(args, ctx, stream, peak, with_cpu))
         if "c1" in legs:
-            configs["c1"] = leg_c1(args, ctx, stream, with_cpu)
+            guarded("c1", lambda: leg_c1(args, ctx, stream, with_cpu))
     if "c5" in legs:
-        configs["c5"] = leg_c5(args, job, local_rank, peak, with_cpu)
+        guarded("c5", lambda: leg_c5(args, job, local_rank, peak, with_cpu), collective=True)
 
     if rank == 0:
         config = workload_config(world)
