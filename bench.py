@@ -472,21 +472,33 @@ def leg_c5(args, job, dev, peak, with_cpu):
            "a rank's six shards run concurrently, one context/stream each", "steps": steps}
     whole = [(gi, 0, nb) for gi, (_, nb) in enumerate(C5_GROUPS)]
     ms_1gpu, mode_1gpu = None, None
+    rr1 = None
     if job.rank == 0:
-        free, _ = torch.cuda.mem_get_info()
-        if need_bytes(whole) + (3 << 30) < free:
-            objs, streams = build(whole)
-            ms_1gpu, mode_1gpu = run(objs, streams), "six groups concurrently (one stream each)"
-            rr1 = max(float(A.residual(x, b).max()) for A, b, x, F, _, _ in objs)
-            del objs, streams
-        else:                                           # not enough HBM for all six at once: group after group
-            ms_1gpu, mode_1gpu, rr1 = 0.0, "six groups back to back (HBM too small to hold them together)", 0.0
-            for piece in whole:
-                objs, streams = build([piece])
-                ms_1gpu += run(objs, streams)
-                rr1 = max(rr1, float(objs[0][0].residual(objs[0][2], objs[0][1]).max()))
-                del objs, streams
+        # rank 0 must reach the barrier below whatever happens here (the other ranks are waiting in it)
+        try:
+            free, _ = torch.cuda.mem_get_info()
+            objs = streams = None
+            if need_bytes(whole) + (3 << 30) < free:
+                try:
+                    objs, streams = build(whole)
+                    ms_1gpu, mode_1gpu = run(objs, streams), "six groups concurrently (one stream each)"
+                    rr1 = max(float(A.residual(x, b).max()) for A, b, x, F, _, _ in objs)
+                except Exception:                           # e.g. fragmentation: fall through to group after group
+                    ms_1gpu = None
+                objs = streams = None
                 release()
+            if ms_1gpu is None:                             # not enough HBM for all six at once: group after group
+                ms_1gpu, mode_1gpu, rr1 = 0.0, "six groups back to back (HBM too small to hold them together)", 0.0
+                for piece in whole:
+                    objs, streams = build([piece])
+                    ms_1gpu += run(objs, streams)
+                    rr1 = max(rr1, float(objs[0][0].residual(objs[0][2], objs[0][1]).max()))
+                    objs = streams = None
+                    release()
+        except Exception as e:  # noqa: BLE001
+            ms_1gpu, mode_1gpu = None, f"failed: {type(e).__name__}: {e}"[:200]
+            if job.world == 1:
+                raise
         release()
     job.barrier()
     if job.world == 1:
