@@ -88,9 +88,23 @@ mutable struct Handle
     destroy::Symbol
     function Handle(p, destroy)
         h = new(p, destroy)
-        finalizer(x -> x.p != C_NULL && _destroy(x), h)
+        finalizer(_finalize_handle, h)
         h
     end
+end
+# Finalizers run on whatever thread the GC runs on: take the device lock without blocking, or try again at the next collection
+function _finalize_handle(h)
+    h.p == C_NULL && return nothing
+    if trylock(DEVLOCK)
+        try
+            _destroy(h)
+        finally
+            unlock(DEVLOCK)
+        end
+    else
+        finalizer(_finalize_handle, h)
+    end
+    nothing
 end
 function _destroy(h::Handle)
     if h.destroy === :ab;        ccall((:ssm_ab_destroy, libssm), Cint, (Ptr{Cvoid},), h.p)
