@@ -311,9 +311,16 @@ static int pick_stages(const ssm_ctx *c, size_t stage_bytes, int64_t ntiles) {
     // deeper when the batch is small (Little: ~6.5 MB must be in flight device-wide to reach the HBM rate).
     int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
     if (per_sm < 1) per_sm = 1;
+    const bool waves = per_sm > 14;          // more tiles than an SM holds at once: the deep ring also caps residency at ~14 CTAs, which measured best there
     if (per_sm > 14) per_sm = 14;
-    const size_t budget = (size_t)(210 * 1024) / (size_t)per_sm;
-    int s = (int)(budget / (stage_bytes + 8));
+    size_t budget = (size_t)(210 * 1024) / (size_t)per_sm;
+    // ... but no deeper than the HBM rate needs: ~6.5 MB in flight device-wide is 44 KB / per_sm for each warp; 64 KB / per_sm leaves a margin.
+    // Measured at config 2 (14 warps per SM): K3 with 2 stages instead of 5 and K2 with 4 instead of 14: ldiv! 1.349 -> 1.272 ms
+    // (tools/scan_ldiv_stages.sh) — a ring that takes all the shared memory there is only costs L1 and re-arming work.  With more than 14 tiles
+    // per SM the shallow ring lets ~28 CTAs in at once and ldiv! gets slower (131,072 systems: 2.51 -> 2.93 ms), so the deep ring stays there.
+    const size_t want = (size_t)(64 * 1024) / (size_t)per_sm;
+    if (budget > want && !waves) budget = want;
+    int s = (int)((budget + (waves ? 0 : stage_bytes / 2)) / (stage_bytes + 8));
     if (s < 2) s = 2;
     if (s > 48) s = 48;
     return s;
@@ -431,7 +438,7 @@ static int qt_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
     }
     if (variant == 2) {
         using LD = RingLoader<L + 1, 1, 0, +1>;
-        const int ns = pick_stages(c, LD::STAGE_BYTES, ntiles);
+        const int ns = c->qt_stages > 0 ? c->qt_stages : pick_stages(c, LD::STAGE_BYTES, ntiles);
         const size_t smem = LD::smem_bytes(ns);
         auto kern = ab_qt_kernel<L, RingLoaderD>;
         SSM_TRY(launch1(c, kern, ntiles, smem, "ab_qt_ring"));
@@ -464,7 +471,7 @@ static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
     }
     if (variant == 2) {
         using LD = RingLoader<D::NFR, R, 1, -1>;
-        const int ns = pick_stages(c, LD::STAGE_BYTES, ntiles);
+        const int ns = c->bs_stages > 0 ? c->bs_stages : pick_stages(c, LD::STAGE_BYTES, ntiles);
         const size_t smem = LD::smem_bytes(ns);
         auto kern = ab_backsolve_kernel<L, U, R, RingLoaderD>;
         SSM_TRY(launch1(c, kern, ntiles, smem, "ab_bs_ring"));

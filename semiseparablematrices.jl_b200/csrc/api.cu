@@ -246,6 +246,8 @@ int ssm_ctx_set_option(ssm_ctx *c, const char *key, int value) {
     SSM_CHECK_ARG(c && key, "null argument");
     if (!strcmp(key, "ab_variant")) c->ab_variant = value;
     else if (!strcmp(key, "pipeline_stages")) c->pipeline_stages = value;
+    else if (!strcmp(key, "qt_stages")) c->qt_stages = value;
+    else if (!strcmp(key, "bs_stages")) c->bs_stages = value;
     else if (!strcmp(key, "group_max_per_sm")) c->group_max_per_sm = value;
     else if (!strcmp(key, "group_bytes")) c->group_bytes = value;
     else if (!strcmp(key, "group_smem_kb")) c->group_smem_kb = value;

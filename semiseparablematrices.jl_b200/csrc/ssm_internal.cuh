@@ -84,6 +84,7 @@ struct ssm_ctx {
     int          group_bytes = 32768;  // GroupRing: target size of one bulk-copy group
     int          group_max_per_sm = 9; // auto: batches of at most this many tiles per SM run the GroupRing kernels
     int          pipeline_stages = 0;  // 0 = kernel default
+    int          qt_stages = 0, bs_stages = 0;   // ring depth of K2 / K3 alone (0 = pick_stages)
     int          abc_tiled_min_chunks = 12288;  // chunked path (K10): from this many chunks on stage 3 runs one lane per chunk over tiled records
     int          sm_count = 148;
     int64_t      launches = 0;
