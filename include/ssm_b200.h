@@ -24,7 +24,10 @@
  *
  * Threading: handles are not shared-state; calls on different ssm_ctx from different host threads are
  * safe.  Every call enqueues on its ctx's stream and returns after the work is ENQUEUED unless it copies
- * to a host pointer (then it synchronises); use ssm_ctx_sync() to wait.
+ * to a host pointer (then it synchronises); use ssm_ctx_sync() to wait.  An entry point given objects of
+ * ANOTHER context of the same device (a vector of ctx 2 solved with a factorisation of ctx 1) orders the
+ * two streams on the device: its own stream first waits for the owner's pending work, and the owner's
+ * stream then waits for the call's work, so the owner's later calls see the result without a host sync.
  */
 #ifndef SSM_B200_H
 #define SSM_B200_H

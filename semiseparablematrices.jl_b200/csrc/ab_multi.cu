@@ -234,6 +234,7 @@ int ssm_abqr_ldiv_mat(const ssm_abqr *F, ssm_mat *B) {
     if (F->ncols < F->n - 1) { set_error("ssm_abqr_ldiv_mat: the factor object holds %d of %d reflectors: finish it first (ssm_abqr_continue)", F->ncols, F->n - 1); return SSM_E_STATE; }
     ssm_ctx *c = F->ctx;
     uses(B->d, c); uses(F->V, c); uses(F->RU, c); uses(F->QT, c);
+    CrossOrder co(c, {B->ctx});
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     int rc = SSM_E_UNSUPPORTED;
     if (c->ab_variant != 9) {

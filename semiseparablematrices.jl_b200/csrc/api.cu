@@ -228,6 +228,7 @@ int ssm_ctx_destroy(ssm_ctx *c) {
     if (c->stg.dev) { cudaFree(c->stg.dev); c->stg.dev = nullptr; c->stg.dev_count = 0; }
     if (c->stg.pin) { cudaFreeHost(c->stg.pin); c->stg.pin = nullptr; c->stg.pin_count = 0; }
     for (auto &s : c->aux) if (s) { cudaStreamDestroy(s); s = nullptr; }
+    if (c->ev) { cudaEventDestroy(c->ev); c->ev = nullptr; }
     if (c->tok) c->tok->alive.store(false);          // blocks that outlive the context must not query its stream any more
     if (c->own_stream) cudaStreamDestroy(c->stream);
     // objects still alive (destroyed out of order by the host runtime): the struct stays until the last of them is gone
@@ -554,6 +555,7 @@ int ssm_ab_qr_cols(const ssm_ab *A, int ncols, ssm_abqr **out) {
     ssm_ctx *c = A->ctx;
     DeviceGuard g(c->device);
     ssm_abqr *F = *out;
+    CrossOrder co(c, {F ? F->ctx : nullptr});
     if (F) {   // refactor into an existing object of the same shape (steady-state benchmarking, no allocation)
         if (F->n != A->n || F->l != A->l || F->u != A->u || F->r != A->r || F->nb != A->nb) { set_error("ssm_ab_qr: factor object has a different shape"); return SSM_E_SHAPE; }
         F->V = A->V;
@@ -580,6 +582,7 @@ int ssm_abqr_continue(ssm_abqr *F, const ssm_ab *A, int ncols) {
     ssm_ctx *c = F->ctx;
     uses(A->AU, c); uses(A->V, c);
     DeviceGuard g(c->device);
+    CrossOrder co(c, {A->ctx});
     AbArgs a{A->AU->p, A->V->p, F->RU->p, F->QT->p, nullptr, nullptr, A->n, A->np, ncols};
     SSM_TRY(F->ncols == 0 ? launch_ab_qr(c, A->l, A->u, A->r, A->ntiles, a, false, true) : launch_ab_qr_continue(c, A->l, A->u, A->r, A->ntiles, a, F->ncols));
     F->V = A->V;
@@ -605,6 +608,7 @@ int ssm_abqr_resize(ssm_abqr *F, const ssm_ab *A) {
     uses(A->AU, c); uses(A->V, c);
     if (A->n == F->n) { F->V = A->V; return 0; }
     DeviceGuard g(c->device);
+    CrossOrder co(c, {A->ctx});
     const int n0 = F->n, k0 = F->ncols;
     DevBufPtr RU, QT;
     SSM_TRY(dev_alloc(c, (size_t)(A->ntiles * A->np * (F->l + F->u + 1 + F->r) * 32), true, RU));
@@ -706,6 +710,7 @@ int ssm_abqr_lmul_qt(const ssm_abqr *F, ssm_vec *b) {
     if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
     abqr_uses(F);                  // a partial factorisation is fine here: the reflectors not yet formed have tau = 0
     DeviceGuard g(F->ctx->device);
+    CrossOrder co(F->ctx, {b->ctx});
     AbSolveArgs a{F->RU->p, F->QT->p, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
     return launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, a, true);
 }
@@ -715,6 +720,7 @@ int ssm_abqr_lmul_q(const ssm_abqr *F, ssm_vec *b) {
     if (!F->QT) { set_error("factor object was created without reflectors"); return SSM_E_STATE; }
     abqr_uses(F);                  // a partial factorisation is fine here: the reflectors not yet formed have tau = 0
     DeviceGuard g(F->ctx->device);
+    CrossOrder co(F->ctx, {b->ctx});
     AbSolveArgs a{F->RU->p, F->QT->p, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
     return launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, a, false);
 }
@@ -724,6 +730,7 @@ int ssm_abqr_upper_ldiv(const ssm_abqr *F, ssm_vec *b) {
     SSM_TRY(abqr_complete(__func__, F));
     abqr_uses(F);
     DeviceGuard g(F->ctx->device);
+    CrossOrder co(F->ctx, {b->ctx});
     AbSolveArgs a{F->RU->p, F->QT ? F->QT->p : nullptr, F->V->p, b->d->p, b->d->p, F->n, F->np, 0};
     return launch_ab_backsolve(F->ctx, F->l, F->u, F->r, F->ntiles, a);
 }
@@ -735,6 +742,7 @@ int ssm_abqr_solve(const ssm_abqr *F, const ssm_vec *b, ssm_vec *x) {
     SSM_TRY(abqr_complete(__func__, F));
     abqr_uses(F);
     DeviceGuard g(F->ctx->device);
+    CrossOrder co(F->ctx, {b->ctx, x->ctx});
     AbSolveArgs q{F->RU->p, F->QT->p, F->V->p, b->d->p, x->d->p, F->n, F->np, 0};        // x <- Q'b
     SSM_TRY(launch_ab_qt(F->ctx, F->l, F->u, F->r, F->ntiles, q, true));
     AbSolveArgs s{F->RU->p, F->QT->p, F->V->p, x->d->p, x->d->p, F->n, F->np, 0};        // x <- R \ x
@@ -748,6 +756,7 @@ int ssm_ab_solve(const ssm_ab *A, const ssm_vec *b, ssm_vec *x) {
     SSM_TRY(check_vec(__func__, A->n, A->nb, A->ctx, x));
     ssm_ctx *c = A->ctx;
     DeviceGuard g(c->device);
+    CrossOrder co(c, {b->ctx, x->ctx});
     // R round-trips through HBM (the back-substitution runs against the sweep); reflectors are not kept.
     if (!A->scratch) SSM_TRY(dev_alloc(c, (size_t)(A->ntiles * A->np * (A->l + A->u + 1 + A->r) * 32), true, A->scratch));
     DevBufPtr RU = A->scratch;
@@ -761,6 +770,7 @@ int ssm_ab_tri_ldiv(const ssm_ab *A, ssm_vec *b, int upper, int unit) {
     SSM_CHECK_ARG(A, "null argument");
     SSM_TRY(check_vec(__func__, A->n, A->nb, A->ctx, b));
     DeviceGuard g(A->ctx->device);
+    CrossOrder co(A->ctx, {b->ctx});
     return launch_ab_tri(A->ctx, A, b->d->p, upper != 0, unit != 0);
 }
 
@@ -770,6 +780,7 @@ int ssm_ab_residual(const ssm_ab *A, const ssm_vec *x, const ssm_vec *b, double 
     SSM_TRY(check_vec(__func__, A->n, A->nb, A->ctx, b));
     ssm_ctx *c = A->ctx;
     DeviceGuard g(c->device);
+    CrossOrder co(c, {x->ctx, b->ctx});
     if (is_device_ptr(relres)) return launch_ab_residual(c, A, x, b, relres);
     double *stg;
     SSM_TRY(staging_dev(c, (size_t)A->ntiles * 32, &stg));

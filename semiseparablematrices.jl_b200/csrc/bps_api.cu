@@ -103,6 +103,7 @@ int ssm_bps_qr(const ssm_bps *A, ssm_bpsqr **out) {
     ssm_ctx *c = A->ctx;
     DevGuard g(c->device);
     ssm_bpsqr *F = *out;
+    CrossOrder co(c, {F ? F->ctx : nullptr});
     if (F) {
         if (F->n != A->n || F->l != A->l || F->m != A->m || F->r != A->r || F->p != A->p || F->nb != A->nb) { set_error("ssm_bps_qr: factor object has a different shape"); return SSM_E_SHAPE; }
         F->REC = A->REC;
@@ -156,6 +157,7 @@ int ssm_bpsqr_lmul_qt(const ssm_bpsqr *F, ssm_vec *b) {
     SSM_TRY(chk_vec(__func__, F->n, F->nb, F->ctx, b));
     bpsqr_uses(F);
     DevGuard g(F->ctx->device);
+    CrossOrder co(F->ctx, {b->ctx});
     return launch_bps_qt(F->ctx, F, b->d->p, b->d->p);
 }
 int ssm_bpsqr_upper_ldiv(const ssm_bpsqr *F, ssm_vec *b) {
@@ -163,6 +165,7 @@ int ssm_bpsqr_upper_ldiv(const ssm_bpsqr *F, ssm_vec *b) {
     SSM_TRY(chk_vec(__func__, F->n, F->nb, F->ctx, b));
     bpsqr_uses(F);
     DevGuard g(F->ctx->device);
+    CrossOrder co(F->ctx, {b->ctx});
     return launch_bps_backsolve(F->ctx, F, b->d->p, b->d->p);
 }
 int ssm_bpsqr_solve(const ssm_bpsqr *F, const ssm_vec *b, ssm_vec *x) {
@@ -171,6 +174,7 @@ int ssm_bpsqr_solve(const ssm_bpsqr *F, const ssm_vec *b, ssm_vec *x) {
     SSM_TRY(chk_vec(__func__, F->n, F->nb, F->ctx, x));
     bpsqr_uses(F);
     DevGuard g(F->ctx->device);
+    CrossOrder co(F->ctx, {b->ctx, x->ctx});
     SSM_TRY(launch_bps_qt(F->ctx, F, b->d->p, x->d->p));
     return launch_bps_backsolve(F->ctx, F, x->d->p, x->d->p);
 }
@@ -182,6 +186,7 @@ int ssm_bps_mul(const ssm_bps *A, const ssm_vec *x, ssm_vec *y) {
     SSM_TRY(chk_vec(__func__, A->n, A->nb, A->ctx, y));
     if (x == y) { set_error("ssm_bps_mul: x and y must be distinct"); return SSM_E_ARG; }
     DevGuard g(A->ctx->device);
+    CrossOrder co(A->ctx, {x->ctx, y->ctx});
     return launch_bps_mul(A->ctx, A, x->d->p, y->d->p, nullptr, nullptr);
 }
 int ssm_bps_residual(const ssm_bps *A, const ssm_vec *x, const ssm_vec *b, double *relres) {
@@ -190,6 +195,7 @@ int ssm_bps_residual(const ssm_bps *A, const ssm_vec *x, const ssm_vec *b, doubl
     SSM_TRY(chk_vec(__func__, A->n, A->nb, A->ctx, b));
     ssm_ctx *c = A->ctx;
     DevGuard g(c->device);
+    CrossOrder co(c, {x->ctx, b->ctx});
     if (is_device_ptr(relres)) return launch_bps_mul(c, A, x->d->p, nullptr, b->d->p, relres);
     double *stg;
     SSM_TRY(staging_dev(c, (size_t)A->ntiles * 32, &stg));
@@ -202,6 +208,7 @@ int ssm_bps_upper_ldiv(const ssm_bps *A, ssm_vec *b) {
     SSM_CHECK_ARG(A, "null argument");
     SSM_TRY(chk_vec(__func__, A->n, A->nb, A->ctx, b));
     DevGuard g(A->ctx->device);
+    CrossOrder co(A->ctx, {b->ctx});
     return launch_bps_upper_ldiv(A->ctx, A, b->d->p);
 }
 

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <memory>
 #include <string>
 #include <vector>
@@ -88,6 +89,7 @@ struct ssm_ctx {
     int          abc_tiled_min_chunks = 12288;  // chunked path (K10): from this many chunks on stage 3 runs one lane per chunk over tiled records
     int          sm_count = 148;
     int64_t      launches = 0;
+    cudaEvent_t  ev = nullptr;         // ordering against other contexts' streams (ssm::CrossOrder), created on first use
     ssm::Staging stg;
     // extra streams / events for the chunk-pipelined host path
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
@@ -113,6 +115,31 @@ inline void obj_sync(const ssm_ctx *c) { if (c && !c->retired.load()) cudaStream
 // `user` is about to enqueue work that touches block d.  If d belongs to another context, the owner's destroy-time synchronisation no longer
 // covers every use, so the block is barred from the free list for good (its destructor falls back to cudaFree, which waits for the device).
 inline void uses(const DevBufPtr &d, const ssm_ctx *user) { if (d && d->tok.get() != user->tok.get()) d->foreign.store(true); }
+// An entry point of context `user` is about to enqueue work that reads or writes objects of OTHER contexts (a vector made on context 2 solved with
+// a factorisation of context 1).  Constructor: user's stream waits for everything the owners have enqueued so far (the operand may still be being
+// written); destructor: every owner's stream waits for what user enqueued in between, so the owner's later calls (ssm_vec_get ...) see the result.
+// Device-side ordering only (events), no host synchronisation.
+struct CrossOrder {
+    ssm_ctx *user; ssm_ctx *owners[4]; int n = 0;
+    static void wait(ssm_ctx *waiter, ssm_ctx *signaller) {
+        if (!signaller->ev && cudaEventCreateWithFlags(&signaller->ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+        cudaEventRecord(signaller->ev, signaller->stream);
+        cudaStreamWaitEvent(waiter->stream, signaller->ev, 0);
+    }
+    CrossOrder(ssm_ctx *u, std::initializer_list<ssm_ctx *> os) : user(u) {
+        for (ssm_ctx *o : os) {
+            if (!o || o == u || o->stream == u->stream || o->retired.load() || n == 4) continue;
+            bool dup = false;
+            for (int i = 0; i < n; ++i) dup = dup || owners[i] == o;
+            if (dup) continue;
+            owners[n++] = o;
+            wait(u, o);
+        }
+    }
+    ~CrossOrder() { for (int i = 0; i < n; ++i) wait(owners[i], user); }
+    CrossOrder(const CrossOrder &) = delete;
+    CrossOrder &operator=(const CrossOrder &) = delete;
+};
 }  // namespace ssm
 
 struct ssm_vec {

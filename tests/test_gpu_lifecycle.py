@@ -34,6 +34,20 @@ def test_blocks_used_by_another_context_are_not_recycled():
     F.ldiv(v)
     x = v.get()
     assert max(relerr(x[s], ox[s]) for s in range(nb)) <= 1e-12
+    # the owner's stream is ordered behind the other context's work (device-side events), so v.get() above needs no host synchronisation:
+    # repeat with a large batch, where the solve is long enough for an unordered read to see stale data
+    n2, nb2 = 512, 8192
+    A2 = ssm.AlmostBandedMatrix.generate(n2, l, u, r, nb2, 21, ctx=c1)
+    F2 = ssm.qr(A2)
+    b2 = oracle.ab_generate(n2, l, u, r, nb2, 21)[3]
+    for _ in range(3):
+        v2 = ssm.Vec(c2, n2, nb2, b2)
+        F2.ldiv(v2)
+        x2 = v2.get()
+        assert A2.residual(x2, b2).max() <= 1e-13
+        del v2
+    del F2, A2
+    ssm.pool_trim(0)
     before = ssm.pool_stats(0)["blocks"]
     del v                                   # foreign-used: must be cudaFree'd, not listed
     assert ssm.pool_stats(0)["blocks"] == before
