@@ -608,9 +608,16 @@ int launch_bps_qr(ssm_ctx *c, const ssm_bps *A, ssm_bpsqr *F) {
     return SSM_E_UNSUPPORTED;
 }
 
-static int bps_stages(const ssm_ctx *c, size_t stage_bytes) {
+// Ring depth of the per-step solve kernels (batches too large for the grouped ring).  As for the AlmostBanded K2 / K3 (pick_stages, ab_kernels.cu):
+// a batch that fits the SMs in one wave needs only what Little's law asks per warp (64 KB / warps per SM) — at config-3 shape and 65,536 systems
+// (14 tiles per SM) two stages instead of six to eight take the solve from 10.7 to 9.7 ms; batches of several waves keep the deep ring (131,072
+// systems: 19.4 ms deep, 22.0 ms shallow).
+static int bps_stages(const ssm_ctx *c, size_t stage_bytes, int64_t ntiles) {
     if (c->pipeline_stages > 0) return c->pipeline_stages;
-    int s = (int)(24000 / (stage_bytes + 8));
+    const int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
+    size_t budget = 24000;
+    if (per_sm >= 1 && per_sm <= 14 && (size_t)(64 * 1024) / (size_t)per_sm < budget) budget = (size_t)(64 * 1024) / (size_t)per_sm;
+    int s = (int)((budget + stage_bytes / 2) / (stage_bytes + 8));
     return s < 2 ? 2 : (s > 8 ? 8 : s);
 }
 
@@ -638,7 +645,7 @@ static int qt_shape(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double
                                                                                            F->np, F->npo, npv, 0);
     } else {
         using LD = RingLoader<R, D::NFQ, 1, +1, D::NFA, D::NFO, 1>;
-        const int ns = bps_stages(c, LD::STAGE_BYTES);
+        const int ns = bps_stages(c, LD::STAGE_BYTES, F->ntiles);
         const size_t smem = LD::smem_bytes(ns);
         auto kern = bps_qt_kernel<L, M, R, P, RingLoader>;
         if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -669,7 +676,7 @@ static int bs_shape(ssm_ctx *c, const ssm_bpsqr *F, const double *rhs_in, double
         bps_bs_kernel<L, M, R, P, DirectLoader><<<(unsigned)F->ntiles, 32, 0, c->stream>>>(F->REC->p, F->OUT->p, rhs_in, rhs, F->n, F->np, F->npo, npv, 0);
     } else {
         using LD = RingLoader<D::NFRP, P, 1, -1, D::NFO, D::NFA, 1>;
-        const int ns = bps_stages(c, LD::STAGE_BYTES);
+        const int ns = bps_stages(c, LD::STAGE_BYTES, F->ntiles);
         const size_t smem = LD::smem_bytes(ns);
         auto kern = bps_bs_kernel<L, M, R, P, RingLoader>;
         if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
