@@ -493,9 +493,11 @@ static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
 // store-heavy), the two light solve kernels with the bulk-async ring (profiles/README.md)
 // Below ~7 single-warp CTAs per SM there are too few warps to hide HBM latency behind one-step-ahead register loads, and the ring's
 // deep bulk-async prefetch wins for the QR sweep as well (measured: n=1024 x 16,384 systems 0.81 -> 0.47 ms, n=8192 x 4,096 5.1 -> 3.6 ms).
-static int effective_variant(const ssm_ctx *c, int kernel_default, int64_t ntiles) {
+// `earlier`: tiles per SM by which a kernel hands over to its big-batch form before the common threshold.  K2 / K3 do so two tiles per SM before K1
+// since their per-step rings follow Little's law (40,960 systems of the config-2 shape: ldiv! 0.810 ms against 0.849 ms with the grouped ring).
+static int effective_variant(const ssm_ctx *c, int kernel_default, int64_t ntiles, int earlier = 0) {
     if (c->ab_variant != 0) return c->ab_variant;
-    if (ntiles <= (int64_t)c->sm_count * c->group_max_per_sm) return 4;   // small batch: GroupRing kernels
+    if (ntiles <= (int64_t)c->sm_count * (c->group_max_per_sm - earlier)) return 4;   // small batch: GroupRing kernels
     return kernel_default;
 }
 
@@ -601,7 +603,7 @@ int launch_ab_grow_fix(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const Ab
 int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a, bool transpose) {
     (void)u; (void)r;
     if (ntiles <= 0) return 0;
-    const int variant = effective_variant(c, 2, ntiles);
+    const int variant = effective_variant(c, 2, ntiles, 2);
     if (variant != 9 && transpose) {
         switch (l) {
             case 1: return qt_inst<1>(c, ntiles, a, variant);
@@ -620,7 +622,7 @@ int launch_ab_qt(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveA
 
 int launch_ab_backsolve(ssm_ctx *c, int l, int u, int r, int64_t ntiles, const AbSolveArgs &a) {
     if (ntiles <= 0) return 0;
-    const int variant = effective_variant(c, 2, ntiles);
+    const int variant = effective_variant(c, 2, ntiles, 2);
     if (variant != 9) {
 #define X(L_, U_, R_) \
     if (l == L_ && u == U_ && r == R_) return bs_inst<L_, U_, R_>(c, ntiles, a, variant);
