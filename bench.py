@@ -90,7 +90,7 @@ class ClockSampler:
     """Samples SM clock / throttle reasons through NVML during the timed region (recipe's clocks line)."""
 
     def __init__(self, index: int):
-        self.samples, self.reasons, self._stop, self.max_mhz, self.err = [], set(), threading.Event(), None, None
+        self.samples, self.reasons, self._stop, self.max_mhz, self.err, self.power = [], set(), threading.Event(), None, None, []
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -113,6 +113,10 @@ class ClockSampler:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -133,7 +137,7 @@ class ClockSampler:
         if self.nv and self.t.is_alive():
             self.t.join(timeout=1)
         out = {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
-               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+               "reasons": sorted(self.reasons), "samples": len(self.samples), "power_w_max": (max(self.power) if self.power else None)}
         if self.err:
             out["error"] = self.err
         return out
