@@ -487,7 +487,7 @@ static int bs_inst(ssm_ctx *c, int64_t ntiles, const AbSolveArgs &a, int variant
 }
 
 // shapes with a register-resident fast path (README (1,0,1); tests (1,1,1),(2,0,2),(1,0,2); C2 (2,2,2); C4 (4,4,2))
-#define SSM_AB_SHAPES(X) X(1, 0, 1) X(1, 1, 1) X(1, 0, 2) X(2, 0, 2) X(2, 2, 2) X(3, 3, 2) X(4, 4, 2)
+#define SSM_AB_SHAPES(X) X(1, 0, 1) X(1, 1, 1) X(1, 0, 2) X(2, 0, 2) X(2, 1, 2) X(2, 2, 1) X(2, 2, 2) X(3, 3, 2) X(3, 3, 3) X(4, 4, 2)
 
 // auto (0): measured on B200 at config 2 — the QR sweep is fastest with direct loads (it is register-rich and
 // store-heavy), the two light solve kernels with the bulk-async ring (profiles/README.md)

@@ -155,7 +155,7 @@ static int multi_inst(ssm_ctx *c, const ssm_abqr *F, ssm_mat *B) {
     return 0;
 }
 
-#define SSM_ABM_SHAPES(X) X(1, 0, 1) X(1, 1, 1) X(1, 0, 2) X(2, 0, 2) X(2, 2, 2) X(3, 3, 2) X(4, 4, 2)
+#define SSM_ABM_SHAPES(X) X(1, 0, 1) X(1, 1, 1) X(1, 0, 2) X(2, 0, 2) X(2, 1, 2) X(2, 2, 1) X(2, 2, 2) X(3, 3, 2) X(3, 3, 3) X(4, 4, 2)
 
 }  // namespace ssm
 

@@ -74,7 +74,7 @@ static int run(int n, const double *bands, const double *Uin, const double *Vin,
 extern "C" int emul_ab(int n, int l, int u, int r, const double *bands, const double *U, const double *V, const double *b,
                        double *factors, double *Uout, double *tau, double *c, double *x) {
 #define X(L_, U_, R_) if (l == L_ && u == U_ && r == R_) return run<L_, U_, R_>(n, bands, U, V, b, factors, Uout, tau, c, x);
-    X(1, 0, 1) X(1, 1, 1) X(1, 0, 2) X(2, 0, 2) X(2, 2, 2) X(3, 3, 2) X(4, 4, 2) X(0, 2, 1) X(3, 1, 3)
+    X(1, 0, 1) X(1, 1, 1) X(1, 0, 2) X(2, 0, 2) X(2, 1, 2) X(2, 2, 1) X(2, 2, 2) X(3, 3, 2) X(3, 3, 3) X(4, 4, 2) X(0, 2, 1) X(3, 1, 3)
 #undef X
     return -3;
 }

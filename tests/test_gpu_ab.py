@@ -18,7 +18,7 @@ from helpers import degenerate_system, kat_n80, randn_system, readme_expz, reler
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).parent / "golden"
 
-FAST_SHAPES = [(1, 0, 1), (1, 1, 1), (1, 0, 2), (2, 0, 2), (2, 2, 2), (3, 3, 2), (4, 4, 2)]
+FAST_SHAPES = [(1, 0, 1), (1, 1, 1), (1, 0, 2), (2, 0, 2), (2, 1, 2), (2, 2, 1), (2, 2, 2), (3, 3, 2), (3, 3, 3), (4, 4, 2)]
 GENERIC_SHAPES = [(0, 2, 1), (3, 1, 3), (5, 2, 4), (8, 8, 2), (2, 2, 0), (0, 0, 1)]
 VARIANTS = [1, 2, 4, 9]   # direct-load, bulk-async ring, group ring, generic
 
