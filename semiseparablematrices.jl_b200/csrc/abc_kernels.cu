@@ -28,6 +28,10 @@
 namespace ssm {
 
 constexpr unsigned FULL = 0xffffffffu;
+// predicated 8-byte store (no branch: a conditional block is a scheduling fence in the unrolled sweeps)
+__device__ __forceinline__ void st_global_if(double *p, const double v, const bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"((int)on) : "memory");
+}
 constexpr int ABC_PAD = 512;    // identity rows behind the system: room for the regular chunk layout (abc_layout) and read-ahead
 constexpr int ABC_CPW = 4;      // chunks per warp in stage 1: chunk lengths change only at multiples of this
 
@@ -77,7 +81,7 @@ struct AbcDims {
 template <int LP, int R, int GS>
 struct AbcQrSmem {
     using D = AbcDims<LP, R>;
-    static constexpr int CPW = 32 / GS, CS = (D::NC + GS - 1) / GS, NSTG = 3;
+    static constexpr int CPW = 32 / GS, CS = (D::NC + GS - 1) / GS, NSTG = GS <= 4 ? 2 : 3;   // (a stage lasts PW steps; at GS = 4 two CTAs per SM need the room)
     static constexpr int CBR = ((D::PW * D::NF * 8 + 15) / 16) * 16 + 16;                     // bytes per chunk and stage: operand rows
     static constexpr int CBV = R > 0 ? ((D::PW * R * 8 + 15) / 16) * 16 + 16 : 0;             // ... V rows
     static constexpr int SGB = CPW * (CBR + CBV);                                            // bytes per stage
@@ -85,11 +89,15 @@ struct AbcQrSmem {
     static constexpr int PWE = D::PW + (D::PW & 1);                                          // rhs values per chunk and stage (even count)
     static constexpr int BOFF = (NSTG * SGB > EPI ? NSTG * SGB : EPI);                       // rhs buffer [NSTG][CPW][PWE] behind the ring
     static constexpr int WREG = ((BOFF + NSTG * CPW * PWE * 8 + 127) / 128) * 128;
-    static constexpr int BARS = 4 * WREG, ZERO = BARS + 4 * NSTG * 8, TOTAL = ZERO + 16;
+    static constexpr int BARS = 4 * WREG, ZERO = BARS + 4 * NSTG * 8, TOTAL = ZERO + ((D::PW * D::NF * 8 + 15) / 16) * 16;   // ZERO: one block of zero rows
 };
 
 template <int LP, int R, int GS, bool TILED>
 __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
+    // BF: branch-free step (reflector scalars masked instead of selected under a branch, predicated record stores): with the six
+    // column slots of GS = 4 the scheduler then has independent arithmetic to put beside the scalar chain; at GS = 8 the extra
+    // registers cost the third CTA per SM and the branches stay (measured: profiles/r2_measurements.md)
+    constexpr bool BF = GS <= 4;
     using D = AbcDims<LP, R>;
     using SM = AbcQrSmem<LP, R, GS>;
     constexpr int PW = D::PW, NR = D::NR, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, NF = D::NF, W = D::W;
@@ -124,8 +132,8 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
         if (lane == 0) {
             for (int st = 0; st < NSTG; ++st) mbar_init(bar0 + 8u * st, 1);
             fence_barrier_init();
-            *zero_s = 0.0;
         }
+        for (int i = lane; i < PW * NF; i += 32) zero_s[i] = 0.0;     // (every warp writes the same zeros: no CTA barrier needed)
         __syncwarp();
     }
     auto ring_issue = [&](const int j, const int st) {         // block j into stage st (whole warp calls)
@@ -240,19 +248,22 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             A[sl][PW + t] = val;
         }
 
-    // Per-slot stream of the entering rows: window / generator columns walk the row records in the ring (their pointer is re-based
-    // at every block), the rhs column reads the rhs buffer, all other columns re-read one zero in shared memory, so the load needs
-    // no predicate.  A window column reads field d = (col - k) mod PW, which is also the position of its entry in the emitted record.
-    int d[CS]; const double *ep[CS]; int estride[CS]; double nxt[CS]; double *fr[CS]; bool emit[CS];
+    // Per-slot stream of the entering rows: window / generator columns read the row records of the current block in the ring (their
+    // pointer is re-based at every block, the row inside the block is a compile-time offset), the rhs column reads the rhs buffer,
+    // all other columns read a block of zero rows in shared memory, so the load needs neither a predicate nor a per-slot stride.
+    // A window column reads field d = (col - k) mod PW, which is also the position of its entry in the emitted record.
+    // Emitted records: one running pointer for the warp's row, a constant element offset per slot.
+    int d[CS]; const double *ep[CS]; double nxt[CS]; int fo[CS]; bool emit[CS];
+    double *frb = TILED ? a.FR + (int64_t)(c >> 2) * a.npf * NC * 4 + (c & 3) : a.FR + r0 * NC;
     const double *bcur = bbuf;                                // this block's rhs values
     double bnx = bcur[0];
 #pragma unroll
     for (int sl = 0; sl < CS; ++sl) {
         d[sl] = isW[sl] ? col[sl] : 0;                        // phase 0
-        if (isW[sl] || isG[sl]) { ep[sl] = ring_rec(0, 0) + (isG[sl] ? PW + col[sl] - G0 : 0); estride[sl] = NF; }
-        else { ep[sl] = zero_s; estride[sl] = 0; }
+        if (isW[sl] || isG[sl]) ep[sl] = ring_rec(0, 0) + (isG[sl] ? PW + col[sl] - G0 : 0);
+        else ep[sl] = zero_s;
         nxt[sl] = ep[sl][d[sl]];
-        fr[sl] = (TILED ? a.FR + (int64_t)(c >> 2) * a.npf * NC * 4 + (c & 3) : a.FR + r0 * NC) + (isW[sl] ? 0 : col[sl]) * FSTR;
+        fo[sl] = (isW[sl] ? 0 : col[sl]) * FSTR;
         emit[sl] = live && col[sl] < NC;
     }
     const double *vp = ring_v(0, 0);                          // V row of the column entering after step 0
@@ -285,9 +296,8 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             for (int sl = 0; sl < CS; ++sl) {
                 // prefetch the row entering at the next step (rows past the chunk are the next chunk's or the identity pad)
                 if (PH == PW - 1) { if (isW[sl] || isG[sl]) ep[sl] = ring_rec(rblock, rstage) + (isG[sl] ? PW + col[sl] - G0 : 0); }
-                else ep[sl] += estride[sl];
                 const int dn = isW[sl] ? (d[sl] == 0 ? LP : d[sl] - 1) : 0;
-                nxt[sl] = ep[sl][dn];
+                nxt[sl] = ep[sl][((PH + 1) % PW) * NF + dn];
             }
             double vn[RQ];
             if (PH == PW - 1) vp = ring_v(rblock, rstage); else vp += R;
@@ -321,8 +331,9 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             nrm = fma(fma(-nrm, nrm, ssq), 0.5 * rs, nrm);    // one correction step: sqrt to ~1 ulp
             const double nu = copysign(nrm, xp);
             const double xi = xp + nu;
-            const double inv = nz ? fast_rcp(xi) : 0.0;
-            const double tau = nz ? xi * copysign(rs, xp) : 0.0;
+            double inv, tau;
+            if constexpr (BF) { inv = keep_if(fast_rcp(xi), nz); tau = keep_if(xi * copysign(rs, xp), nz); }
+            else { inv = nz ? fast_rcp(xi) : 0.0; tau = nz ? xi * copysign(rs, xp) : 0.0; }
 #pragma unroll
             for (int sl = 0; sl < CS; ++sl) {
                 const double dot = fma(inv, raw[sl], A[sl][PH]) * tau;     // tau * v'a, v = (1, x_s * inv)
@@ -334,10 +345,12 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             // emit the finished row (canonical order: window entry of column k+t at position t)
 #pragma unroll
             for (int sl = 0; sl < CS; ++sl) {
-                if (emit[sl]) fr[sl][(isW[sl] ? d[sl] : 0) * FSTR] = A[sl][PH];
-                fr[sl] += RSTR;
+                double *dst = frb + (fo[sl] + (isW[sl] ? d[sl] : 0) * FSTR);
+                if constexpr (BF) st_global_if(dst, A[sl][PH], emit[sl]);
+                else if (emit[sl]) *dst = A[sl][PH];
                 d[sl] = isW[sl] ? (d[sl] == 0 ? LP : d[sl] - 1) : 0;
             }
+            frb += RSTR;
             // the window slides: local column k+LP+1 replaces the pivot column (fill region of every surviving row)
 #pragma unroll
             for (int s = 0; s < NR; ++s) {
@@ -1066,13 +1079,19 @@ static void abc_layout(int64_t n, int lp, int same, int &P, int &m0, int &jx) {
     if (jx > P) jx = P;
 }
 
+// shapes with a 4-lanes-per-chunk instance of stage 1 (the wide active blocks), and the group size a context asks for
+constexpr bool abc_has_gs4(int lp, int r) { return 2 * lp + 2 * r + 2 >= 18; }
+static int abc_gs_of(const ssm_ctx *c, int lp, int r) { return abc_has_gs4(lp, r) && c->abc_gs == 4 ? 4 : 8; }
+
 static int abc_default_chunks(const ssm_abc *A) {
     // Stage 1 holds 12 warps of 4 chunks per SM, and all chunks are equally long, so its time moves in whole WAVES of
     // sm_count * 48 chunks.  Large systems: ~512 rows per chunk, rounded down to whole waves, at most 4 (measured at n = 2^24:
     // 28,416 and 32,768 chunks 2.89 ms, 35,520 2.96, 42,624 3.14).  Below one wave of 512-row chunks the sweep is latency bound and
     // shorter chunks win until the separator tree takes over: 128 rows per chunk, at most one wave (n = 10^6: 1,953 chunks 0.50 ms,
     // 7,104 0.40 ms; n = 65,536: 128 chunks 0.37 ms, 512 0.20 ms).
-    const int64_t wave = (int64_t)(A->ctx->sm_count > 0 ? A->ctx->sm_count : 148) * 12 * ABC_CPW;
+    // (4 lanes per chunk: 8 warps of 8 chunks per SM, waves of sm_count * 64; n = 2^24 gets 28,416 chunks either way)
+    const int per_sm = abc_gs_of(A->ctx, A->lp, A->r) == 4 ? 8 * 8 : 12 * ABC_CPW;
+    const int64_t wave = (int64_t)(A->ctx->sm_count > 0 ? A->ctx->sm_count : 148) * per_sm;
     int64_t P = A->n / 512;
     if (P >= wave) P = std::min<int64_t>(P / wave, 4) * wave;
     else P = std::min<int64_t>(A->n / 128, wave);
@@ -1089,10 +1108,10 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     constexpr int W = D::W, EW = 2 * W + 1, TW = 3 * W + 1;
     AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P, A->m0, A->jx, LP + 1, A->npf};
     const unsigned gchunks = (unsigned)((P + 3) / 4);
-    constexpr int GS = 8;                                      // lanes per chunk in stage 1 (4 chunks per warp)
-    static_assert(ABC_CPW == 32 / GS, "abc_layout must round jx to the chunks-per-warp of stage 1");
-    const unsigned gqr = (unsigned)((P + 4 * ABC_CPW - 1) / (4 * ABC_CPW));
-    {
+    // lanes per chunk in stage 1: 8 (4 chunks per warp) or, for the wide active blocks, 4 (8 chunks per warp; option "abc_gs")
+    auto stage1 = [&](auto gs_tag) -> int {
+        constexpr int GS = decltype(gs_tag)::value, CPW = 32 / GS;
+        const unsigned gqr = (unsigned)((P + 4 * CPW - 1) / (4 * CPW));
         constexpr int smem = AbcQrSmem<LP, R, GS>::TOTAL;
         auto launch = [&](auto kern) -> int {
             if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1102,6 +1121,13 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
         };
         if (A->tiled) SSM_TRY(launch(abc_qr_kernel<LP, R, GS, true>));
         else SSM_TRY(launch(abc_qr_kernel<LP, R, GS, false>));
+        return 0;
+    };
+    if constexpr (abc_has_gs4(LP, R)) {
+        if (abc_gs_of(c, LP, R) == 4) SSM_TRY(stage1(std::integral_constant<int, 4>{}));
+        else SSM_TRY(stage1(std::integral_constant<int, 8>{}));
+    } else {
+        SSM_TRY(stage1(std::integral_constant<int, 8>{}));
     }
     c->launches++;
     // levels: level t has cnt[t] blocks stored at E + eoff[t]; levels with more than 32 blocks are one launch each, the rest of the
@@ -1250,7 +1276,7 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
     int P = nchunks > 0 ? nchunks : abc_default_chunks(A);
     int m0 = 0, jx = 0;
-    abc_layout(A->n, A->lp, ABC_CPW, P, m0, jx);
+    abc_layout(A->n, A->lp, 32 / abc_gs_of(c, A->lp, A->r), P, m0, jx);
     const bool tiled = P >= c->abc_tiled_min_chunks;          // P only shrinks for tiny n, where neither rounding changes it
     if (tiled) abc_layout(A->n, A->lp, 32, P, m0, jx);
     const int64_t npf = (int64_t)m0 + 1;                      // rows eliminated by a long chunk: m0 + (lp+1) - lp

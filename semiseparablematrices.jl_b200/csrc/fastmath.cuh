@@ -40,6 +40,16 @@ SSM_FM_HD double fast_rsqrt(double a) {
 #endif
 }
 
+// on ? a : 0.0 without giving the compiler a reason to branch: a conditional block around the reciprocal fences the reflector's
+// scalar chain off from the independent arithmetic that should overlap it (ptxas schedules inside basic blocks only)
+SSM_FM_HD double keep_if(double a, bool on) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(__double_as_longlong(a) & (on ? -1ll : 0ll));
+#else
+    return on ? a : 0.0;
+#endif
+}
+
 // sqrt(a) to ~1 ulp from the refined reciprocal square root (a > 0 and finite; a == 0 gives NaN, callers mask it)
 SSM_FM_HD double fast_sqrt_from_rsqrt(double a, double rs) {
     const double nrm = a * rs;

@@ -87,6 +87,7 @@ struct ssm_ctx {
     int          pipeline_stages = 0;  // 0 = kernel default
     int          qt_stages = 0, bs_stages = 0;   // ring depth of K2 / K3 alone (0 = pick_stages)
     int          abc_tiled_min_chunks = 12288;  // chunked path (K10): from this many chunks on stage 3 runs one lane per chunk over tiled records
+    int          abc_gs = 4;                    // chunked path: lanes that share one chunk in stage 1 of the wide shapes (4, or 8 as for all others)
     int          sm_count = 148;
     int64_t      launches = 0;
     cudaEvent_t  ev = nullptr;         // ordering against other contexts' streams (ssm::CrossOrder), created on first use

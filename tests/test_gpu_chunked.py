@@ -38,20 +38,27 @@ def _rand(rng, n, l, u, r):
                                        (200, 3, 1, 2, 8), (500, 2, 2, 2, 16), (777, 4, 4, 2, 7), (130, 1, 1, 2, 5), (64, 2, 1, 1, 3),
                                        (300, 2, 2, 0, 6), (90, 1, 0, 0, 3), (128, 1, 1, 0, 4)])
 @pytest.mark.parametrize("tiled", [False, True])
-def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P, tiled):
+@pytest.mark.parametrize("gs", [8, 4])
+def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P, tiled, gs):
     """`tiled`: stage 3 with one lane per chunk over tile-interleaved records (the path large systems take) forced onto the
-    small case; otherwise one warp per chunk over row-major records."""
+    small case; otherwise one warp per chunk over row-major records.  `gs`: lanes that share a chunk in stage 1 (the wide
+    active blocks, 2(l+u) + 2r + 2 >= 18 columns, have a 4-lane instance; the others always run 8 lanes per chunk)."""
+    gs_eff = 4 if gs == 4 and 2 * (l + u) + 2 * r + 2 >= 18 else 8
+    if gs == 4 and gs_eff == 8:
+        pytest.skip("shape has no 4-lane instance")
     rng = np.random.default_rng(n * 13 + P)
     bands, U, V, b = _rand(rng, n, l, u, r)
     A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
-    default = ctx.get_option("abc_tiled_min_chunks")
+    default, default_gs = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_gs")
     ctx.set_option("abc_tiled_min_chunks", 1 if tiled else 1 << 30)
+    ctx.set_option("abc_gs", gs)
     try:
         x = A.solve(b, nchunks=P)
     finally:
         ctx.set_option("abc_tiled_min_chunks", default)
+        ctx.set_option("abc_gs", default_gs)
     lp, w = l + u, l + u + r
-    P, bnd = regular_layout(n, lp, P, same=32 if tiled else 4)
+    P, bnd = regular_layout(n, lp, P, same=32 if tiled else 32 // gs_eff)
     assert A.chunks == P
     pb, pU, pV, pbv = pad_system(bands, U, V, b, l, u, bnd[-1])
     # stage 1 output: level-0 reduced blocks [F | G | h] per chunk, against the numpy restatement (rows may differ by
