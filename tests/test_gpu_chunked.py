@@ -157,9 +157,10 @@ def test_random_shapes_and_chunk_counts_match_oracle(ctx):
     from ssm_b200 import chunked
     shapes = [(1, 0), (2, 0), (4, 0), (1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (6, 2), (8, 2)]
     rng = np.random.default_rng(2028)
-    default = ctx.get_option("abc_tiled_min_chunks")
+    default, default_gs = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_gs")
     try:
         for it in range(40):
+            ctx.set_option("abc_gs", 4 if it % 2 == 0 else 8)      # lanes per chunk in stage 1 of the wide shapes
             lp, r = shapes[int(rng.integers(0, len(shapes)))]
             l = int(rng.integers(0, lp + 1)); u = lp - l
             n = int(rng.choice([1, 2, lp + 1, 2 * lp + 3, 100, 1000, 4097, 20000]))
@@ -176,3 +177,4 @@ def test_random_shapes_and_chunk_counts_match_oracle(ctx):
                     assert A.residual(x, b[0]) <= 1e-13, tag
     finally:
         ctx.set_option("abc_tiled_min_chunks", default)
+        ctx.set_option("abc_gs", default_gs)
