@@ -44,6 +44,9 @@ struct AbcArgs {
     int64_t n; int l, u; int P;
     int m0, jx, pw;              // chunk c has m0 + pw*(c < jx) rows: every chunk length is == lp (mod lp+1), see abc_layout()
     int64_t npf;                 // tiled FR: records per mini-tile of 4 chunks, FR[c / 4][npf][NC][c % 4]
+    int *smc;                    // lane-per-chunk stage 1: one arrival counter per SM (never reset: only its low bits are used)
+    const double *RI, *VI;       // lane-per-chunk stage 1: chunk-interleaved entering rows / V rows (abc_interleave_kernel), nrow_i steps per tile
+    int nrow_i;
 };
 
 // Regular chunks: the system is padded with < lp+1 identity rows to n' = P*m0 + jx*pw so that every chunk eliminates a
@@ -393,6 +396,390 @@ __global__ void __launch_bounds__(128) abc_qr_kernel(const AbcArgs a) {
             }
         }
     }
+}
+
+// Chunk-interleaved copy of the rows and V rows that enter the sweep of stage 1, for the lane-per-chunk kernel: tile t = chunks
+// 32t .. 32t+31 (equally long), step i = 0 .. nsteps-1:  RI[((t * nrow + i) * NF + f) * 32 + lane] = REC[r0 + LP + i][f],
+// VI[((t * nrow + i) * R + q) * 32 + lane] = V[r0 + u + LP + 1 + i][q]  (r0 = first row of chunk 32t + lane; spare lanes repeat chunk P-1).
+template <int NF, int R>
+__global__ void __launch_bounds__(256) abc_interleave_kernel(const AbcArgs a, double *RI, double *VI, const int lp, const int nrow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = blockIdx.y;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= nrow) return;
+    int c = (int)(t * 32 + lane);
+    if (c >= a.P) c = a.P - 1;
+    const int64_t r0 = chunk_start(a, c);
+    const double *src = a.REC + (r0 + lp + i) * NF, *vs = a.V + (r0 + a.u + lp + 1 + i) * R;
+    double *dst = RI + ((t * nrow + i) * NF) * 32 + lane, *vd = VI + ((t * nrow + i) * R) * 32 + lane;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) dst[f * 32] = src[f];
+#pragma unroll
+    for (int q = 0; q < R; ++q) vd[q * 32] = vs[q];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage 1, one LANE per chunk (the wide shape (l+u, r) = (8, 2) at many chunks).  A CTA is FOUR warps sweeping the same 32 chunks,
+// lane = chunk in every warp, so there is no pivot broadcast, no redundant reflector arithmetic and no shuffle at all; the 22
+// columns of a chunk's active block are spread over the four warps' registers:
+//   P1  window positions 0..NP1-1   forms the reflector of every step (the pivot column is always position 0) and publishes
+//                                   (x, 1/xi, tau) plus the entering row's remaining fields and the entering V row
+//   P2  window positions NP1+1..l+u | generator columns     applies it, builds the column that enters the window, and hands the column
+//                                   that moves from position NP1+1 to NP1 over to P1 (one column per step, through shared memory)
+//   T1, T2   separator | tail | rhs columns                  apply it
+// The window is kept in RELATIVE position — column k+j of step k at position j, row k+i in slot i — and every update writes its
+// result one position / one slot down (a different destination register, no extra instruction), so the step is the same code for
+// every k and the loop is not unrolled over k mod (l+u+1).  Rings: reflectors P1 -> {P2, T1, T2} (NSX slots, full / empty
+// mbarriers, one arrival per warp), moving column P2 -> P1 (2 slots), entering operand and V rows by TWO bulk-async copies per
+// stage for the whole warp — they come from a chunk-interleaved copy of the operands, RI[tile of 32 chunks][step][field][lane]
+// and VI[tile][step][r][lane], that abc_interleave_kernel writes once per operand set and chunk layout (feeding 32 separate
+// row-major chunk streams into one warp costs a bulk copy per lane and stage: measured, profiles/r2_measurements.md); rhs values
+// by plain loads two steps ahead (T2).  Same arithmetic, R records and level-0 blocks as abc_qr_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+template <int LP, int R>
+struct AbcLpcSmem {
+    using D = AbcDims<LP, R>;
+    static constexpr int NP1 = 5;                                   // window positions 0..NP1-1 live in P1; position NP1 arrives every step
+    static constexpr int NT1 = (LP + R + 1 + 1) / 2;                // trailing columns of T1 (the rest, with the rhs, in T2)
+    static constexpr int SBK = 3;                                   // steps per stage of the entering-row ring
+    static_assert(D::PW % SBK == 0 && NP1 + 1 < D::PW, "ring stage / column split");
+    static constexpr int NSTG = 2, NSX = 4, NSC = 2;
+    static constexpr int CBR = SBK * D::NF * 256, CBV = SBK * R * 256;           // a stage: SBK rows of the tile-interleaved operand / V rows
+    static constexpr int SGB = CBR + CBV;
+    static constexpr int XF = (D::NR - 1) + 2;                      // x[1 .. NR-1], 1/xi, tau
+    static constexpr int XN = XF + (D::NF - NP1 - 1) + R;           // + entering row fields NP1+1 .. NF-1, entering V row
+    static constexpr int CN = D::NR - 1;                            // moving column: every slot but the entering row's
+    static constexpr int OFF_RING = 0, OFF_X = OFF_RING + NSTG * SGB, OFF_C = OFF_X + NSX * XN * 256, BARS = OFF_C + NSC * CN * 256;
+    static constexpr int NBAR = NSTG + 2 * NSX + 2 * NSC;           // entering-row ring | X full | X empty | C full | C empty
+    static constexpr int TOTAL = BARS + NBAR * 8;
+};
+
+template <int LP, int R, bool TILED>
+__global__ void __launch_bounds__(128, 3) abc_qr_lpc_kernel(const AbcArgs a) {
+    using D = AbcDims<LP, R>;
+    using SM = AbcLpcSmem<LP, R>;
+    static_assert(R >= 1, "built for shapes with a fill");
+    constexpr int PW = D::PW, NR = D::NR, NC = D::NC, NF = D::NF, W = D::W, C0 = D::C0;
+    constexpr int NP1 = SM::NP1, NP2 = PW - NP1 - 1, NCB = LP + R + 1, NT1 = SM::NT1, NT2 = NCB - NT1;
+    constexpr int SBK = SM::SBK, NSTG = SM::NSTG, NSX = SM::NSX, NSC = SM::NSC, XF = SM::XF, XN = SM::XN, CN = SM::CN;
+    constexpr int FSTR = TILED ? 4 : 1, RSTR = TILED ? NC * 4 : NC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    // The four roles rotate over the CTA's warps with the order in which CTAs arrive on this SM (a counter per SM), so that the CTAs
+    // resident together give every scheduler a mix of roles wherever the block scheduler puts them
+    __shared__ int rot_s;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        rot_s = atomicAdd(a.smc + (smid & 511), 1) & 3;
+    }
+    if (threadIdx.x < SM::NBAR) {
+        const int i = threadIdx.x;
+        mbar_init(smem_u32(smem + SM::BARS + i * 8), (i >= NSTG + NSX && i < NSTG + 2 * NSX) ? 3 : 1);   // X empty: three consumer warps
+    }
+    fence_barrier_init();
+    __syncthreads();
+    const int lane = threadIdx.x & 31, role = ((threadIdx.x >> 5) + rot_s) & 3;     // 0 P1, 1 P2, 2 T1, 3 T2
+    int c = blockIdx.x * 32 + lane;
+    const bool live = c < a.P;
+    if (!live) c = a.P - 1;
+    const int64_t r0 = chunk_start(a, c);
+    const int m = a.m0 + (c < a.jx ? PW : 0), nsteps = m - LP, nsb = nsteps / SBK;   // the same for the 32 chunks of a CTA
+    const int u = a.u;
+    const double *rec0 = a.REC + r0 * NF;
+    const double *v0 = a.V + (r0 + u) * R;
+    const double *b0 = a.b + r0;
+    const int64_t brows = a.n - r0;
+    const uint32_t bar_ring = smem_u32(smem + SM::BARS), bar_xf = bar_ring + NSTG * 8, bar_xe = bar_xf + NSX * 8, bar_cf = bar_xe + NSX * 8, bar_ce = bar_cf + NSC * 8;
+    double *frb = TILED ? a.FR + (int64_t)(c >> 2) * a.npf * NC * 4 + (c & 3) : a.FR + r0 * NC;
+    double *E = a.E0 + (int64_t)c * W * (2 * W + 1);
+    double *Xs = reinterpret_cast<double *>(smem + SM::OFF_X) + lane;           // Xs[(slot * XN + f) * 32]
+    double *Cs = reinterpret_cast<double *>(smem + SM::OFF_C) + lane;           // Cs[(slot * CN + i) * 32], i = slot index without the entering row's
+    // value of window column j (local), band row ip < LP, before any elimination: band entry, or fill U[ip,:] . V[:, j]
+    auto wval = [&](const int ip, const int j) -> double {
+        const double *rec = rec0 + (int64_t)ip * NF;
+        if (j <= ip) return rec[LP - ip + j];
+        double val = 0.0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) val = fma(rec[PW + q], v0[(int64_t)j * R + q], val);
+        return val;
+    };
+    // one column through one reflector (x[1..], inv, tau): cv has the entering entry in slot LP; band rows move one slot down
+#define ABC_LPC_REFLECT(cv, out, ev)                                                                   \
+    {                                                                                                  \
+        double d0_ = 0.0, d1_ = 0.0;                                                                   \
+        _Pragma("unroll") for (int s = 1; s < NR; ++s) { if (s & 1) d1_ = fma(x[s], (cv)[s], d1_); else d0_ = fma(x[s], (cv)[s], d0_); } \
+        const double dot_ = fma(inv, d0_ + d1_, (cv)[0]) * tau;                                        \
+        const double cf_ = dot_ * inv;                                                                 \
+        ev = (cv)[0] - dot_;                                                                           \
+        _Pragma("unroll") for (int s = 1; s < PW; ++s) (out)[s - 1] = fma(-x[s], cf_, (cv)[s]);        \
+        _Pragma("unroll") for (int s = PW; s < NR; ++s) (out)[s] = fma(-x[s], cf_, (cv)[s]);           \
+    }
+
+    if (role == 0) {
+        // ===== P1: window positions 0..NP1-1, the reflector =====
+        unsigned char *ring = smem + SM::OFF_RING;
+        const double *ri_t = a.RI + (int64_t)blockIdx.x * a.nrow_i * NF * 32, *vi_t = a.VI + (int64_t)blockIdx.x * a.nrow_i * R * 32;
+        auto ring_issue = [&](const int j, const int st) {
+            if (lane == 0) {
+                const uint32_t bar = bar_ring + 8u * st;
+                mbar_expect_tx(bar, SM::SGB);
+                bulk_g2s(smem_u32(ring + st * SM::SGB), ri_t + (int64_t)j * SBK * NF * 32, SM::CBR, bar);
+                bulk_g2s(smem_u32(ring + st * SM::SGB + SM::CBR), vi_t + (int64_t)j * SBK * R * 32, SM::CBV, bar);
+            }
+        };
+        for (int j = 0; j < NSTG && j < nsb; ++j) ring_issue(j, j);
+        double Wr[NP1][NR];
+#pragma unroll
+        for (int j = 0; j < NP1; ++j) {
+#pragma unroll
+            for (int ip = 0; ip < LP; ++ip) Wr[j][ip] = wval(ip, j);
+            Wr[j][LP] = 0.0;
+#pragma unroll
+            for (int t = 0; t < R; ++t) Wr[j][PW + t] = -v0[(int64_t)j * R + t];
+        }
+        int st = 0, xs = 0, cs = 0; uint32_t par = 0, xpar = 1, cpar = 0;
+        for (int jb = 0; jb < nsb; ++jb) {
+            mbar_wait(bar_ring + 8u * st, par);
+            const double *rb = reinterpret_cast<const double *>(ring + st * SM::SGB) + lane;              // rb[(i * NF + f) * 32]
+            const double *vb = reinterpret_cast<const double *>(ring + st * SM::SGB + SM::CBR) + lane;    // vb[(i * R + q) * 32]
+#pragma unroll
+            for (int i = 0; i < SBK; ++i) {
+                auto rec = [&](const int f) -> double { return rb[(i * NF + f) * 32]; };       // entering row, read where it is used
+                double x[NR];
+#pragma unroll
+                for (int s = 0; s < NR; ++s) x[s] = Wr[0][s];
+                x[LP] = rec(0);                               // the entering row (local row k + LP) sits in slot LP
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+                for (int s = 0; s < NR; ++s) { if (s % 3 == 0) q0 = fma(x[s], x[s], q0); else if (s % 3 == 1) q1 = fma(x[s], x[s], q1); else q2 = fma(x[s], x[s], q2); }
+                const double ssq = (q0 + q1) + q2;
+                const double xp = x[0];
+                const bool nz = ssq != 0.0;
+                const double rs = fast_rsqrt(ssq);
+                double nrm = ssq * rs;
+                nrm = fma(fma(-nrm, nrm, ssq), 0.5 * rs, nrm);
+                const double nu = copysign(nrm, xp);
+                const double xi = xp + nu;
+                const double inv = nz ? fast_rcp(xi) : 0.0;
+                const double tau = nz ? xi * copysign(rs, xp) : 0.0;
+                // publish the reflector, the rest of the entering row and the entering V row
+                mbar_wait(bar_xe + 8u * xs, xpar);
+                {
+                    double *xo = Xs + xs * XN * 32;
+#pragma unroll
+                    for (int s = 1; s < NR; ++s) xo[(s - 1) * 32] = x[s];
+                    xo[(NR - 1) * 32] = inv; xo[NR * 32] = tau;
+#pragma unroll
+                    for (int f = NP1 + 1; f < NF; ++f) xo[(XF + f - NP1 - 1) * 32] = rec(f);
+#pragma unroll
+                    for (int q = 0; q < R; ++q) xo[(XF + NF - NP1 - 1 + q) * 32] = vb[(i * R + q) * 32];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_xf + 8u * xs);
+                if (++xs == NSX) { xs = 0; xpar ^= 1u; }
+                if (live) frb[0] = nz ? -nu : xp;
+#pragma unroll
+                for (int j = 1; j < NP1; ++j) {
+                    Wr[j][LP] = rec(j);
+                    double ev;
+                    ABC_LPC_REFLECT(Wr[j], Wr[j - 1], ev)
+                    if (live) frb[j * FSTR] = ev;
+                }
+                {   // the column at position NP1: handed over by P2 after the previous step (by its prologue for step 0)
+                    double cv[NR], ev;
+                    mbar_wait(bar_cf + 8u * cs, cpar);
+                    const double *ci = Cs + cs * CN * 32;
+#pragma unroll
+                    for (int s = 0; s < NR; ++s) cv[s] = s == LP ? rec(NP1) : ci[(s < LP ? s : s - 1) * 32];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_ce + 8u * cs);
+                    if (++cs == NSC) { cs = 0; cpar ^= 1u; }
+                    ABC_LPC_REFLECT(cv, Wr[NP1 - 1], ev)
+                    if (live) frb[NP1 * FSTR] = ev;
+                }
+                frb += RSTR;
+            }
+            __syncwarp();
+            fence_proxy_async();
+            if (jb + NSTG < nsb) ring_issue(jb + NSTG, st);
+            if (++st == NSTG) { st = 0; par ^= 1u; }
+        }
+        // leftover rows -> window part of the level-0 block, positions 0..NP1 (the last one arrives from P2 once more)
+        double cl[NR];
+        mbar_wait(bar_cf + 8u * cs, cpar);
+        {
+            const double *ci = Cs + cs * CN * 32;
+#pragma unroll
+            for (int s = 0; s < NR; ++s) cl[s] = s == LP ? 0.0 : ci[(s < LP ? s : s - 1) * 32];
+        }
+        if (!live) return;
+#pragma unroll
+        for (int row = 0; row < W; ++row) {
+            const int slot = row < LP ? row : PW + (row - LP);
+#pragma unroll
+            for (int j = 0; j < NP1; ++j) E[row * (2 * W + 1) + W + j] = Wr[j][slot];
+            E[row * (2 * W + 1) + W + NP1] = cl[slot];
+        }
+    } else if (role == 1) {
+        // ===== P2: window positions NP1+1..LP (registers Wp[0..NP2-1]) | generator columns =====
+        double Wp[NP2][NR], G[R][NR];
+#pragma unroll
+        for (int ip = 0; ip < LP; ++ip) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) G[q][ip] = rec0[(int64_t)ip * NF + PW + q];
+#pragma unroll
+            for (int j = 0; j < NP2; ++j) Wp[j][ip] = wval(ip, NP1 + 1 + j);
+        }
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+#pragma unroll
+            for (int j = 0; j < NP2; ++j) Wp[j][PW + t] = -v0[(int64_t)(NP1 + 1 + j) * R + t];
+#pragma unroll
+            for (int q = 0; q < R; ++q) G[q][PW + t] = q == t ? -1.0 : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NP2; ++j) Wp[j][LP] = 0.0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) G[q][LP] = 0.0;
+        int xs = 0, cs = 0; uint32_t xpar = 0, cpar = 1;
+        {   // message 0 of the column ring: position NP1 as the prologue leaves it
+            mbar_wait(bar_ce + 8u * cs, cpar);
+            double *co = Cs + cs * CN * 32;
+#pragma unroll
+            for (int ip = 0; ip < LP; ++ip) co[ip * 32] = wval(ip, NP1);
+#pragma unroll
+            for (int t = 0; t < R; ++t) co[(LP + t) * 32] = -v0[(int64_t)NP1 * R + t];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_cf + 8u * cs);
+            if (++cs == NSC) { cs = 0; cpar ^= 1u; }
+        }
+        for (int k = 0; k < nsteps; ++k) {
+            double x[NR], inv, tau, rec[NF], vr[R];
+            mbar_wait(bar_xf + 8u * xs, xpar);
+            {
+                const double *xi_ = Xs + xs * XN * 32;
+#pragma unroll
+                for (int s = 1; s < NR; ++s) x[s] = xi_[(s - 1) * 32];
+                inv = xi_[(NR - 1) * 32]; tau = xi_[NR * 32];
+#pragma unroll
+                for (int f = NP1 + 1; f < NF; ++f) rec[f] = xi_[(XF + f - NP1 - 1) * 32];
+#pragma unroll
+                for (int q = 0; q < R; ++q) vr[q] = xi_[(XF + NF - NP1 - 1 + q) * 32];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xe + 8u * xs);
+            if (++xs == NSX) { xs = 0; xpar ^= 1u; }
+            {   // position NP1+1 moves to NP1: over to P1
+                double out[NR], ev;
+                Wp[0][LP] = rec[NP1 + 1];
+                ABC_LPC_REFLECT(Wp[0], out, ev)
+                if (live) frb[(NP1 + 1) * FSTR] = ev;
+                mbar_wait(bar_ce + 8u * cs, cpar);
+                double *co = Cs + cs * CN * 32;
+#pragma unroll
+                for (int s = 0; s < NR; ++s) if (s != LP) co[(s < LP ? s : s - 1) * 32] = out[s];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_cf + 8u * cs);
+                if (++cs == NSC) { cs = 0; cpar ^= 1u; }
+            }
+#pragma unroll
+            for (int j = 1; j < NP2; ++j) {
+                Wp[j][LP] = rec[NP1 + 1 + j];
+                double ev;
+                ABC_LPC_REFLECT(Wp[j], Wp[j - 1], ev)
+                if (live) frb[(NP1 + 1 + j) * FSTR] = ev;
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                G[q][LP] = rec[PW + q];
+                double ev;
+                ABC_LPC_REFLECT(G[q], G[q], ev)
+                if (live) frb[(PW + q) * FSTR] = ev;
+            }
+            // the column that enters the window at position LP: fill region of every surviving row
+#pragma unroll
+            for (int s = 0; s < NR; ++s) {
+                if (s == LP) continue;
+                double f = 0.0;
+#pragma unroll
+                for (int q = 0; q < R; ++q) f = fma(G[q][s], vr[q], f);
+                Wp[NP2 - 1][s] = f;
+            }
+            frb += RSTR;
+        }
+        if (!live) return;
+        // leftover rows -> window positions NP1+1..LP-1 and generator part of the level-0 block
+#pragma unroll
+        for (int row = 0; row < W; ++row) {
+            const int slot = row < LP ? row : PW + (row - LP);
+#pragma unroll
+            for (int j = 0; j + NP1 + 1 < LP; ++j) E[row * (2 * W + 1) + W + NP1 + 1 + j] = Wp[j][slot];
+#pragma unroll
+            for (int q = 0; q < R; ++q) E[row * (2 * W + 1) + W + LP + q] = G[q][slot];
+        }
+    } else {
+        // ===== T1 / T2: trailing columns jt (separator jt < LP, tail LP <= jt < LP + R, rhs jt = LP + R) =====
+        const int jt0 = role == 2 ? 0 : NT1;
+        constexpr int NTM = NT1 > NT2 ? NT1 : NT2;
+        double Tr[NTM][NR];
+        bool isrhs[NTM], act[NTM];
+#pragma unroll
+        for (int j = 0; j < NTM; ++j) {
+            const int jt = jt0 + j;
+            act[j] = j < (role == 2 ? NT1 : NT2);
+            isrhs[j] = act[j] && jt == LP + R;
+#pragma unroll
+            for (int s = 0; s < NR; ++s) {
+                double val = 0.0;
+                if (act[j]) {
+                    if (s < LP) {
+                        if (jt < LP) { if (s <= jt) val = rec0[(int64_t)s * NF + (jt - s)]; }
+                        else if (jt == LP + R) { if (s < brows) val = b0[s]; }
+                    } else if (s >= PW) {
+                        if (jt >= LP && jt < LP + R && jt - LP == s - PW) val = 1.0;
+                    }
+                }
+                Tr[j][s] = val;
+            }
+        }
+        auto bload = [&](const int64_t i) -> double { return (role == 3 && i < brows) ? b0[i] : 0.0; };
+        double bq0 = bload(LP), bq1 = bload(LP + 1), bq2 = bload(LP + 2);
+        int xs = 0; uint32_t xpar = 0;
+        for (int k = 0; k < nsteps; ++k) {
+            double x[NR], inv, tau;
+            mbar_wait(bar_xf + 8u * xs, xpar);
+            {
+                const double *xi_ = Xs + xs * XN * 32;
+#pragma unroll
+                for (int s = 1; s < NR; ++s) x[s] = xi_[(s - 1) * 32];
+                inv = xi_[(NR - 1) * 32]; tau = xi_[NR * 32];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xe + 8u * xs);
+            if (++xs == NSX) { xs = 0; xpar ^= 1u; }
+            const double bval = bq0;
+            bq0 = bq1; bq1 = bq2; bq2 = bload((int64_t)k + LP + 3);
+#pragma unroll
+            for (int j = 0; j < NTM; ++j) {
+                Tr[j][LP] = isrhs[j] ? bval : 0.0;
+                double ev;
+                ABC_LPC_REFLECT(Tr[j], Tr[j], ev)
+                if (live && act[j]) frb[(C0 + jt0 + j) * FSTR] = ev;
+            }
+            frb += RSTR;
+        }
+        if (!live) return;
+#pragma unroll
+        for (int row = 0; row < W; ++row) {
+            const int slot = row < LP ? row : PW + (row - LP);
+#pragma unroll
+            for (int j = 0; j < NTM; ++j) {
+                const int jt = jt0 + j;
+                if (act[j]) E[row * (2 * W + 1) + (jt < W ? jt : 2 * W)] = Tr[j][slot];
+            }
+        }
+    }
+#undef ABC_LPC_REFLECT
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1021,6 +1408,8 @@ struct ssm_abc {
     ssm_ctx *ctx; ssm::CtxRef ref; int64_t n; int l, u, r, lp, w, nf, nc;
     DevBufPtr REC, V;                 // operands
     DevBufPtr FR, E, TOP, Z, tmp;     // workspace of the last solve (allocated on first use)
+    DevBufPtr RI, VI;                 // chunk-interleaved entering rows of the lane-per-chunk stage 1, valid for the operands and the layout below
+    int ri_P = 0, ri_m0 = 0, ri_jx = 0;
     int P = 0, m0 = 0, jx = 0;
     bool tiled = false;               // layout of FR in the last solve
     int64_t npf = 0;
@@ -1106,7 +1495,8 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     ssm_ctx *c = A->ctx;
     using D = AbcDims<LP, R>;
     constexpr int W = D::W, EW = 2 * W + 1, TW = 3 * W + 1;
-    AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P, A->m0, A->jx, LP + 1, A->npf};
+    AbcArgs a{A->REC->p, A->V->p, b, A->FR->p, A->E->p, A->Z->p, x, A->n, A->l, A->u, P, A->m0, A->jx, LP + 1, A->npf,
+              reinterpret_cast<int *>(A->Z->p + ((int64_t)P + 2) * W), nullptr, nullptr, 0};
     const unsigned gchunks = (unsigned)((P + 3) / 4);
     // lanes per chunk in stage 1: 8 (4 chunks per warp) or, for the wide active blocks, 4 (8 chunks per warp; option "abc_gs")
     auto stage1 = [&](auto gs_tag) -> int {
@@ -1123,7 +1513,30 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
         else SSM_TRY(launch(abc_qr_kernel<LP, R, GS, false>));
         return 0;
     };
-    if constexpr (abc_has_gs4(LP, R)) {
+    bool lpc_done = false;
+    if constexpr (LP == 8 && R == 2) {
+        if (A->tiled && c->abc_lpc) {                          // one lane per chunk over tiles of 32 equally long chunks
+            using LS = AbcLpcSmem<LP, R>;
+            const int64_t ntile = (P + 31) / 32;
+            const int nrow = A->m0 + (LP + 1) - LP;            // steps of a long chunk
+            if (!A->RI || A->ri_P != P || A->ri_m0 != A->m0 || A->ri_jx != A->jx) {      // (operand setters drop RI: see ssm_abc_set / _generate)
+                A->RI.reset(); A->VI.reset();
+                SSM_TRY(dev_alloc(c, (size_t)ntile * nrow * D::NF * 32, false, A->RI));
+                SSM_TRY(dev_alloc(c, (size_t)ntile * nrow * R * 32, false, A->VI));
+                abc_interleave_kernel<D::NF, R><<<dim3((unsigned)((nrow + 7) / 8), (unsigned)ntile), 256, 0, c->stream>>>(a, A->RI->p, A->VI->p, LP, nrow);
+                c->launches++;
+                A->ri_P = P; A->ri_m0 = A->m0; A->ri_jx = A->jx;
+            }
+            a.RI = A->RI->p; a.VI = A->VI->p; a.nrow_i = nrow;
+            auto kern = abc_qr_lpc_kernel<LP, R, true>;
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LS::TOTAL));
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            kern<<<(unsigned)ntile, 128, LS::TOTAL, c->stream>>>(a);
+            lpc_done = true;
+        }
+    }
+    if (lpc_done) {
+    } else if constexpr (abc_has_gs4(LP, R)) {
         if (abc_gs_of(c, LP, R) == 4) SSM_TRY(stage1(std::integral_constant<int, 4>{}));
         else SSM_TRY(stage1(std::integral_constant<int, 8>{}));
     } else {
@@ -1234,6 +1647,7 @@ int ssm_abc_generate(ssm_abc *A, uint64_t seed, int dist) {
     SSM_CHECK_ARG(A, "null argument");
     ssm_ctx *c = A->ctx;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+    A->RI.reset(); A->VI.reset();                             // the interleaved copy belongs to the old operands
     abc_generate_kernel<<<(unsigned)((A->n + ABC_PAD + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, A->n, A->l, A->u, A->r, seed, dist);
     c->launches++;
     cudaError_t e = cudaGetLastError();
@@ -1246,6 +1660,7 @@ int ssm_abc_set(ssm_abc *A, const double *bands, const double *U, const double *
     SSM_CHECK_ARG(A && bands && (A->r == 0 || (U && V)), "null argument");
     ssm_ctx *c = A->ctx;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
+    A->RI.reset(); A->VI.reset();                             // the interleaved copy belongs to the old operands
     Staged st;
     const int kb = st.add(bands, (size_t)(A->lp + 1) * A->n, true), ku = st.add(A->r ? U : nullptr, (size_t)A->n * A->r, true),
               kv = st.add(A->r ? V : nullptr, (size_t)A->n * A->r, true);
@@ -1291,7 +1706,7 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
         rc = dev_alloc(c, frcount, tiled, A->FR);   // tiled: spare lanes of the last tile are read, so they are defined
         if (!rc) rc = dev_alloc(c, (size_t)(2 * (int64_t)P + 64) * W * (2 * W + 1), true, A->E);
         if (!rc) rc = dev_alloc(c, (size_t)((int64_t)P + 64) * W * (3 * W + 1), true, A->TOP);
-        if (!rc) rc = dev_alloc(c, (size_t)((int64_t)P + 2) * W, true, A->Z);
+        if (!rc) rc = dev_alloc(c, (size_t)((int64_t)P + 2) * W + 256, true, A->Z);   // (+ 512 per-SM arrival counters of the lane-per-chunk stage 1)
         A->P = P;
     }
     A->m0 = m0; A->jx = jx; A->tiled = tiled; A->npf = npf;

@@ -254,6 +254,7 @@ int ssm_ctx_set_option(ssm_ctx *c, const char *key, int value) {
     else if (!strcmp(key, "group_smem_kb")) c->group_smem_kb = value;
     else if (!strcmp(key, "carveout_all")) c->carveout_all = value;
     else if (!strcmp(key, "abc_tiled_min_chunks")) c->abc_tiled_min_chunks = value;
+    else if (!strcmp(key, "abc_lpc")) c->abc_lpc = value;
     else if (!strcmp(key, "abc_gs")) { SSM_CHECK_ARG(value == 4 || value == 8, "abc_gs must be 4 or 8"); c->abc_gs = value; }
     else { set_error("unknown option '%s'", key); return SSM_E_ARG; }
     return 0;
@@ -267,6 +268,7 @@ int ssm_ctx_get_option(ssm_ctx *c, const char *key, int *value) {
     else if (!strcmp(key, "group_smem_kb")) *value = c->group_smem_kb;
     else if (!strcmp(key, "abc_tiled_min_chunks")) *value = c->abc_tiled_min_chunks;
     else if (!strcmp(key, "abc_gs")) *value = c->abc_gs;
+    else if (!strcmp(key, "abc_lpc")) *value = c->abc_lpc;
     else if (!strcmp(key, "sm_count")) *value = c->sm_count;
     else { set_error("unknown option '%s'", key); return SSM_E_ARG; }
     return 0;
