@@ -1479,7 +1479,9 @@ static int abc_default_chunks(const ssm_abc *A) {
     // shorter chunks win until the separator tree takes over: 128 rows per chunk, at most one wave (n = 10^6: 1,953 chunks 0.50 ms,
     // 7,104 0.40 ms; n = 65,536: 128 chunks 0.37 ms, 512 0.20 ms).
     // (4 lanes per chunk: 8 warps of 8 chunks per SM, waves of sm_count * 64; n = 2^24 gets 28,416 chunks either way)
-    const int per_sm = abc_gs_of(A->ctx, A->lp, A->r) == 4 ? 8 * 8 : 12 * ABC_CPW;
+    // (one lane per chunk, (l+u, r) = (8, 2): 3 CTAs of 32 chunks per SM, waves of sm_count * 96 — 28,416 chunks once more)
+    const bool lpc = A->lp == 8 && A->r == 2 && A->ctx->abc_lpc && A->n / 512 >= A->ctx->abc_tiled_min_chunks;
+    const int per_sm = lpc ? 3 * 32 : abc_gs_of(A->ctx, A->lp, A->r) == 4 ? 8 * 8 : 12 * ABC_CPW;
     const int64_t wave = (int64_t)(A->ctx->sm_count > 0 ? A->ctx->sm_count : 148) * per_sm;
     int64_t P = A->n / 512;
     if (P >= wave) P = std::min<int64_t>(P / wave, 4) * wave;

@@ -49,14 +49,17 @@ def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P, tiled
     rng = np.random.default_rng(n * 13 + P)
     bands, U, V, b = _rand(rng, n, l, u, r)
     A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
-    default, default_gs = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_gs")
+    default, default_gs, default_lpc = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_gs"), ctx.get_option("abc_lpc")
     ctx.set_option("abc_tiled_min_chunks", 1 if tiled else 1 << 30)
     ctx.set_option("abc_gs", gs)
+    # (l+u, r) = (8, 2) over tiled records: gs = 4 runs the one-lane-per-chunk stage 1 (the default for large systems), gs = 8 the lanes = columns one
+    ctx.set_option("abc_lpc", 1 if gs == 4 else 0)
     try:
         x = A.solve(b, nchunks=P)
     finally:
         ctx.set_option("abc_tiled_min_chunks", default)
         ctx.set_option("abc_gs", default_gs)
+        ctx.set_option("abc_lpc", default_lpc)
     lp, w = l + u, l + u + r
     P, bnd = regular_layout(n, lp, P, same=32 if tiled else 32 // gs_eff)
     assert A.chunks == P
@@ -151,16 +154,42 @@ def test_config4_full_size(chunked, ctx):
     assert np.linalg.norm(x2 - ox) / np.linalg.norm(ox) <= 1e-12
 
 
+def test_lpc_interleaved_copy_follows_the_operands(chunked, ctx):
+    """The one-lane-per-chunk stage 1 sweeps a chunk-interleaved copy of the operands that the library builds on the first solve and
+    keeps: new operands in the same (recycled) object, another chunk count, and the lanes = columns kernels must all give the
+    oracle's solution."""
+    import gc
+    n, l, u, r = 300_000, 4, 4, 2
+    default, default_lpc = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_lpc")
+    ctx.set_option("abc_tiled_min_chunks", 1)
+    try:
+        for seed in (11, 12):                                   # the second object recycles the first one's storage (context cache)
+            bands, U, V, b = oracle.ab_generate(n, l, u, r, 1, seed=seed, dist=1)
+            ox = oracle.ab_solve(bands, U, V, b, l, u)[0]
+            A = chunked.LargeAlmostBandedMatrix(bands[0], (U[0], V[0]), (l, u), ctx=ctx)
+            for lpc, nchunks in ((1, 2048), (1, 2048), (1, 640), (0, 2048)):
+                ctx.set_option("abc_lpc", lpc)
+                x = A.solve(b[0], nchunks=nchunks)
+                assert np.linalg.norm(x - ox) <= 1e-12 * np.linalg.norm(ox), (seed, lpc, nchunks)
+                assert A.residual(x, b[0]) <= 1e-13
+            del A
+            gc.collect()
+    finally:
+        ctx.set_option("abc_tiled_min_chunks", default)
+        ctx.set_option("abc_lpc", default_lpc)
+
+
 def test_random_shapes_and_chunk_counts_match_oracle(ctx):
     """Sweep of 40 drawn single systems over every compiled (l+u, r) of the chunked path, sizes from 1 row to a few thousand and chunk
     counts from 1 to n/8, both stage-3 variants: the solution against the oracle's sequential sweep and the structured residual."""
     from ssm_b200 import chunked
     shapes = [(1, 0), (2, 0), (4, 0), (1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (6, 2), (8, 2)]
     rng = np.random.default_rng(2028)
-    default, default_gs = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_gs")
+    default, default_gs, default_lpc = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_gs"), ctx.get_option("abc_lpc")
     try:
         for it in range(40):
             ctx.set_option("abc_gs", 4 if it % 2 == 0 else 8)      # lanes per chunk in stage 1 of the wide shapes
+            ctx.set_option("abc_lpc", 1 if it % 4 < 2 else 0)      # one lane per chunk for (8, 2) over tiled records
             lp, r = shapes[int(rng.integers(0, len(shapes)))]
             l = int(rng.integers(0, lp + 1)); u = lp - l
             n = int(rng.choice([1, 2, lp + 1, 2 * lp + 3, 100, 1000, 4097, 20000]))
@@ -178,3 +207,4 @@ def test_random_shapes_and_chunk_counts_match_oracle(ctx):
     finally:
         ctx.set_option("abc_tiled_min_chunks", default)
         ctx.set_option("abc_gs", default_gs)
+        ctx.set_option("abc_lpc", default_lpc)
