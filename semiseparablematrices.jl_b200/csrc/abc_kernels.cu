@@ -1410,6 +1410,7 @@ struct ssm_abc {
     DevBufPtr FR, E, TOP, Z, tmp;     // workspace of the last solve (allocated on first use)
     DevBufPtr RI, VI;                 // chunk-interleaved entering rows of the lane-per-chunk stage 1, valid for the operands and the layout below
     int ri_P = 0, ri_m0 = 0, ri_jx = 0;
+    int nsolve = 0;                   // solves since the operands were written
     int P = 0, m0 = 0, jx = 0;
     bool tiled = false;               // layout of FR in the last solve
     int64_t npf = 0;
@@ -1517,7 +1518,10 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     };
     bool lpc_done = false;
     if constexpr (LP == 8 && R == 2) {
-        if (A->tiled && c->abc_lpc) {                          // one lane per chunk over tiles of 32 equally long chunks
+        // one lane per chunk over tiles of 32 equally long chunks.  It sweeps an interleaved copy of the operands that costs a pass over
+        // them to build: operands that are solved against once (the Julia glue's `A \ b`) never pay for it — option abc_lpc = 1 switches
+        // over at the SECOND solve of the same operands, 2 at the first, 0 never
+        if (A->tiled && (c->abc_lpc >= 2 || (c->abc_lpc == 1 && (A->RI || A->nsolve >= 1)))) {
             using LS = AbcLpcSmem<LP, R>;
             const int64_t ntile = (P + 31) / 32;
             const int nrow = A->m0 + (LP + 1) - LP;            // steps of a long chunk
@@ -1649,7 +1653,7 @@ int ssm_abc_generate(ssm_abc *A, uint64_t seed, int dist) {
     SSM_CHECK_ARG(A, "null argument");
     ssm_ctx *c = A->ctx;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
-    A->RI.reset(); A->VI.reset();                             // the interleaved copy belongs to the old operands
+    A->RI.reset(); A->VI.reset(); A->nsolve = 0;              // the interleaved copy belongs to the old operands
     abc_generate_kernel<<<(unsigned)((A->n + ABC_PAD + 255) / 256), 256, 0, c->stream>>>(A->REC->p, A->V->p, A->n, A->l, A->u, A->r, seed, dist);
     c->launches++;
     cudaError_t e = cudaGetLastError();
@@ -1662,7 +1666,7 @@ int ssm_abc_set(ssm_abc *A, const double *bands, const double *U, const double *
     SSM_CHECK_ARG(A && bands && (A->r == 0 || (U && V)), "null argument");
     ssm_ctx *c = A->ctx;
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device);
-    A->RI.reset(); A->VI.reset();                             // the interleaved copy belongs to the old operands
+    A->RI.reset(); A->VI.reset(); A->nsolve = 0;              // the interleaved copy belongs to the old operands
     Staged st;
     const int kb = st.add(bands, (size_t)(A->lp + 1) * A->n, true), ku = st.add(A->r ? U : nullptr, (size_t)A->n * A->r, true),
               kv = st.add(A->r ? V : nullptr, (size_t)A->n * A->r, true);
@@ -1722,6 +1726,7 @@ int ssm_abc_solve(ssm_abc *A, const double *b, double *x, int nchunks) {
 #define X(LP_, R_) if (A->lp == LP_ && A->r == R_) rc = abc_solve_inst<LP_, R_>(A, db, dx, P);
         SSM_ABC_SHAPES(X)
 #undef X
+        if (!rc) A->nsolve++;
     }
     if (!rc && xhost) {
         cudaError_t e = cudaMemcpyAsync(x, dx, (size_t)A->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);

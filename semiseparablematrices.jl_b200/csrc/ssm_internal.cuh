@@ -87,7 +87,7 @@ struct ssm_ctx {
     int          pipeline_stages = 0;  // 0 = kernel default
     int          qt_stages = 0, bs_stages = 0;   // ring depth of K2 / K3 alone (0 = pick_stages)
     int          abc_tiled_min_chunks = 12288;  // chunked path (K10): from this many chunks on stage 3 runs one lane per chunk over tiled records
-    int          abc_lpc = 1;                   // chunked path, (l+u, r) = (8, 2) at many chunks: one lane per chunk in stage 1 (abc_qr_lpc_kernel)
+    int          abc_lpc = 1;                   // chunked path, (l+u, r) = (8, 2) at many chunks: one lane per chunk in stage 1 (abc_qr_lpc_kernel): 0 never, 1 from the second solve of the same operands on, 2 always
     int          abc_gs = 4;                    // chunked path: lanes that share one chunk in stage 1 of the wide shapes (4, or 8 as for all others)
     int          sm_count = 148;
     int64_t      launches = 0;

@@ -53,7 +53,7 @@ def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P, tiled
     ctx.set_option("abc_tiled_min_chunks", 1 if tiled else 1 << 30)
     ctx.set_option("abc_gs", gs)
     # (l+u, r) = (8, 2) over tiled records: gs = 4 runs the one-lane-per-chunk stage 1 (the default for large systems), gs = 8 the lanes = columns one
-    ctx.set_option("abc_lpc", 1 if gs == 4 else 0)
+    ctx.set_option("abc_lpc", 2 if gs == 4 else 0)
     try:
         x = A.solve(b, nchunks=P)
     finally:
@@ -167,7 +167,8 @@ def test_lpc_interleaved_copy_follows_the_operands(chunked, ctx):
             bands, U, V, b = oracle.ab_generate(n, l, u, r, 1, seed=seed, dist=1)
             ox = oracle.ab_solve(bands, U, V, b, l, u)[0]
             A = chunked.LargeAlmostBandedMatrix(bands[0], (U[0], V[0]), (l, u), ctx=ctx)
-            for lpc, nchunks in ((1, 2048), (1, 2048), (1, 640), (0, 2048)):
+            # abc_lpc: 1 = lanes = columns on the first solve of new operands, one lane per chunk from the second on; 2 = always; 0 = never
+            for lpc, nchunks in ((1, 2048), (1, 2048), (1, 2048), (2, 640), (0, 2048), (2, 2048)):
                 ctx.set_option("abc_lpc", lpc)
                 x = A.solve(b[0], nchunks=nchunks)
                 assert np.linalg.norm(x - ox) <= 1e-12 * np.linalg.norm(ox), (seed, lpc, nchunks)
@@ -189,7 +190,7 @@ def test_random_shapes_and_chunk_counts_match_oracle(ctx):
     try:
         for it in range(40):
             ctx.set_option("abc_gs", 4 if it % 2 == 0 else 8)      # lanes per chunk in stage 1 of the wide shapes
-            ctx.set_option("abc_lpc", 1 if it % 4 < 2 else 0)      # one lane per chunk for (8, 2) over tiled records
+            ctx.set_option("abc_lpc", 2 if it % 4 < 2 else 0)      # one lane per chunk for (8, 2) over tiled records
             lp, r = shapes[int(rng.integers(0, len(shapes)))]
             l = int(rng.integers(0, lp + 1)); u = lp - l
             n = int(rng.choice([1, 2, lp + 1, 2 * lp + 3, 100, 1000, 4097, 20000]))
