@@ -180,6 +180,36 @@ def test_lpc_interleaved_copy_follows_the_operands(chunked, ctx):
         ctx.set_option("abc_lpc", default_lpc)
 
 
+def test_lpc_drawn_systems_match_oracle(ctx):
+    """The one-lane-per-chunk stage 1 alone (abc_lpc = 2, tiled records forced): every split l + u = 8 at r = 2, sizes from a few rows per
+    chunk to tens of thousands of rows, chunk counts that leave partial tiles of 32 and both kinds of chunk length, both generators —
+    the solution against the oracle's sequential sweep and the structured residual; and against the lanes = columns kernels."""
+    from ssm_b200 import chunked
+    rng = np.random.default_rng(4242)
+    default, default_lpc = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_lpc")
+    ctx.set_option("abc_tiled_min_chunks", 1)
+    try:
+        for it in range(24):
+            l = int(rng.choice([0, 1, 3, 4, 5, 8])); u = 8 - l; r = 2
+            n = int(rng.choice([40, 333, 2000, 4097, 33000, 70001]))
+            dist = int(rng.integers(0, 2))
+            bands, U, V, b = oracle.ab_generate(n, l, u, r, 1, seed=7000 + it, dist=dist)
+            ox = oracle.ab_solve(bands[0], U[0], V[0], b[0], l, u)
+            A = chunked.LargeAlmostBandedMatrix(bands[0], (U[0], V[0]), (l, u), ctx=ctx)
+            for nchunks in sorted({1, 33, int(rng.integers(1, max(2, n // 27 + 1))), int(rng.integers(1, max(2, n // 200 + 1)))}):
+                ctx.set_option("abc_lpc", 2)
+                x = A.solve(b[0], nchunks=nchunks)
+                tag = (it, n, l, u, dist, nchunks, A.chunks)
+                assert np.linalg.norm(x - ox) <= 1e-12 * np.linalg.norm(ox), tag
+                assert A.residual(x, b[0]) <= 1e-13, tag
+                ctx.set_option("abc_lpc", 0)
+                x0 = A.solve(b[0], nchunks=nchunks)
+                assert np.linalg.norm(x - x0) <= 1e-13 * np.linalg.norm(ox), tag
+    finally:
+        ctx.set_option("abc_tiled_min_chunks", default)
+        ctx.set_option("abc_lpc", default_lpc)
+
+
 def test_random_shapes_and_chunk_counts_match_oracle(ctx):
     """Sweep of 40 drawn single systems over every compiled (l+u, r) of the chunked path, sizes from 1 row to a few thousand and chunk
     counts from 1 to n/8, both stage-3 variants: the solution against the oracle's sequential sweep and the structured residual."""
