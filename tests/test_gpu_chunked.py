@@ -152,6 +152,11 @@ def test_config4_full_size(chunked, ctx):
     # a different chunking gives the same solution to rounding
     x2 = A.solve(b, nchunks=1000).cpu().numpy()
     assert np.linalg.norm(x2 - ox) / np.linalg.norm(ox) <= 1e-12
+    # later solves of the same operands at the default chunking run stage 1 with one lane per chunk (the form bench.py times)
+    for _ in range(2):
+        x3 = A.solve(b)
+    assert A.residual(x3, b) <= 1e-13
+    assert np.linalg.norm(x3.cpu().numpy() - ox) / np.linalg.norm(ox) <= 1e-12
 
 
 def test_lpc_interleaved_copy_follows_the_operands(chunked, ctx):
