@@ -1480,13 +1480,17 @@ static int abc_default_chunks(const ssm_abc *A) {
     // shorter chunks win until the separator tree takes over: 128 rows per chunk, at most one wave (n = 10^6: 1,953 chunks 0.50 ms,
     // 7,104 0.40 ms; n = 65,536: 128 chunks 0.37 ms, 512 0.20 ms).
     // (4 lanes per chunk: 8 warps of 8 chunks per SM, waves of sm_count * 64; n = 2^24 gets 28,416 chunks either way)
-    // (one lane per chunk, (l+u, r) = (8, 2): 3 CTAs of 32 chunks per SM, waves of sm_count * 96 — 28,416 chunks once more)
-    const bool lpc = A->lp == 8 && A->r == 2 && A->ctx->abc_lpc && A->n / 512 >= A->ctx->abc_tiled_min_chunks;
+    // One lane per chunk ((l+u, r) = (8, 2)): 3 CTAs of 32 chunks per SM, waves of sm_count * 96 = 14,208 chunks — 28,416 at n = 2^24 once
+    // more.  It needs tiled records and wins from one full wave of >= 128-row chunks on (measured, n = 2 / 3 / 4 / 6 M: 0.47 / 0.59 / 0.71 /
+    // 0.95 ms with 14,208 chunks against 0.50 / 0.65 / 0.79 / 1.10 ms with the lanes = columns kernels at 9,472).
+    const int64_t sms = A->ctx->sm_count > 0 ? A->ctx->sm_count : 148;
+    const int64_t wave_lpc = sms * 3 * 32;
+    const bool lpc = A->lp == 8 && A->r == 2 && A->ctx->abc_lpc && A->n / 128 >= wave_lpc && wave_lpc >= A->ctx->abc_tiled_min_chunks;
     const int per_sm = lpc ? 3 * 32 : abc_gs_of(A->ctx, A->lp, A->r) == 4 ? 8 * 8 : 12 * ABC_CPW;
-    const int64_t wave = (int64_t)(A->ctx->sm_count > 0 ? A->ctx->sm_count : 148) * per_sm;
+    const int64_t wave = sms * per_sm;
     int64_t P = A->n / 512;
     if (P >= wave) P = std::min<int64_t>(P / wave, 4) * wave;
-    else P = std::min<int64_t>(A->n / 128, wave);
+    else P = lpc ? wave : std::min<int64_t>(A->n / 128, wave);
     const int64_t pmax = A->n / (2 * A->lp + 2 + 8);
     if (P > pmax) P = pmax;
     if (P < 1) P = 1;
