@@ -462,7 +462,8 @@ __global__ void __launch_bounds__(128, 3) abc_qr_lpc_kernel(const AbcArgs a) {
     constexpr int PW = D::PW, NR = D::NR, NC = D::NC, NF = D::NF, W = D::W, C0 = D::C0;
     constexpr int NP1 = SM::NP1, NP2 = PW - NP1 - 1, NCB = LP + R + 1, NT1 = SM::NT1, NT2 = NCB - NT1;
     constexpr int SBK = SM::SBK, NSTG = SM::NSTG, NSX = SM::NSX, NSC = SM::NSC, XF = SM::XF, XN = SM::XN, CN = SM::CN;
-    constexpr int FSTR = TILED ? 4 : 1, RSTR = TILED ? NC * 4 : NC;
+    static_assert(TILED, "the lane-per-chunk stage 1 writes records interleaved over its tile of 32 chunks");
+    constexpr int FSTR = 32, RSTR = NC * 32;                  // FR[tile][k][field][lane]: a field of one step is one coalesced 256-byte store
     extern __shared__ __align__(128) unsigned char smem[];
     // The four roles rotate over the CTA's warps with the order in which CTAs arrive on this SM (a counter per SM), so that the CTAs
     // resident together give every scheduler a mix of roles wherever the block scheduler puts them
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(128, 3) abc_qr_lpc_kernel(const AbcArgs a) {
     const double *b0 = a.b + r0;
     const int64_t brows = a.n - r0;
     const uint32_t bar_ring = smem_u32(smem + SM::BARS), bar_xf = bar_ring + NSTG * 8, bar_xe = bar_xf + NSX * 8, bar_cf = bar_xe + NSX * 8, bar_ce = bar_cf + NSC * 8;
-    double *frb = TILED ? a.FR + (int64_t)(c >> 2) * a.npf * NC * 4 + (c & 3) : a.FR + r0 * NC;
+    double *frb = a.FR + (int64_t)blockIdx.x * a.npf * NC * 32 + lane;
     double *E = a.E0 + (int64_t)c * W * (2 * W + 1);
     double *Xs = reinterpret_cast<double *>(smem + SM::OFF_X) + lane;           // Xs[(slot * XN + f) * 32]
     double *Cs = reinterpret_cast<double *>(smem + SM::OFF_C) + lane;           // Cs[(slot * CN + i) * 32], i = slot index without the entering row's
@@ -1134,9 +1135,11 @@ __global__ void __launch_bounds__(128) abc_bs_kernel(const AbcArgs a) {
 // The ring that feeds it: a stage holds ONE row of the warp's eight mini-tiles (8 x NC x 4 doubles); eight lanes issue one
 // bulk-async copy each (NC*32 bytes, contiguous in the mini-tile's stream) onto the stage's mbarrier.  Mini-tile blocks are
 // padded by 4 doubles in shared memory so that a half warp's 8-byte reads fall into distinct banks.
-template <int NC>
+template <int NC, bool W32 = false>
 struct MiniTileRing {
-    static constexpr int MT_STRIDE = NC * 4 + 4, STAGE_DOUBLES = 8 * MT_STRIDE;
+    // W32: records interleaved over the 32 chunks of the tile, FR[tile][k][field][32] (what the lane-per-chunk stage 1 writes: a field of
+    // one step is one coalesced 256-byte store for it, and one bulk copy per row here) instead of over mini-tiles of 4 chunks
+    static constexpr int MT_STRIDE = NC * 4 + 4, STAGE_DOUBLES = W32 ? NC * 32 : 8 * MT_STRIDE;
     static constexpr uint32_t ROW_BYTES = NC * 32;
     static __host__ __device__ size_t smem_bytes(int nstage) { return (size_t)nstage * STAGE_DOUBLES * 8 + (size_t)nstage * 8; }
     const double *src;            // lanes 0..7: row 0 of mini-tile `lane` of this tile
@@ -1145,13 +1148,20 @@ struct MiniTileRing {
     // step g reads row last - g
     __device__ __forceinline__ void issue(int64_t g, int s) {
         const uint32_t bar = bar0 + 8u * s;
+        if (W32) {
+            if (lane == 0) {
+                mbar_expect_tx(bar, 8 * ROW_BYTES);
+                bulk_g2s(smem_u32(ring + (size_t)s * STAGE_DOUBLES), src + (last - g) * NC * 32, 8 * ROW_BYTES, bar);
+            }
+            return;
+        }
         if (lane == 0) mbar_expect_tx(bar, 8 * ROW_BYTES);
         __syncwarp();
         if (lane < 8) bulk_g2s(smem_u32(ring + (size_t)s * STAGE_DOUBLES + lane * MT_STRIDE), src + (last - g) * NC * 4, ROW_BYTES, bar);
     }
     __device__ __forceinline__ void init(const double *fr, int64_t tile, int64_t npf, void *smem, int nst, int64_t total_steps) {
         lane = threadIdx.x & 31; nstage = nst; nsteps = total_steps; last = total_steps - 1;
-        src = fr + (tile * 8 + (lane & 7)) * npf * NC * 4;
+        src = W32 ? fr + tile * npf * NC * 32 : fr + (tile * 8 + (lane & 7)) * npf * NC * 4;
         ring = reinterpret_cast<double *>(smem);
         bar0 = smem_u32(reinterpret_cast<unsigned char *>(smem) + (size_t)nst * STAGE_DOUBLES * 8);
         if (lane == 0) {
@@ -1165,9 +1175,9 @@ struct MiniTileRing {
     __device__ __forceinline__ void acquire(int64_t g, double *rec) {
         const int s = cur;
         mbar_wait(bar0 + 8u * s, parity);
-        const double *p = ring + (size_t)s * STAGE_DOUBLES + (lane >> 2) * MT_STRIDE + (lane & 3);
+        const double *p = W32 ? ring + (size_t)s * STAGE_DOUBLES + lane : ring + (size_t)s * STAGE_DOUBLES + (lane >> 2) * MT_STRIDE + (lane & 3);
 #pragma unroll
-        for (int f = 0; f < NC; ++f) rec[f] = p[f * 4];
+        for (int f = 0; f < NC; ++f) rec[f] = p[f * (W32 ? 32 : 4)];
         __syncwarp();                 // every lane has its copy in registers before the stage is re-armed
         fence_proxy_async();          // ... and those reads are ordered before the re-arming bulk copies (see stream_loader.cuh)
         if (g + nstage < nsteps) issue(g + nstage, s);
@@ -1175,7 +1185,7 @@ struct MiniTileRing {
     }
 };
 
-template <int LP, int R>
+template <int LP, int R, bool W32>
 __global__ void __launch_bounds__(32) abc_bs_tiled_kernel(const AbcArgs a, const int nstage) {
     using D = AbcDims<LP, R>;
     constexpr int PW = D::PW, NC = D::NC, G0 = D::G0, C0 = D::C0, T0 = D::T0, B0 = D::B0, W = D::W;
@@ -1214,7 +1224,7 @@ __global__ void __launch_bounds__(32) abc_bs_tiled_kernel(const AbcArgs a, const
     double sb[RQ];
 #pragma unroll
     for (int q = 0; q < RQ; ++q) sb[q] = R > 0 ? zn[LP + q] : 0.0;
-    MiniTileRing<NC> ld;
+    MiniTileRing<NC, W32> ld;
     ld.init(a.FR, tile, a.npf, smem, nstage, nsteps);
     // vb[ph][:] = V row of local column kb+PW+ph, the column that leaves the band of row kb+ph (rows behind the system are zero)
     const double *vloc = a.V + (r0 + u) * RQ;
@@ -1589,18 +1599,24 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
     }
     if (A->tiled) {
         // ring depth: the shared memory an SM has, shared by the single-warp CTAs the grid puts on it (at most 16 stages)
-        using LD = MiniTileRing<D::NC>;
-        const int64_t ntiles = (P + 31) / 32;
-        int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
-        per_sm = std::min<int64_t>(std::max<int64_t>(per_sm, 1), 16);
-        int ns = (int)((size_t)(208 * 1024) / (size_t)per_sm / (LD::STAGE_DOUBLES * 8 + 8));
-        ns = std::min(std::max(ns, 2), 16);
-        if (c->pipeline_stages > 0) ns = c->pipeline_stages;
-        const size_t smem = LD::smem_bytes(ns);
-        auto kern = abc_bs_tiled_kernel<LP, R>;
-        if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        kern<<<(unsigned)ntiles, 32, smem, c->stream>>>(a, ns);
+        auto stage3 = [&](auto w32_tag) -> int {
+            constexpr bool W32 = decltype(w32_tag)::value;       // records interleaved over 32 chunks (written by the lane-per-chunk stage 1) or over 4
+            using LD = MiniTileRing<D::NC, W32>;
+            const int64_t ntiles = (P + 31) / 32;
+            int64_t per_sm = (ntiles + c->sm_count - 1) / (c->sm_count > 0 ? c->sm_count : 148);
+            per_sm = std::min<int64_t>(std::max<int64_t>(per_sm, 1), 16);
+            int ns = (int)((size_t)(208 * 1024) / (size_t)per_sm / (LD::STAGE_DOUBLES * 8 + 8));
+            ns = std::min(std::max(ns, 2), 16);
+            if (c->pipeline_stages > 0) ns = c->pipeline_stages;
+            const size_t smem = LD::smem_bytes(ns);
+            auto kern = abc_bs_tiled_kernel<LP, R, W32>;
+            if (smem > 48 * 1024) SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            kern<<<(unsigned)ntiles, 32, smem, c->stream>>>(a, ns);
+            return 0;
+        };
+        if (lpc_done) SSM_TRY(stage3(std::true_type{}));
+        else SSM_TRY(stage3(std::false_type{}));
     } else {
         abc_bs_kernel<LP, R><<<gchunks, 128, 0, c->stream>>>(a);
     }
