@@ -720,65 +720,66 @@ __global__ void __launch_bounds__(128, 3) abc_qr_lpc_kernel(const AbcArgs a) {
         }
     } else {
         // ===== T1 / T2: trailing columns jt (separator jt < LP, tail LP <= jt < LP + R, rhs jt = LP + R) =====
-        const int jt0 = role == 2 ? 0 : NT1;
-        constexpr int NTM = NT1 > NT2 ? NT1 : NT2;
-        double Tr[NTM][NR];
-        bool isrhs[NTM], act[NTM];
+        // (one body per warp, with its column range as compile-time constants: a run-time column count would either cost T2 a reflector
+        // of zeros per step or put a branch into the column loop, and the branch costs the overlap of the reflectors — measured)
+        auto trailing = [&](auto jt0_tag, auto cnt_tag) {
+            constexpr int JT0 = decltype(jt0_tag)::value, NTC = decltype(cnt_tag)::value;
+            constexpr bool HASRHS = JT0 + NTC == NCB;
+            double Tr[NTC][NR];
 #pragma unroll
-        for (int j = 0; j < NTM; ++j) {
-            const int jt = jt0 + j;
-            act[j] = j < (role == 2 ? NT1 : NT2);
-            isrhs[j] = act[j] && jt == LP + R;
+            for (int j = 0; j < NTC; ++j) {
+                const int jt = JT0 + j;
 #pragma unroll
-            for (int s = 0; s < NR; ++s) {
-                double val = 0.0;
-                if (act[j]) {
+                for (int s = 0; s < NR; ++s) {
+                    double val = 0.0;
                     if (s < LP) {
                         if (jt < LP) { if (s <= jt) val = rec0[(int64_t)s * NF + (jt - s)]; }
                         else if (jt == LP + R) { if (s < brows) val = b0[s]; }
                     } else if (s >= PW) {
                         if (jt >= LP && jt < LP + R && jt - LP == s - PW) val = 1.0;
                     }
+                    Tr[j][s] = val;
                 }
-                Tr[j][s] = val;
             }
-        }
-        auto bload = [&](const int64_t i) -> double { return (role == 3 && i < brows) ? b0[i] : 0.0; };
-        double bq0 = bload(LP), bq1 = bload(LP + 1), bq2 = bload(LP + 2);
-        int xs = 0; uint32_t xpar = 0;
-        for (int k = 0; k < nsteps; ++k) {
-            double x[NR], inv, tau;
-            mbar_wait(bar_xf + 8u * xs, xpar);
-            {
-                const double *xi_ = Xs + xs * XN * 32;
+            auto bload = [&](const int64_t i) -> double { return (HASRHS && i < brows) ? b0[i] : 0.0; };
+            double bq0 = bload(LP), bq1 = bload(LP + 1), bq2 = bload(LP + 2);
+            int xs = 0; uint32_t xpar = 0;
+            for (int k = 0; k < nsteps; ++k) {
+                double x[NR], inv, tau;
+                mbar_wait(bar_xf + 8u * xs, xpar);
+                {
+                    const double *xi_ = Xs + xs * XN * 32;
 #pragma unroll
-                for (int s = 1; s < NR; ++s) x[s] = xi_[(s - 1) * 32];
-                inv = xi_[(NR - 1) * 32]; tau = xi_[NR * 32];
+                    for (int s = 1; s < NR; ++s) x[s] = xi_[(s - 1) * 32];
+                    inv = xi_[(NR - 1) * 32]; tau = xi_[NR * 32];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_xe + 8u * xs);
+                if (++xs == NSX) { xs = 0; xpar ^= 1u; }
+                const double bval = bq0;
+                bq0 = bq1; bq1 = bq2; bq2 = bload((int64_t)k + LP + 3);
+#pragma unroll
+                for (int j = 0; j < NTC; ++j) {
+                    Tr[j][LP] = (JT0 + j == LP + R) ? bval : 0.0;
+                    double ev;
+                    ABC_LPC_REFLECT(Tr[j], Tr[j], ev)
+                    if (live) frb[(C0 + JT0 + j) * FSTR] = ev;
+                }
+                frb += RSTR;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_xe + 8u * xs);
-            if (++xs == NSX) { xs = 0; xpar ^= 1u; }
-            const double bval = bq0;
-            bq0 = bq1; bq1 = bq2; bq2 = bload((int64_t)k + LP + 3);
+            if (!live) return;
 #pragma unroll
-            for (int j = 0; j < NTM; ++j) {
-                Tr[j][LP] = isrhs[j] ? bval : 0.0;
-                double ev;
-                ABC_LPC_REFLECT(Tr[j], Tr[j], ev)
-                if (live && act[j]) frb[(C0 + jt0 + j) * FSTR] = ev;
+            for (int row = 0; row < W; ++row) {
+                const int slot = row < LP ? row : PW + (row - LP);
+#pragma unroll
+                for (int j = 0; j < NTC; ++j) {
+                    const int jt = JT0 + j;
+                    E[row * (2 * W + 1) + (jt < W ? jt : 2 * W)] = Tr[j][slot];
+                }
             }
-            frb += RSTR;
-        }
-        if (!live) return;
-#pragma unroll
-        for (int row = 0; row < W; ++row) {
-            const int slot = row < LP ? row : PW + (row - LP);
-#pragma unroll
-            for (int j = 0; j < NTM; ++j) {
-                const int jt = jt0 + j;
-                if (act[j]) E[row * (2 * W + 1) + (jt < W ? jt : 2 * W)] = Tr[j][slot];
-            }
-        }
+        };
+        if (role == 2) trailing(std::integral_constant<int, 0>{}, std::integral_constant<int, NT1>{});
+        else trailing(std::integral_constant<int, NT1>{}, std::integral_constant<int, NT2>{});
     }
 #undef ABC_LPC_REFLECT
 }
