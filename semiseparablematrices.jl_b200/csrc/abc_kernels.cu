@@ -8,6 +8,10 @@
 //                        coefficients | rhs), reflectors are broadcast with shuffles; rows and window columns rotate through fixed
 //                        slots/lanes so nothing moves when the window slides.  The entering operand rows and V rows arrive through
 //                        a per-warp bulk-async ring (TMA 1-D copies), so the sweep's only global load is the rhs value.
+//                        Large systems of the wide shape (l+u, r) = (8, 2): abc_qr_lpc, ONE LANE per chunk — four warps per 32 chunks
+//                        share a chunk's 22 columns (reflector | rest of the panel | trailing columns x 2), coupled by shared-memory
+//                        rings, no shuffles, a rolled step loop; entering rows from a chunk-interleaved copy of the operands
+//                        (abc_interleave), records interleaved over the tile of 32 chunks.  Wide shapes otherwise: 4 lanes per chunk.
 //   stage 2  abc_merge   cyclic reduction of the block-bidiagonal separator system F_c z_c + G_c z_{c+1} = h_c by QR of
 //                        [G_a; F_b], one warp per merge, log2(P) launches; abc_root solves the last block; abc_expand
 //                        recovers the eliminated separators top-down.
