@@ -8,7 +8,7 @@
 //                        coefficients | rhs), reflectors are broadcast with shuffles; rows and window columns rotate through fixed
 //                        slots/lanes so nothing moves when the window slides.  The entering operand rows and V rows arrive through
 //                        a per-warp bulk-async ring (TMA 1-D copies), so the sweep's only global load is the rhs value.
-//                        Large systems of the wide shape (l+u, r) = (8, 2): abc_qr_lpc, ONE LANE per chunk — four warps per 32 chunks
+//                        Large systems of the shapes (l+u, r) = (8 | 6 | 4, 2): abc_qr_lpc, ONE LANE per chunk — four warps per 32 chunks
 //                        share a chunk's 22 columns (reflector | rest of the panel | trailing columns x 2), coupled by shared-memory
 //                        rings, no shuffles, a rolled step loop; entering rows from a chunk-interleaved copy of the operands
 //                        (abc_interleave), records interleaved over the tile of 32 chunks.  Wide shapes otherwise: 4 lanes per chunk.
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) abc_interleave_kernel(const AbcArgs a, do
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// stage 1, one LANE per chunk (the wide shape (l+u, r) = (8, 2) at many chunks).  A CTA is FOUR warps sweeping the same 32 chunks,
+// stage 1, one LANE per chunk (shapes (l+u, r) = (8 | 6 | 4, 2) at many chunks).  A CTA is FOUR warps sweeping the same 32 chunks,
 // lane = chunk in every warp, so there is no pivot broadcast, no redundant reflector arithmetic and no shuffle at all; the 22
 // columns of a chunk's active block are spread over the four warps' registers:
 //   P1  window positions 0..NP1-1   forms the reflector of every step (the pivot column is always position 0) and publishes
@@ -443,9 +443,9 @@ __global__ void __launch_bounds__(256) abc_interleave_kernel(const AbcArgs a, do
 template <int LP, int R>
 struct AbcLpcSmem {
     using D = AbcDims<LP, R>;
-    static constexpr int NP1 = 5;                                   // window positions 0..NP1-1 live in P1; position NP1 arrives every step
+    static constexpr int NP1 = (D::PW + 1) / 2;                     // window positions 0..NP1-1 live in P1 (5 of 9 at l+u = 8); position NP1 arrives every step
     static constexpr int NT1 = (LP + R + 1 + 1) / 2;                // trailing columns of T1 (the rest, with the rhs, in T2)
-    static constexpr int SBK = 3;                                   // steps per stage of the entering-row ring
+    static constexpr int SBK = D::PW % 3 == 0 ? 3 : D::PW;          // steps per stage of the entering-row ring (a divisor of the chunks' step counts)
     static_assert(D::PW % SBK == 0 && NP1 + 1 < D::PW, "ring stage / column split");
     static constexpr int NSTG = 2, NSX = 4, NSC = 2;
     static constexpr int CBR = SBK * D::NF * 256, CBV = SBK * R * 256;           // a stage: SBK rows of the tile-interleaved operand / V rows
@@ -1484,6 +1484,8 @@ static void abc_layout(int64_t n, int lp, int same, int &P, int &m0, int &jx) {
     if (jx > P) jx = P;
 }
 
+// shapes with a lane-per-chunk instance of stage 1
+constexpr bool abc_has_lpc(int lp, int r) { return r == 2 && (lp == 8 || lp == 6 || lp == 4); }
 // shapes with a 4-lanes-per-chunk instance of stage 1 (the wide active blocks), and the group size a context asks for
 constexpr bool abc_has_gs4(int lp, int r) { return 2 * lp + 2 * r + 2 >= 18; }
 static int abc_gs_of(const ssm_ctx *c, int lp, int r) { return abc_has_gs4(lp, r) && c->abc_gs == 4 ? 4 : 8; }
@@ -1499,9 +1501,9 @@ static int abc_default_chunks(const ssm_abc *A) {
     // more.  It needs tiled records and wins from one full wave of >= 128-row chunks on (measured, n = 2 / 3 / 4 / 6 M: 0.47 / 0.59 / 0.71 /
     // 0.95 ms with 14,208 chunks against 0.50 / 0.65 / 0.79 / 1.10 ms with the lanes = columns kernels at 9,472).
     const int64_t sms = A->ctx->sm_count > 0 ? A->ctx->sm_count : 148;
-    const int64_t wave_lpc = sms * 3 * 32;
-    const bool lpc = A->lp == 8 && A->r == 2 && A->ctx->abc_lpc && A->n / 128 >= wave_lpc && wave_lpc >= A->ctx->abc_tiled_min_chunks;
-    const int per_sm = lpc ? 3 * 32 : abc_gs_of(A->ctx, A->lp, A->r) == 4 ? 8 * 8 : 12 * ABC_CPW;
+    const int64_t wave_lpc = sms * (A->lp == 4 ? 5 : 3) * 32;      // CTAs per SM: 168 / 138 registers at l+u = 8 / 6, 96 at l+u = 4
+    const bool lpc = abc_has_lpc(A->lp, A->r) && A->ctx->abc_lpc && A->n / 128 >= wave_lpc && wave_lpc >= A->ctx->abc_tiled_min_chunks;
+    const int per_sm = lpc ? (int)(wave_lpc / sms) : abc_gs_of(A->ctx, A->lp, A->r) == 4 ? 8 * 8 : 12 * ABC_CPW;
     const int64_t wave = sms * per_sm;
     int64_t P = A->n / 512;
     if (lpc) P = std::min<int64_t>(std::max<int64_t>(A->n / 1024 / wave, 1), 2) * wave;   // ~1,024 rows per chunk, one or two waves (measured:
@@ -1539,7 +1541,7 @@ static int abc_solve_inst(ssm_abc *A, const double *b, double *x, int P) {
         return 0;
     };
     bool lpc_done = false;
-    if constexpr (LP == 8 && R == 2) {
+    if constexpr (abc_has_lpc(LP, R)) {
         // one lane per chunk over tiles of 32 equally long chunks.  It sweeps an interleaved copy of the operands that costs a pass over
         // them to build: operands that are solved against once (the Julia glue's `A \ b`) never pay for it — option abc_lpc = 1 switches
         // over at the SECOND solve of the same operands, 2 at the first, 0 never

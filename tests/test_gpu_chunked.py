@@ -38,7 +38,7 @@ def _rand(rng, n, l, u, r):
                                        (200, 3, 1, 2, 8), (500, 2, 2, 2, 16), (777, 4, 4, 2, 7), (130, 1, 1, 2, 5), (64, 2, 1, 1, 3),
                                        (300, 2, 2, 0, 6), (90, 1, 0, 0, 3), (128, 1, 1, 0, 4)])
 @pytest.mark.parametrize("tiled", [False, True])
-@pytest.mark.parametrize("gs", [8, 4])
+@pytest.mark.parametrize("gs", [8, 4, 1])
 def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P, tiled, gs):
     """`tiled`: stage 3 with one lane per chunk over tile-interleaved records (the path large systems take) forced onto the
     small case; otherwise one warp per chunk over row-major records.  `gs`: lanes that share a chunk in stage 1 (the wide
@@ -46,14 +46,16 @@ def test_chunked_small_vs_dense_and_stagewise(chunked, ctx, n, l, u, r, P, tiled
     gs_eff = 4 if gs == 4 and 2 * (l + u) + 2 * r + 2 >= 18 else 8
     if gs == 4 and gs_eff == 8:
         pytest.skip("shape has no 4-lane instance")
+    if gs == 1 and not (tiled and r == 2 and l + u in (4, 6, 8)):
+        pytest.skip("one lane per chunk: shapes (l+u, r) = (4 | 6 | 8, 2) over tiled records")
     rng = np.random.default_rng(n * 13 + P)
     bands, U, V, b = _rand(rng, n, l, u, r)
     A = chunked.LargeAlmostBandedMatrix(bands, (U, V), (l, u), ctx=ctx)
     default, default_gs, default_lpc = ctx.get_option("abc_tiled_min_chunks"), ctx.get_option("abc_gs"), ctx.get_option("abc_lpc")
     ctx.set_option("abc_tiled_min_chunks", 1 if tiled else 1 << 30)
-    ctx.set_option("abc_gs", gs)
-    # (l+u, r) = (8, 2) over tiled records: gs = 4 runs the one-lane-per-chunk stage 1 (the default for large systems), gs = 8 the lanes = columns one
-    ctx.set_option("abc_lpc", 2 if gs == 4 else 0)
+    # gs = 1: the one-lane-per-chunk stage 1 (what large systems of these shapes run from their second solve on); 4 | 8: lanes = columns
+    ctx.set_option("abc_lpc", 2 if gs == 1 else 0)
+    ctx.set_option("abc_gs", 8 if gs == 1 else gs)
     try:
         x = A.solve(b, nchunks=P)
     finally:
@@ -186,7 +188,7 @@ def test_lpc_interleaved_copy_follows_the_operands(chunked, ctx):
 
 
 def test_lpc_drawn_systems_match_oracle(ctx):
-    """The one-lane-per-chunk stage 1 alone (abc_lpc = 2, tiled records forced): every split l + u = 8 at r = 2, sizes from a few rows per
+    """The one-lane-per-chunk stage 1 alone (abc_lpc = 2, tiled records forced): splits of l + u = 8, 6 and 4 at r = 2, sizes from a few rows per
     chunk to tens of thousands of rows, chunk counts that leave partial tiles of 32 and both kinds of chunk length, both generators —
     the solution against the oracle's sequential sweep and the structured residual; and against the lanes = columns kernels."""
     from ssm_b200 import chunked
@@ -195,7 +197,7 @@ def test_lpc_drawn_systems_match_oracle(ctx):
     ctx.set_option("abc_tiled_min_chunks", 1)
     try:
         for it in range(24):
-            l = int(rng.choice([0, 1, 3, 4, 5, 8])); u = 8 - l; r = 2
+            lp = int(rng.choice([8, 8, 6, 4])); l = int(rng.integers(0, lp + 1)); u = lp - l; r = 2
             n = int(rng.choice([40, 333, 2000, 4097, 33000, 70001]))
             dist = int(rng.integers(0, 2))
             bands, U, V, b = oracle.ab_generate(n, l, u, r, 1, seed=7000 + it, dist=dist)
