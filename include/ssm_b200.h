@@ -66,7 +66,10 @@ int  ssm_ctx_sync(ssm_ctx *ctx);
 /* tuning knobs (kernel variant selection for A/B measurements): key in {"ab_variant" (0 auto, 1 direct loads, 2 per-step
    bulk-async ring, 4 grouped ring with a producer warp, 9 generic shapes), "pipeline_stages", "group_bytes",
    "group_max_per_sm" (auto: batches of at most this many 32-system tiles per SM use variant 4), "group_smem_kb" (shared memory a
-   variant-4 CTA may take; lower it, e.g. 96, when several contexts work on one GPU at the same time)} */
+   variant-4 CTA may take; lower it, e.g. 96, when several contexts work on one GPU at the same time), and for the single-system
+   chunked path: "abc_tiled_min_chunks" (chunk count from which the R records are tiled, default 12288), "abc_gs" (lanes per chunk of the
+   lanes = columns stage 1 of the wide shapes, 4 | 8), "abc_lpc" (one-lane-per-chunk stage 1 of the shapes l+u = 8 | 6 | 4, r = 2:
+   0 never, 1 from the second solve of the same operands on — it builds an interleaved copy of them —, 2 from the first)} */
 int  ssm_ctx_set_option(ssm_ctx *ctx, const char *key, int value);
 int  ssm_ctx_get_option(ssm_ctx *ctx, const char *key, int *value);
 /* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */
